@@ -1,0 +1,28 @@
+# Top-level build: libfxg.so (CUDA, sm_100a only), the drop-in host tools (C) and the test oracle.
+NVCC     ?= /usr/local/cuda/bin/nvcc
+CC       ?= gcc
+ARCH     := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS  := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Iinclude -Ifastx_toolkit_b200/csrc
+CSRC     := fastx_toolkit_b200/csrc
+LIB      := fastx_toolkit_b200/libfxg.so
+CU       := $(CSRC)/fxg_kernels.cu $(CSRC)/fxg_api.cu
+HDR      := include/fxg.h include/fxg_synth.h $(CSRC)/fxg_device.cuh $(CSRC)/fxg_kernels.cuh
+
+.PHONY: all lib tools oracle clean ptxas
+all: lib tools oracle
+
+lib: $(LIB)
+$(LIB): $(CU) $(HDR)
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(CU)
+
+ptxas: $(CU) $(HDR)
+	$(NVCC) $(NVFLAGS) -Xptxas -v -c $(CSRC)/fxg_kernels.cu -o /dev/null
+
+tools: lib
+	@if [ -f $(CSRC)/host/Makefile ]; then $(MAKE) --no-print-directory -C $(CSRC)/host; fi
+
+oracle:
+	$(MAKE) --no-print-directory -C oracle all
+
+clean:
+	rm -f $(LIB); rm -rf bin; $(MAKE) -C oracle clean

@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark: Mreads/s of the fastq_quality_trimmer hot path on 150 bp reads.
+
+  python bench.py --gpus N --steps K --warmup W            (torchrun launches N>1, one rank per GPU)
+  python bench.py --impl reference ...                      (the reference CPU tool on the host cores)
+
+A "step" is one pass of the trimmer loop body (`-t 20 -l 20 -Q33`, validation fused) over one batch of
+synthetic reads that is already resident in HBM as SoA slabs (`value`, kernel K-TRIM), and — for
+`e2e` — the same call through the C-ABI host entry point fxg_trim_host() with PINNED HOST slabs, the
+H2D copy of the inputs and the D2H copy of the per-read result inside the timed region.
+Reads shard contiguously across ranks; the trimmer has no exchange step, so there is no collective on
+the data path ("scaling": "weak": every rank owns --reads reads).
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mreads/sec fastq_quality_trimmer 150bp"
+UNIT = "Mreads/s"
+L, STRIDE, Q, T, MINLEN = 150, 160, 33, 20, 20
+ALGO_BYTES_PER_READ = 2 * L + 4          # validate seq + scan qual + 4 B result
+SEED = 20260925 + 1
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (of fallback; MEASURED_PEAKS.json absent)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        exe = shutil.which("nvidia-smi")
+        if not exe:
+            return
+        try:
+            self.proc = subprocess.Popen([exe, "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line)
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8 or f[0] != str(self.gpu):
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[4 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def ref_tool(name):
+    p = os.path.join(ROOT, "oracle", "_ref", name)
+    return p if os.path.exists(p) else None
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def make_sample_fastq(path, reads):
+    exe = os.path.join(ROOT, "bin", "fxg_synth")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", ROOT, "tools"], stdout=subprocess.DEVNULL)
+    subprocess.check_call([exe, "-n", str(reads), "-l", str(L), "-s", str(SEED), "-k", "plain", "-o", path])
+
+
+def time_reference_cpu(sample_reads, procs, steps, warmup):
+    """Run the UNMODIFIED reference fastq_quality_trimmer (oracle/_ref, gcc -O3) file -> file on
+    `procs` host cores at once (the reference has no threads: one process per core, same input).
+    Falls back to the oracle port when the reference binary is unavailable."""
+    tool = ref_tool("fastq_quality_trimmer")
+    tmp = tempfile.mkdtemp(prefix="fxg_bench_")
+    try:
+        if tool:
+            fq = os.path.join(tmp, "sample.fq")
+            make_sample_fastq(fq, sample_reads)
+            def one_step():
+                t0 = time.perf_counter()
+                ps = [subprocess.Popen([tool, "-Q", str(Q), "-t", str(T), "-l", str(MINLEN), "-i", fq,
+                                        "-o", os.path.join(tmp, "out%d.fq" % k)]) for k in range(procs)]
+                rcs = [p.wait() for p in ps]
+                dt = time.perf_counter() - t0
+                if any(rcs):
+                    raise RuntimeError("reference tool failed: %r" % rcs)
+                return dt
+            kind = "reference"
+        else:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import helpers as H   # oracle port: checker/baseline only
+            seq, qual = H.synth_slab(SEED, sample_reads, L)
+            procs = 1
+            def one_step():
+                t0 = time.perf_counter()
+                H.o_trim(seq, qual, None, L, STRIDE, Q, T, MINLEN)
+                return time.perf_counter() - t0
+            kind = "port"
+        for _ in range(warmup):
+            one_step()
+        times = [one_step() for _ in range(steps)]
+        total = sum(times)
+        mreads = sample_reads * procs * steps / total / 1e6
+        return mreads, kind, procs, total / steps
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    procs = host_threads()
+    sample = args.ref_sample
+    val, kind, procs, sec = time_reference_cpu(sample, procs, args.steps, args.warmup)
+    what = ("%d x fastq_quality_trimmer -t 20 -l 20 -Q33 (reference 0.0.14, gcc -O3) on the same %d x %d bp synthetic FASTQ, "
+            "file->file, one process per host core" % (procs, sample, L)) if kind == "reference" else \
+           ("oracle port fxo_trim_batch on %d x %d bp slabs, 1 thread (reference binary unavailable)" % (sample, L))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "fastq_quality_trimmer -t 20 -l 20 -Q33, %d bp synthetic reads" % L, "read_len": L,
+                   "sample_reads_per_process": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": procs, "kind": kind, "sample": what},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--reads", type=int, default=100_000_000, help="reads per GPU (HBM-resident batch)")
+    ap.add_argument("--e2e-reads", type=int, default=8_000_000, help="reads per GPU per e2e step (pinned host slabs)")
+    ap.add_argument("--cpu-sample", type=int, default=3_000_000, help="reads in the single-core CPU baseline sample")
+    ap.add_argument("--ref-sample", type=int, default=500_000, help="reads per process per step for --impl reference")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import fastx_toolkit_b200 as F
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    ctx = F.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    n = args.reads
+    free = torch.cuda.mem_get_info()[0]
+    need = n * (2 * STRIDE + 4)
+    if need > free * 0.9:
+        n = int(free * 0.9 / (2 * STRIDE + 4)) // 4096 * 4096
+    dseq = torch.empty((n, STRIDE), dtype=torch.uint8, device="cuda")
+    dqual = torch.empty((n, STRIDE), dtype=torch.uint8, device="cuda")
+    out = torch.empty(n, dtype=torch.int32, device="cuda")
+    ctx.synth_dev(dseq, dqual, n, L, STRIDE, SEED, 0, Q, first_read=rank * n, n_total=world * n)
+    batch = ctx.batch(dseq, dqual, n, STRIDE, L)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- HBM-resident: K-TRIM ----------------
+    for _ in range(max(args.warmup, 3)):
+        ctx.trim_dev(batch, Q, T, MINLEN, out, rank * n)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # keep the timed region long enough for the clock sampler to see it (>= ~1.5 s) without changing K's meaning
+    reps = 1
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        ctx.trim_dev(batch, Q, T, MINLEN, out, rank * n)
+    e1.record(stream)
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = ctx.launches() - launches0
+    rep = ctx.sync()
+    if rep.first_bad_read != -1:
+        raise SystemExit("bench.py: synthetic input flagged invalid at read %d" % rep.first_bad_read)
+    kept = int((out >= 0).sum().item())
+    ms_per_step = ms_total / args.steps
+    value = world * n / (ms_per_step * 1e-3) / 1e6
+    kernel_ms = ms_per_step / reps
+    peak, peak_src = measured_hbm_peak()
+    achieved = n * ALGO_BYTES_PER_READ / (kernel_ms * 1e-3) / 1e9
+
+    # keep the GPU busy a little longer under the sampler if the timed region was very short
+    t_busy = time.perf_counter()
+    while time.perf_counter() - t_busy < 1.0:
+        for _ in range(5):
+            ctx.trim_dev(batch, Q, T, MINLEN, out, rank * n)
+        torch.cuda.synchronize()
+    clocks = sampler.stop()
+
+    # ---------------- end to end through the host C-ABI ----------------
+    ne = min(args.e2e_reads, n)
+    hseq = torch.empty((ne, STRIDE), dtype=torch.uint8).pin_memory()
+    hqual = torch.empty((ne, STRIDE), dtype=torch.uint8).pin_memory()
+    hout = torch.empty(ne, dtype=torch.int32).pin_memory()
+    hseq.copy_(dseq[:ne]); hqual.copy_(dqual[:ne])
+    torch.cuda.synchronize()
+    hb = ctx.batch(hseq, hqual, ne, STRIDE, L)
+    for _ in range(max(args.warmup, 3)):
+        ctx.trim_host(hb, Q, T, MINLEN, hout)
+    barrier()
+    launches_e0 = ctx.launches()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = ctx.trim_host(hb, Q, T, MINLEN, hout)
+    torch.cuda.synchronize()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    launches_e2e = ctx.launches() - launches_e0
+    assert bool((hout == out[:ne].cpu()).all()), "e2e result differs from the HBM-resident result"
+    e2e_value = world * ne * args.steps / dt / 1e6
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {
+            "workload": "fastq_quality_trimmer -t 20 -l 20 -Q33 (+ fused record validation) on %d x %d bp synthetic reads per GPU, "
+                        "HBM-resident SoA slabs (stride %d)" % (n, L, STRIDE),
+            "reads_per_gpu": n, "read_len": L, "stride": STRIDE, "kept_reads_rank0": kept,
+            "cache": "inputs are %.1f GB per GPU, far larger than the 126 MB L2: no flush needed" % (2 * n * STRIDE / 1e9),
+            "sharding": "contiguous read blocks per rank, no data-path collective",
+            "timing": "CUDA events on the launch stream, barrier+synchronize both sides, max over ranks",
+        },
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "fxg::k_scan<G=2,TRIM,HAS_SEQ>", "algorithmic_bytes_per_read": ALGO_BYTES_PER_READ,
+                     "kernel_ms": kernel_ms, "peak_source": peak_src},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * ne * 2 * STRIDE, "d2h_bytes_per_step": world * ne * 4,
+                "reads_per_step_per_gpu": ne, "api": "fxg_trim_host (pinned host slabs -> H2D -> K-TRIM -> D2H int32 per read)",
+                "timing": "host wall clock around the blocking C-ABI calls, synchronize both sides, max over ranks",
+                "gpu_launches": launches_e2e},
+        "gpu_launches": launches,
+        "clocks": clocks,
+    }
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        val, kind, procs, sec = time_reference_cpu(args.cpu_sample, 1, 1, 0)
+        line["cpu_baseline"] = {
+            "value": val, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": ("reference fastq_quality_trimmer 0.0.14 (gcc -O3), -t 20 -l 20 -Q33, %d x %d bp synthetic FASTQ file -> file, "
+                       "1 process, %.1f s" % (args.cpu_sample, L, sec)) if kind == "reference" else
+                      ("oracle port on %d x %d bp slabs, 1 thread, %.1f s" % (args.cpu_sample, L, sec)),
+            "host_threads_available": host_threads(),
+        }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,176 @@
+"""ctypes binding of include/fxg.h (one function per C entry point, same names and argument order)."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+FXG_OK = 0
+QBINS = 109
+
+
+class FxgError(RuntimeError):
+    def __init__(self, code, detail=""):
+        self.code = code
+        super().__init__("libfxg error %d: %s" % (code, detail))
+
+
+class Batch(C.Structure):
+    """struct fxg_batch"""
+    _fields_ = [("seq", C.c_void_p), ("qual", C.c_void_p), ("len", C.c_void_p),
+                ("uniform_len", C.c_int32), ("stride", C.c_int32), ("n", C.c_int64)]
+
+
+class Report(C.Structure):
+    """struct fxg_report"""
+    _fields_ = [("n_in", C.c_int64), ("n_out", C.c_int64), ("first_bad_read", C.c_int64), ("aux", C.c_int64 * 6)]
+
+
+def lib_path():
+    return os.path.join(_HERE, "libfxg.so")
+
+
+def lib():
+    """Load libfxg.so.  Missing library is a hard error (no fallback path exists)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    p = lib_path()
+    if not os.path.exists(p):
+        raise FxgError(-1, "%s not built: run `make lib` (nvcc, sm_100a). There is no CPU fallback." % p)
+    L = C.CDLL(p)
+    vp, i32, i64, u64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_size_t
+    BP, RP = C.POINTER(Batch), C.POINTER(Report)
+    sig = {
+        "fxg_init": (i32, [i32, C.POINTER(vp)]),
+        "fxg_destroy": (None, [vp]),
+        "fxg_strerror": (C.c_char_p, [i32]),
+        "fxg_last_error": (C.c_char_p, [vp]),
+        "fxg_device_info": (i32, [vp, C.POINTER(i32), C.POINTER(sz), C.POINTER(i32), C.POINTER(i32)]),
+        "fxg_set_stream": (i32, [vp, vp]),
+        "fxg_sync": (i32, [vp]),
+        "fxg_get_report": (i32, [vp, RP]),
+        "fxg_report_reset": (i32, [vp]),
+        "fxg_kernel_launches": (i64, [vp]),
+        "fxg_alloc_pinned": (vp, [sz]),
+        "fxg_free_pinned": (None, [vp]),
+        "fxg_host_register": (i32, [vp, sz]),
+        "fxg_host_unregister": (i32, [vp]),
+        "fxg_alloc_device": (vp, [vp, sz]),
+        "fxg_free_device": (None, [vp, vp]),
+        "fxg_memcpy_h2d": (i32, [vp, vp, vp, sz]),
+        "fxg_memcpy_d2h": (i32, [vp, vp, vp, sz]),
+        "fxg_memset_dev": (i32, [vp, vp, i32, sz]),
+        "fxg_set_tuning": (i32, [vp, i32, i32, i32]),
+        "fxg_synth_dev": (i32, [vp, vp, vp, i64, i64, i64, C.c_int32, C.c_int32, u64, i32, i32]),
+        "fxg_trim_dev": (i32, [vp, BP, i32, i32, i32, vp, i64]),
+        "fxg_trim_host": (i32, [vp, BP, i32, i32, i32, vp, RP]),
+        "fxg_filter_dev": (i32, [vp, BP, i32, i32, i32, vp, i64]),
+        "fxg_filter_host": (i32, [vp, BP, i32, i32, i32, vp, RP]),
+        "fxg_revcomp_dev": (i32, [vp, BP, i32, vp, vp, i64]),
+        "fxg_revcomp_host": (i32, [vp, BP, i32, vp, vp, RP]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+    _LIB = L
+    return L
+
+
+def _ptr(x):
+    """Device/host address of a torch tensor, numpy array, int or None."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    if hasattr(x, "ctypes"):
+        return x.ctypes.data
+    raise TypeError(type(x))
+
+
+class Context:
+    """One fxg_ctx (one GPU).  Methods mirror the C entry points 1:1 and raise FxgError on failure."""
+
+    def __init__(self, device=0):
+        self.L = lib()
+        h = C.c_void_p()
+        rc = self.L.fxg_init(device, C.byref(h))
+        if rc != FXG_OK:
+            raise FxgError(rc, self.L.fxg_strerror(rc).decode() + " (fxg_init: a B200/sm_100 GPU is required)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.fxg_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _ck(self, rc):
+        if rc != FXG_OK:
+            raise FxgError(rc, self.L.fxg_last_error(self.h).decode() or self.L.fxg_strerror(rc).decode())
+
+    # ---- plumbing
+    def set_stream(self, stream_handle):
+        self._ck(self.L.fxg_set_stream(self.h, stream_handle))
+
+    def set_tuning(self, tile_reads=0, stages=0, ctas_per_sm=0):
+        self._ck(self.L.fxg_set_tuning(self.h, tile_reads, stages, ctas_per_sm))
+
+    def sync(self):
+        self._ck(self.L.fxg_sync(self.h))
+        return self.report()
+
+    def report(self):
+        r = Report()
+        self._ck(self.L.fxg_get_report(self.h, C.byref(r)))
+        return r
+
+    def report_reset(self):
+        self._ck(self.L.fxg_report_reset(self.h))
+
+    def launches(self):
+        return int(self.L.fxg_kernel_launches(self.h))
+
+    def device_info(self):
+        sm, hbm, mj, mn = C.c_int(), C.c_size_t(), C.c_int(), C.c_int()
+        self._ck(self.L.fxg_device_info(self.h, C.byref(sm), C.byref(hbm), C.byref(mj), C.byref(mn)))
+        return dict(sm_count=sm.value, hbm_bytes=hbm.value, cc=(mj.value, mn.value))
+
+    @staticmethod
+    def batch(seq, qual, n, stride, uniform_len=0, lens=None):
+        return Batch(_ptr(seq), _ptr(qual), _ptr(lens), uniform_len, stride, n)
+
+    # ---- ops (device pointers)
+    def synth_dev(self, seq, qual, n, length, stride, seed, kind=0, q_offset=33, first_read=0, n_total=None):
+        self._ck(self.L.fxg_synth_dev(self.h, _ptr(seq), _ptr(qual), n, first_read, n_total or (first_read + n),
+                                      length, stride, seed, kind, q_offset))
+
+    def trim_dev(self, b, q_offset, threshold, min_len, out_len, index_base=0):
+        self._ck(self.L.fxg_trim_dev(self.h, C.byref(b), q_offset, threshold, min_len, _ptr(out_len), index_base))
+
+    def filter_dev(self, b, q_offset, min_quality, min_percent, keep, index_base=0):
+        self._ck(self.L.fxg_filter_dev(self.h, C.byref(b), q_offset, min_quality, min_percent, _ptr(keep), index_base))
+
+    def revcomp_dev(self, b, q_offset, out_seq, out_qual, index_base=0):
+        self._ck(self.L.fxg_revcomp_dev(self.h, C.byref(b), q_offset, _ptr(out_seq), _ptr(out_qual), index_base))
+
+    # ---- ops (host pointers; copies are inside the call)
+    def trim_host(self, b, q_offset, threshold, min_len, out_len):
+        r = Report()
+        self._ck(self.L.fxg_trim_host(self.h, C.byref(b), q_offset, threshold, min_len, _ptr(out_len), C.byref(r)))
+        return r
+
+    def filter_host(self, b, q_offset, min_quality, min_percent, keep):
+        r = Report()
+        self._ck(self.L.fxg_filter_host(self.h, C.byref(b), q_offset, min_quality, min_percent, _ptr(keep), C.byref(r)))
+        return r
+
+    def revcomp_host(self, b, q_offset, out_seq, out_qual):
+        r = Report()
+        self._ck(self.L.fxg_revcomp_host(self.h, C.byref(b), q_offset, _ptr(out_seq), _ptr(out_qual), C.byref(r)))
+        return r

@@ -1,0 +1,490 @@
+// fxg_api.cu — the C ABI declared in include/fxg.h: context, memory, launch planning and the
+// host-buffer pipelines (pinned host slab -> H2D on a side stream -> kernel -> D2H).
+// No CPU fallback anywhere: every failure is reported as an error code.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "fxg.h"
+#include "fxg_kernels.cuh"
+
+using namespace fxg;
+
+namespace {
+constexpr int PIPE_LANES = 3;          // chunks in flight in a *_host call
+constexpr unsigned long long NO_BAD = ~0ull;
+}
+
+struct fxg_ctx {
+    int device;
+    int sm_count;
+    int cc_major, cc_minor;
+    size_t hbm_bytes;
+    cudaStream_t own_stream;
+    cudaStream_t stream;               // own_stream or an adopted one
+    unsigned long long *d_counters;    // CNT_WORDS
+    unsigned long long *h_counters;    // pinned mirror
+    fxg_report report;
+    int64_t launches;
+    int tune_tile_reads, tune_stages, tune_ctas;
+    char err[256];
+    // host-pipeline resources (grow-only)
+    cudaStream_t lane_stream[PIPE_LANES];
+    void *lane_buf[PIPE_LANES][4];     // seq, qual, out0, out1
+    size_t lane_cap[PIPE_LANES][4];
+};
+
+#define CK(ctx, call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d %s: %s", __FILE__, __LINE__, #call,    \
+                     cudaGetErrorString(e_));                                                      \
+            return FXG_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+static int arg_error(fxg_ctx *ctx, const char *what)
+{
+    snprintf(ctx->err, sizeof(ctx->err), "bad argument: %s", what);
+    return FXG_ERR_ARG;
+}
+
+extern "C" const char *fxg_strerror(int code)
+{
+    switch (code) {
+    case FXG_OK: return "ok";
+    case FXG_ERR_CUDA: return "CUDA error (no usable GPU, or a launch/copy failed)";
+    case FXG_ERR_ARG: return "invalid argument";
+    case FXG_ERR_NOMEM: return "out of memory";
+    case FXG_ERR_UNSUPPORTED: return "unsupported configuration";
+    case FXG_ERR_NCCL: return "NCCL error";
+    default: return "unknown error";
+    }
+}
+
+extern "C" const char *fxg_last_error(const fxg_ctx *ctx) { return ctx ? ctx->err : "no context"; }
+
+extern "C" int fxg_init(int device, fxg_ctx **out)
+{
+    if (!out) return FXG_ERR_ARG;
+    *out = NULL;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return FXG_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return FXG_ERR_CUDA;
+    fxg_ctx *ctx = (fxg_ctx *)calloc(1, sizeof(fxg_ctx));
+    if (!ctx) return FXG_ERR_NOMEM;
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { free(ctx); return FXG_ERR_CUDA; }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->cc_major = prop.major;
+    ctx->cc_minor = prop.minor;
+    ctx->hbm_bytes = prop.totalGlobalMem;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { free(ctx); return FXG_ERR_CUDA; }
+    ctx->stream = ctx->own_stream;
+    for (int l = 0; l < PIPE_LANES; l++)
+        if (cudaStreamCreateWithFlags(&ctx->lane_stream[l], cudaStreamNonBlocking) != cudaSuccess) { free(ctx); return FXG_ERR_CUDA; }
+    if (cudaMalloc(&ctx->d_counters, CNT_WORDS * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMallocHost(&ctx->h_counters, CNT_WORDS * sizeof(unsigned long long)) != cudaSuccess) { free(ctx); return FXG_ERR_CUDA; }
+    if (kernels_set_smem_attrs() != cudaSuccess) {
+        // the image built for sm_100a cannot run on this device
+        cudaGetLastError();
+        free(ctx);
+        return FXG_ERR_CUDA;
+    }
+    *out = ctx;
+    return fxg_report_reset(ctx);
+}
+
+extern "C" void fxg_destroy(fxg_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (int l = 0; l < PIPE_LANES; l++) {
+        for (int b = 0; b < 4; b++) if (ctx->lane_buf[l][b]) cudaFree(ctx->lane_buf[l][b]);
+        cudaStreamDestroy(ctx->lane_stream[l]);
+    }
+    cudaFree(ctx->d_counters);
+    cudaFreeHost(ctx->h_counters);
+    cudaStreamDestroy(ctx->own_stream);
+    free(ctx);
+}
+
+extern "C" int fxg_device_info(fxg_ctx *ctx, int *sm_count, size_t *hbm_bytes, int *cc_major, int *cc_minor)
+{
+    if (!ctx) return FXG_ERR_ARG;
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (hbm_bytes) *hbm_bytes = ctx->hbm_bytes;
+    if (cc_major) *cc_major = ctx->cc_major;
+    if (cc_minor) *cc_minor = ctx->cc_minor;
+    return FXG_OK;
+}
+
+extern "C" int fxg_set_stream(fxg_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return FXG_ERR_ARG;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return FXG_OK;
+}
+
+extern "C" int fxg_set_tuning(fxg_ctx *ctx, int tile_reads, int stages, int ctas_per_sm)
+{
+    if (!ctx || tile_reads < 0 || stages < 0 || stages > MAX_STAGES || ctas_per_sm < 0) return FXG_ERR_ARG;
+    ctx->tune_tile_reads = tile_reads;
+    ctx->tune_stages = stages;
+    ctx->tune_ctas = ctas_per_sm;
+    return FXG_OK;
+}
+
+static int refresh_report(fxg_ctx *ctx, cudaStream_t st)
+{
+    CK(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, CNT_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
+    ctx->report.n_out = (int64_t)ctx->h_counters[CNT_OUT];
+    ctx->report.first_bad_read = ctx->h_counters[CNT_FIRST_BAD] == NO_BAD ? -1 : (int64_t)ctx->h_counters[CNT_FIRST_BAD];
+    for (int k = 0; k < 6; k++) ctx->report.aux[k] = (int64_t)ctx->h_counters[CNT_AUX0 + k];
+    return FXG_OK;
+}
+
+extern "C" int fxg_sync(fxg_ctx *ctx)
+{
+    if (!ctx) return FXG_ERR_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    return refresh_report(ctx, ctx->stream);
+}
+
+extern "C" int fxg_get_report(fxg_ctx *ctx, fxg_report *out)
+{
+    if (!ctx || !out) return FXG_ERR_ARG;
+    *out = ctx->report;
+    return FXG_OK;
+}
+
+extern "C" int fxg_report_reset(fxg_ctx *ctx)
+{
+    if (!ctx) return FXG_ERR_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    memset(&ctx->report, 0, sizeof(ctx->report));
+    ctx->report.first_bad_read = -1;
+    for (int k = 0; k < CNT_WORDS; k++) ctx->h_counters[k] = 0;
+    ctx->h_counters[CNT_FIRST_BAD] = NO_BAD;
+    CK(ctx, cudaMemcpyAsync(ctx->d_counters, ctx->h_counters, CNT_WORDS * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return FXG_OK;
+}
+
+extern "C" int64_t fxg_kernel_launches(const fxg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- memory ------------------------------------------------------------------------------------
+extern "C" void *fxg_alloc_pinned(size_t bytes)
+{
+    void *p = NULL;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return NULL; }
+    return p;
+}
+extern "C" void fxg_free_pinned(void *p) { if (p) cudaFreeHost(p); }
+extern "C" int fxg_host_register(void *p, size_t bytes)
+{
+    return cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess ? FXG_OK : (cudaGetLastError(), FXG_ERR_CUDA);
+}
+extern "C" int fxg_host_unregister(void *p)
+{
+    return cudaHostUnregister(p) == cudaSuccess ? FXG_OK : (cudaGetLastError(), FXG_ERR_CUDA);
+}
+extern "C" void *fxg_alloc_device(fxg_ctx *ctx, size_t bytes)
+{
+    if (!ctx) return NULL;
+    void *p = NULL;
+    if (cudaSetDevice(ctx->device) != cudaSuccess || cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) {
+        snprintf(ctx->err, sizeof(ctx->err), "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+        return NULL;
+    }
+    return p;
+}
+extern "C" void fxg_free_device(fxg_ctx *ctx, void *p) { if (ctx && p) { cudaSetDevice(ctx->device); cudaFree(p); } }
+extern "C" int fxg_memcpy_h2d(fxg_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    if (!ctx) return FXG_ERR_ARG;
+    CK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return FXG_OK;
+}
+extern "C" int fxg_memcpy_d2h(fxg_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    if (!ctx) return FXG_ERR_ARG;
+    CK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return FXG_OK;
+}
+extern "C" int fxg_memset_dev(fxg_ctx *ctx, void *dst, int value, size_t bytes)
+{
+    if (!ctx) return FXG_ERR_ARG;
+    CK(ctx, cudaMemsetAsync(dst, value, bytes, ctx->stream));
+    return FXG_OK;
+}
+
+// ---- launch planning -----------------------------------------------------------------------------
+// G lanes per read: the 8 lanes of a quarter-warp must touch 8 distinct 16-byte bank groups when they
+// issue LDS.128 at rows `stride` apart, which holds when G = lowbit(stride/16) (capped at 8); long
+// reads get more lanes so a tile still fills the CTA.
+static int choose_g(int stride)
+{
+    const int c = stride >> 4;
+    int g = c & -c;
+    if (g > 8) g = 8;
+    while (g < 32 && c / g > 24) g <<= 1;
+    return g;
+}
+
+static int make_plan(fxg_ctx *ctx, const fxg_batch *b, int nslabs, int extra_stage_bufs, TilePlan *plan)
+{
+    const int S = b->stride;
+    const int g = choose_g(S);
+    const int rpp = THREADS / g;
+    const size_t per_read = (size_t)S * (size_t)nslabs;
+    const size_t smem_max = 227 * 1024 - 1024;       // static smem (barriers) + margin
+    int stages = ctx->tune_stages ? ctx->tune_stages : 3;
+    size_t target = 32 * 1024;                        // bytes per stage
+    int tr = ctx->tune_tile_reads ? ctx->tune_tile_reads : (int)(target / per_read);
+    if (tr >= rpp) tr -= tr % rpp; else if (tr < 1) tr = 1;
+    if ((int64_t)tr > b->n) tr = (int)(b->n > 0 ? b->n : 1);
+    while (stages > 1 && (size_t)(stages + extra_stage_bufs) * per_read * tr > smem_max) stages--;
+    while (tr > 1 && (size_t)(stages + extra_stage_bufs) * per_read * tr > smem_max) tr--;
+    const size_t smem = (size_t)(stages + extra_stage_bufs) * per_read * tr;
+    if (smem > smem_max || per_read * tr >= (1u << 20)) return arg_error(ctx, "read stride too large for shared memory");
+    int ctas = ctx->tune_ctas ? ctx->tune_ctas : (int)(smem_max / (smem + 1024));
+    if (ctas < 1) ctas = 1;
+    if (ctas > 4) ctas = 4;
+    const int64_t ntiles = (b->n + tr - 1) / tr;
+    int64_t grid = (int64_t)ctx->sm_count * ctas;
+    if (grid > ntiles) grid = ntiles;
+    if (grid < 1) grid = 1;
+    plan->g = g;
+    plan->tile_reads = tr;
+    plan->stages = stages;
+    plan->grid = (int)grid;
+    plan->smem_bytes = (uint32_t)smem;
+    return FXG_OK;
+}
+
+static int check_batch(fxg_ctx *ctx, const fxg_batch *b, bool need_seq, bool need_qual, int q_offset)
+{
+    if (!ctx) return FXG_ERR_ARG;
+    if (!b) return arg_error(ctx, "batch is NULL");
+    if (b->n < 0) return arg_error(ctx, "n < 0");
+    if (b->stride <= 0 || (b->stride & 15)) return arg_error(ctx, "stride must be a positive multiple of 16");
+    if (need_seq && !b->seq) return arg_error(ctx, "seq is NULL");
+    if (need_qual && !b->qual) return arg_error(ctx, "qual is NULL");
+    if (((uintptr_t)b->seq & 15) || ((uintptr_t)b->qual & 15)) return arg_error(ctx, "slab base must be 16-byte aligned");
+    if (!b->len && (b->uniform_len <= 0 || b->uniform_len > b->stride)) return arg_error(ctx, "uniform_len out of range");
+    if (q_offset < 15 || q_offset > 127) {
+        snprintf(ctx->err, sizeof(ctx->err), "quality offset %d unsupported (15..127)", q_offset);
+        return FXG_ERR_UNSUPPORTED;
+    }
+    return FXG_OK;
+}
+
+// ---- synthetic data --------------------------------------------------------------------------------
+extern "C" int fxg_synth_dev(fxg_ctx *ctx, uint8_t *seq, uint8_t *qual, int64_t n, int64_t first_read, int64_t n_total,
+                             int32_t len, int32_t stride, uint64_t seed, int kind, int q_offset)
+{
+    if (!ctx) return FXG_ERR_ARG;
+    if (n < 0 || len <= 0 || stride < len || (stride & 15)) return arg_error(ctx, "synth geometry");
+    if (n == 0) return FXG_OK;
+    CK(ctx, cudaSetDevice(ctx->device));
+    SynthParams p;
+    p.seq = seq; p.qual = qual; p.n = n; p.first_read = first_read; p.n_total = n_total;
+    p.len = len; p.stride = stride; p.seed = seed; p.kind = kind; p.q_offset = q_offset;
+    CK(ctx, launch_synth(p, ctx->stream));
+    ctx->launches++;
+    return FXG_OK;
+}
+
+// ---- trim / filter -----------------------------------------------------------------------------------
+static int scan_enqueue(fxg_ctx *ctx, int mode, const fxg_batch *b, int q_offset, int thr_q, int min_len, int min_percent,
+                        void *out, int64_t index_base, cudaStream_t st)
+{
+    if (b->n == 0) return FXG_OK;
+    const bool has_seq = b->seq != NULL;
+    TilePlan plan;
+    int rc = make_plan(ctx, b, has_seq ? 2 : 1, 0, &plan);
+    if (rc) return rc;
+    ScanParams p;
+    p.seq = b->seq; p.qual = b->qual; p.len = b->len; p.uniform_len = b->uniform_len; p.stride = b->stride; p.n = b->n;
+    p.tile_reads = plan.tile_reads; p.stages = plan.stages;
+    p.qk = make_qualk(q_offset, thr_q);
+    p.min_len = min_len;
+    p.pct_keep = 100 - min_percent;
+    p.force_drop = (mode == MODE_FILTER && min_percent == 0 && thr_q > 93) ? 1 : 0;
+    p.out = out; p.index_base = index_base; p.counters = ctx->d_counters;
+    CK(ctx, launch_scan(mode, has_seq, plan, p, st));
+    ctx->launches++;
+    ctx->report.n_in += b->n;
+    return FXG_OK;
+}
+
+extern "C" int fxg_trim_dev(fxg_ctx *ctx, const fxg_batch *b, int q_offset, int threshold, int min_len,
+                            int32_t *out_len, int64_t index_base)
+{
+    int rc = check_batch(ctx, b, false, true, q_offset);
+    if (rc) return rc;
+    if (!out_len) return arg_error(ctx, "out_len is NULL");
+    CK(ctx, cudaSetDevice(ctx->device));
+    return scan_enqueue(ctx, MODE_TRIM, b, q_offset, threshold, min_len, 0, out_len, index_base, ctx->stream);
+}
+
+extern "C" int fxg_filter_dev(fxg_ctx *ctx, const fxg_batch *b, int q_offset, int min_quality, int min_percent,
+                              uint8_t *keep, int64_t index_base)
+{
+    int rc = check_batch(ctx, b, false, true, q_offset);
+    if (rc) return rc;
+    if (!keep) return arg_error(ctx, "keep is NULL");
+    if (min_percent < 0 || min_percent > 100) return arg_error(ctx, "min_percent must be 0..100");
+    CK(ctx, cudaSetDevice(ctx->device));
+    return scan_enqueue(ctx, MODE_FILTER, b, q_offset, min_quality, 0, min_percent, keep, index_base, ctx->stream);
+}
+
+// ---- revcomp ---------------------------------------------------------------------------------------
+static int revcomp_enqueue(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint8_t *out_seq, uint8_t *out_qual,
+                           int64_t index_base, cudaStream_t st)
+{
+    if (b->n == 0) return FXG_OK;
+    const bool has_qual = b->qual != NULL;
+    TilePlan plan;
+    int rc = make_plan(ctx, b, has_qual ? 2 : 1, 2, &plan);
+    if (rc) return rc;
+    RevcompParams p;
+    p.seq = b->seq; p.qual = b->qual; p.len = b->len; p.uniform_len = b->uniform_len; p.stride = b->stride; p.n = b->n;
+    p.tile_reads = plan.tile_reads; p.stages = plan.stages;
+    p.qk = make_qualk(q_offset, 0);
+    p.out_seq = out_seq; p.out_qual = out_qual; p.index_base = index_base; p.counters = ctx->d_counters;
+    CK(ctx, launch_revcomp(has_qual, plan, p, st));
+    ctx->launches++;
+    ctx->report.n_in += b->n;
+    return FXG_OK;
+}
+
+extern "C" int fxg_revcomp_dev(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint8_t *out_seq, uint8_t *out_qual,
+                               int64_t index_base)
+{
+    int rc = check_batch(ctx, b, true, false, q_offset);
+    if (rc) return rc;
+    if (!out_seq || (b->qual && !out_qual)) return arg_error(ctx, "output slab is NULL");
+    if (((uintptr_t)out_seq & 15) || ((uintptr_t)out_qual & 15)) return arg_error(ctx, "output slab must be 16-byte aligned");
+    CK(ctx, cudaSetDevice(ctx->device));
+    return revcomp_enqueue(ctx, b, q_offset, out_seq, out_qual, index_base, ctx->stream);
+}
+
+// ---- host-buffer pipelines ---------------------------------------------------------------------------
+static int lane_reserve(fxg_ctx *ctx, int lane, int slot, size_t bytes)
+{
+    if (ctx->lane_cap[lane][slot] >= bytes) return FXG_OK;
+    if (ctx->lane_buf[lane][slot]) cudaFree(ctx->lane_buf[lane][slot]);
+    ctx->lane_buf[lane][slot] = NULL;
+    ctx->lane_cap[lane][slot] = 0;
+    CK(ctx, cudaMalloc(&ctx->lane_buf[lane][slot], bytes));
+    ctx->lane_cap[lane][slot] = bytes;
+    return FXG_OK;
+}
+
+static int64_t chunk_reads(const fxg_batch *b)
+{
+    // ~48 MB per slab per chunk: large enough to run PCIe at full rate, small enough to pipeline
+    int64_t cr = (48ll << 20) / b->stride;
+    if (cr < 1) cr = 1;
+    const int64_t third = (b->n + PIPE_LANES - 1) / PIPE_LANES;
+    if (cr > third && third > 0) cr = third;
+    return cr;
+}
+
+enum { HOST_TRIM, HOST_FILTER, HOST_REVCOMP };
+
+static int host_pipeline(fxg_ctx *ctx, int op, const fxg_batch *b, int q_offset, int a0, int a1,
+                         void *out0, void *out1, fxg_report *report)
+{
+    CK(ctx, cudaSetDevice(ctx->device));
+    int rc = fxg_report_reset(ctx);
+    if (rc) return rc;
+    const int64_t cr = chunk_reads(b);
+    const size_t S = (size_t)b->stride;
+    int lane = 0;
+    for (int64_t r0 = 0; r0 < b->n; r0 += cr, lane = (lane + 1) % PIPE_LANES) {
+        const int64_t nr = (b->n - r0 < cr) ? (b->n - r0) : cr;
+        cudaStream_t st = ctx->lane_stream[lane];
+        // the lane's previous chunk must be fully drained before its buffers are reused:
+        // stream order already guarantees that (copies and kernels of one lane are serialized).
+        const bool has_seq = b->seq != NULL, has_qual = b->qual != NULL;
+        if (has_seq && (rc = lane_reserve(ctx, lane, 0, (size_t)cr * S))) return rc;
+        if (has_qual && (rc = lane_reserve(ctx, lane, 1, (size_t)cr * S))) return rc;
+        size_t o0 = 0, o1 = 0;
+        if (op == HOST_TRIM) o0 = (size_t)cr * sizeof(int32_t);
+        else if (op == HOST_FILTER) o0 = (size_t)cr;
+        else { o0 = (size_t)cr * S; o1 = has_qual ? (size_t)cr * S : 0; }
+        const size_t o1_al = (o1 + 15) & ~(size_t)15;
+        const size_t slot3 = o1_al + (b->len ? (size_t)cr * sizeof(int32_t) + 16 : 0);   // out1 | lengths
+        if ((rc = lane_reserve(ctx, lane, 2, o0))) return rc;
+        if (slot3 && (rc = lane_reserve(ctx, lane, 3, slot3))) return rc;
+
+        uint8_t *dseq = (uint8_t *)ctx->lane_buf[lane][0], *dqual = (uint8_t *)ctx->lane_buf[lane][1];
+        if (has_seq) CK(ctx, cudaMemcpyAsync(dseq, b->seq + (size_t)r0 * S, (size_t)nr * S, cudaMemcpyHostToDevice, st));
+        if (has_qual) CK(ctx, cudaMemcpyAsync(dqual, b->qual + (size_t)r0 * S, (size_t)nr * S, cudaMemcpyHostToDevice, st));
+        int32_t *dlen = NULL;
+        fxg_batch db = *b;
+        db.seq = has_seq ? dseq : NULL;
+        db.qual = has_qual ? dqual : NULL;
+        db.n = nr;
+        if (b->len) {
+            dlen = (int32_t *)((uint8_t *)ctx->lane_buf[lane][3] + o1_al);   // lengths ride behind out1
+            CK(ctx, cudaMemcpyAsync(dlen, b->len + r0, (size_t)nr * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+            db.len = dlen;
+        }
+        void *d0 = ctx->lane_buf[lane][2], *d1 = ctx->lane_buf[lane][3];
+        if (op == HOST_TRIM) {
+            if ((rc = scan_enqueue(ctx, MODE_TRIM, &db, q_offset, a0, a1, 0, d0, r0, st))) return rc;
+            CK(ctx, cudaMemcpyAsync((int32_t *)out0 + r0, d0, (size_t)nr * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        } else if (op == HOST_FILTER) {
+            if ((rc = scan_enqueue(ctx, MODE_FILTER, &db, q_offset, a0, 0, a1, d0, r0, st))) return rc;
+            CK(ctx, cudaMemcpyAsync((uint8_t *)out0 + r0, d0, (size_t)nr, cudaMemcpyDeviceToHost, st));
+        } else {
+            if ((rc = revcomp_enqueue(ctx, &db, q_offset, (uint8_t *)d0, has_qual ? (uint8_t *)d1 : NULL, r0, st))) return rc;
+            CK(ctx, cudaMemcpyAsync((uint8_t *)out0 + (size_t)r0 * S, d0, (size_t)nr * S, cudaMemcpyDeviceToHost, st));
+            if (has_qual) CK(ctx, cudaMemcpyAsync((uint8_t *)out1 + (size_t)r0 * S, d1, (size_t)nr * S, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    for (int l = 0; l < PIPE_LANES; l++) CK(ctx, cudaStreamSynchronize(ctx->lane_stream[l]));
+    rc = refresh_report(ctx, ctx->lane_stream[0]);
+    if (rc) return rc;
+    if (report) *report = ctx->report;
+    return FXG_OK;
+}
+
+extern "C" int fxg_trim_host(fxg_ctx *ctx, const fxg_batch *b, int q_offset, int threshold, int min_len,
+                             int32_t *out_len, fxg_report *report)
+{
+    int rc = check_batch(ctx, b, false, true, q_offset);
+    if (rc) return rc;
+    if (!out_len) return arg_error(ctx, "out_len is NULL");
+    return host_pipeline(ctx, HOST_TRIM, b, q_offset, threshold, min_len, out_len, NULL, report);
+}
+
+extern "C" int fxg_filter_host(fxg_ctx *ctx, const fxg_batch *b, int q_offset, int min_quality, int min_percent,
+                               uint8_t *keep, fxg_report *report)
+{
+    int rc = check_batch(ctx, b, false, true, q_offset);
+    if (rc) return rc;
+    if (!keep) return arg_error(ctx, "keep is NULL");
+    if (min_percent < 0 || min_percent > 100) return arg_error(ctx, "min_percent must be 0..100");
+    return host_pipeline(ctx, HOST_FILTER, b, q_offset, min_quality, min_percent, keep, NULL, report);
+}
+
+extern "C" int fxg_revcomp_host(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint8_t *out_seq, uint8_t *out_qual,
+                                fxg_report *report)
+{
+    int rc = check_batch(ctx, b, true, false, q_offset);
+    if (rc) return rc;
+    if (!out_seq || (b->qual && !out_qual)) return arg_error(ctx, "output slab is NULL");
+    return host_pipeline(ctx, HOST_REVCOMP, b, q_offset, 0, 0, out_seq, out_qual, report);
+}

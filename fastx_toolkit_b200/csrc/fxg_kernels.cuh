@@ -1,0 +1,74 @@
+// fxg_kernels.cuh — launch-parameter structs shared between the kernels (fxg_kernels.cu) and the
+// C-ABI layer (fxg_api.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "fxg_device.cuh"
+
+namespace fxg {
+
+constexpr int THREADS = 256;     // threads per CTA for the tile-pipeline kernels
+constexpr int MAX_STAGES = 8;
+
+enum { MODE_TRIM = 0, MODE_FILTER = 1 };
+
+// counters block in device memory (one per context)
+enum { CNT_OUT = 0, CNT_FIRST_BAD = 1, CNT_AUX0 = 2, CNT_WORDS = 16 };
+
+struct TilePlan {
+    int32_t g;            // lanes cooperating on one read (power of two, 1..32)
+    int32_t tile_reads;   // reads per TMA tile
+    int32_t stages;       // smem ring depth
+    int32_t grid;         // persistent CTAs
+    uint32_t smem_bytes;  // dynamic shared memory per CTA
+};
+
+struct ScanParams {
+    const uint8_t *seq;   // may be NULL (HAS_SEQ=false instantiation)
+    const uint8_t *qual;
+    const int32_t *len;   // may be NULL
+    int32_t uniform_len;
+    int32_t stride;
+    int64_t n;
+    int32_t tile_reads;
+    int32_t stages;
+    QualK qk;
+    int32_t min_len;      // trim: -l
+    int32_t pct_keep;     // filter: 100 - p   (keep iff 100*low <= L*pct_keep)
+    int32_t force_drop;   // filter: -p 0 with -q > 93 drops everything (reference walks off its table)
+    void *out;            // int32[n] (trim) or uint8[n] (filter)
+    int64_t index_base;
+    unsigned long long *counters;
+};
+
+struct RevcompParams {
+    const uint8_t *seq;
+    const uint8_t *qual;  // may be NULL (FASTA)
+    const int32_t *len;
+    int32_t uniform_len;
+    int32_t stride;
+    int64_t n;
+    int32_t tile_reads;
+    int32_t stages;
+    QualK qk;
+    uint8_t *out_seq;
+    uint8_t *out_qual;
+    int64_t index_base;
+    unsigned long long *counters;
+};
+
+struct SynthParams {
+    uint8_t *seq;
+    uint8_t *qual;
+    int64_t n, first_read, n_total;
+    int32_t len, stride;
+    uint64_t seed;
+    int32_t kind, q_offset;
+};
+
+cudaError_t launch_scan(int mode, bool has_seq, const TilePlan &plan, const ScanParams &p, cudaStream_t st);
+cudaError_t launch_revcomp(bool has_qual, const TilePlan &plan, const RevcompParams &p, cudaStream_t st);
+cudaError_t launch_synth(const SynthParams &p, cudaStream_t st);
+cudaError_t kernels_set_smem_attrs();   // opt in to > 48 KB dynamic shared memory for every kernel
+
+}  // namespace fxg

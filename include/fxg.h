@@ -1,0 +1,118 @@
+/*
+ * fxg.h — thin C ABI of the B200-native FASTX hot path (libfxg.so).
+ *
+ * The reference (agordon/fastx_toolkit 0.0.14) has no plugin/FFI interface: its only seams are the
+ * six executables and libfastx's record API (src/libfastx/fastx.h:120-142).  This header is the
+ * boundary the drop-in executables in bin/ (host C, fastx_toolkit_b200/csrc/host/) call instead of
+ * running the per-read transform loop on the CPU.  Each entry point names the reference loop body
+ * it replaces.  Plain C structs, plain pointers and sizes, int error codes, no exceptions.
+ *
+ * Conventions
+ *   - A *batch* is a structure-of-arrays slab: read i occupies bytes [i*stride, i*stride+len_i) of
+ *     `seq` and of `qual` (raw FASTQ bytes, i.e. ASCII quality, not yet offset by -Q).  `stride`
+ *     is a multiple of 16 and both base pointers are 16-byte aligned.  Padding bytes are ignored.
+ *   - `*_dev` entry points take DEVICE pointers and only enqueue work on the context's stream;
+ *     results are valid after fxg_sync().  `*_host` entry points take HOST pointers (pinned for
+ *     full speed: fxg_alloc_pinned / fxg_host_register), pipeline H2D copy -> kernel -> D2H copy
+ *     over chunks on side streams, and return when the results are in host memory.
+ *   - A context is bound to one GPU and is single-threaded; contexts are independent (one per GPU).
+ *   - There is NO CPU fallback: without a usable GPU every call fails with FXG_ERR_CUDA.
+ *   - Supported quality offsets: 15 <= q_offset <= 127 (Phred+33 and +64 are the real ones).
+ */
+#ifndef FXG_H
+#define FXG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FXG_OK               0
+#define FXG_ERR_CUDA         1   /* CUDA runtime/driver error (no device, launch failure, ...) */
+#define FXG_ERR_ARG          2   /* bad argument (alignment, stride, NULL, unsupported -Q)      */
+#define FXG_ERR_NOMEM        3
+#define FXG_ERR_UNSUPPORTED  4
+#define FXG_ERR_NCCL         5
+
+#define FXG_QBINS            109 /* quality values -15..93 (src/libfastx/fastx.h:28-29)         */
+#define FXG_MAX_ADAPTER      100 /* src/fastx_clipper/fastx_clipper.cpp:38 MAX_ADAPTER_LEN       */
+
+typedef struct fxg_ctx fxg_ctx;
+
+/* SoA slab of reads (see Conventions). len == NULL means every read has uniform_len bases. */
+typedef struct {
+    const uint8_t *seq;
+    const uint8_t *qual;      /* NULL for FASTA input (only ops that accept it)                 */
+    const int32_t *len;
+    int32_t        uniform_len;
+    int32_t        stride;
+    int64_t        n;
+} fxg_batch;
+
+/* Filled by fxg_sync() / by the *_host calls. Counters accumulate until fxg_report_reset(). */
+typedef struct {
+    int64_t n_in;             /* reads processed                                                */
+    int64_t n_out;            /* reads kept / emitted                                           */
+    int64_t first_bad_read;   /* smallest batch-relative index (+base) of a read that fails the
+                                 reader's validation (fastx.c:45-54,118-135,361-362); -1 = none */
+    int64_t aux[6];           /* op specific (clipper: discard classes, see fxg_clip_*)         */
+} fxg_report;
+
+/* ---- context, memory -------------------------------------------------------------------- */
+int         fxg_init(int device, fxg_ctx **out);
+void        fxg_destroy(fxg_ctx *ctx);
+const char *fxg_strerror(int code);
+const char *fxg_last_error(const fxg_ctx *ctx);          /* detail of the last failure           */
+int         fxg_device_info(fxg_ctx *ctx, int *sm_count, size_t *hbm_bytes, int *cc_major, int *cc_minor);
+int         fxg_set_stream(fxg_ctx *ctx, void *cuda_stream);  /* adopt caller's stream (NULL = own) */
+int         fxg_sync(fxg_ctx *ctx);                      /* wait, then refresh the report        */
+int         fxg_get_report(fxg_ctx *ctx, fxg_report *out);
+int         fxg_report_reset(fxg_ctx *ctx);
+int64_t     fxg_kernel_launches(const fxg_ctx *ctx);     /* kernels launched by this context     */
+
+void       *fxg_alloc_pinned(size_t bytes);
+void        fxg_free_pinned(void *p);
+int         fxg_host_register(void *p, size_t bytes);
+int         fxg_host_unregister(void *p);
+void       *fxg_alloc_device(fxg_ctx *ctx, size_t bytes);
+void        fxg_free_device(fxg_ctx *ctx, void *p);
+int         fxg_memcpy_h2d(fxg_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
+int         fxg_memcpy_d2h(fxg_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+int         fxg_memset_dev(fxg_ctx *ctx, void *dst_dev, int value, size_t bytes);
+
+/* Tuning knobs (0 = library default). tile_reads: reads per TMA tile; stages: smem ring depth;
+ * ctas_per_sm: persistent CTAs per SM. */
+int         fxg_set_tuning(fxg_ctx *ctx, int tile_reads, int stages, int ctas_per_sm);
+
+/* ---- synthetic workload (include/fxg_synth.h), generated on the device ------------------- */
+int fxg_synth_dev(fxg_ctx *ctx, uint8_t *seq_dev, uint8_t *qual_dev, int64_t n, int64_t first_read,
+                  int64_t n_total, int32_t len, int32_t stride, uint64_t seed, int kind, int q_offset);
+
+/* ---- a2: fastq_quality_trimmer loop body (src/fastq_quality_trimmer/fastq_quality_trimmer.c:91-103)
+ * out_len[i] = surviving prefix length, or -1 when the read is discarded.  batch->seq may be NULL
+ * to skip base validation ("decide-only", L+4 bytes/read); the full form reads 2L+4 bytes/read. */
+int fxg_trim_dev (fxg_ctx *ctx, const fxg_batch *b, int q_offset, int threshold, int min_len,
+                  int32_t *out_len_dev, int64_t index_base);
+int fxg_trim_host(fxg_ctx *ctx, const fxg_batch *b, int q_offset, int threshold, int min_len,
+                  int32_t *out_len_host, fxg_report *report);
+
+/* ---- a3: fastq_quality_filter loop body (src/fastq_quality_filter/fastq_quality_filter.c:78-129,141-161)
+ * keep[i] = 1 iff the read passes (-q min_quality, -p min_percent). */
+int fxg_filter_dev (fxg_ctx *ctx, const fxg_batch *b, int q_offset, int min_quality, int min_percent,
+                    uint8_t *keep_dev, int64_t index_base);
+int fxg_filter_host(fxg_ctx *ctx, const fxg_batch *b, int q_offset, int min_quality, int min_percent,
+                    uint8_t *keep_host, fxg_report *report);
+
+/* ---- a4: fastx_reverse_complement loop body (src/fastx_reverse_complement/fastx_reverse_complement.c:43-104)
+ * Writes the reverse complement (and reversed qualities) with the same stride; padding is zeroed. */
+int fxg_revcomp_dev (fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint8_t *out_seq_dev,
+                     uint8_t *out_qual_dev, int64_t index_base);
+int fxg_revcomp_host(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint8_t *out_seq_host,
+                     uint8_t *out_qual_host, fxg_report *report);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FXG_H */

@@ -52,12 +52,14 @@ FXG_HD uint64_t fxg_synth_read_key(uint64_t seed, uint64_t read_idx, int kind, u
 FXG_HD uint8_t fxg_synth_base(uint64_t r, int pos, int L, int kind)
 {
     uint64_t h = fxg_sm64(r + (uint64_t)pos);
-    uint8_t b = (uint8_t)("ACGT"[h & 3ull]);
+    uint8_t b = (uint8_t)(0x54474341u >> (8u * (unsigned)(h & 3ull)));   /* "ACGT"[h & 3] */
     if (kind == FXG_SYNTH_WITH_N && ((h >> 2) & 1023ull) == 0ull) b = (uint8_t)'N';
     if (kind == FXG_SYNTH_ADAPTER && ((r >> 32) % 100ull) < 30ull && L > 20) {
         int start = 20 + (int)((r >> 40) % (uint64_t)(L - 20));
         int off = pos - start;
-        if (off >= 0 && off < 13) b = (uint8_t)("AGATCGGAAGAGC"[off]);
+        /* "AGATCGGAAGAGC"[off], packed little-endian so device code needs no string table */
+        if (off >= 0 && off < 8) b = (uint8_t)(0x4147474354414741ull >> (8 * off));
+        else if (off >= 8 && off < 13) b = (uint8_t)(0x4347414741ull >> (8 * (off - 8)));
     }
     return b;
 }
