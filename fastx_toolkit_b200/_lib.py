@@ -99,7 +99,8 @@ class Context:
         h = C.c_void_p()
         rc = self.L.fxg_init(device, C.byref(h))
         if rc != FXG_OK:
-            raise FxgError(rc, self.L.fxg_strerror(rc).decode() + " (fxg_init: a B200/sm_100 GPU is required)")
+            raise FxgError(rc, self.L.fxg_strerror(rc).decode() + " — " + self.L.fxg_last_error(None).decode()
+                           + " (a B200/sm_100 GPU is required; there is no CPU fallback)")
         self.h = h
         self.device = device
 

@@ -64,36 +64,48 @@ extern "C" const char *fxg_strerror(int code)
     }
 }
 
-extern "C" const char *fxg_last_error(const fxg_ctx *ctx) { return ctx ? ctx->err : "no context"; }
+static char g_init_err[256] = "no context";   // detail of the last fxg_init failure
+extern "C" const char *fxg_last_error(const fxg_ctx *ctx) { return ctx ? ctx->err : g_init_err; }
+
+#define INIT_FAIL(what, e)                                                                         \
+    do {                                                                                           \
+        snprintf(g_init_err, sizeof(g_init_err), "fxg_init: %s: %s", what, cudaGetErrorString(e)); \
+        cudaGetLastError();                                                                        \
+        return FXG_ERR_CUDA;                                                                       \
+    } while (0)
 
 extern "C" int fxg_init(int device, fxg_ctx **out)
 {
     if (!out) return FXG_ERR_ARG;
     *out = NULL;
     int count = 0;
-    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return FXG_ERR_CUDA;
-    if (cudaSetDevice(device) != cudaSuccess) return FXG_ERR_CUDA;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess) INIT_FAIL("cudaGetDeviceCount", e);
+    if (count <= 0 || device < 0 || device >= count) {
+        snprintf(g_init_err, sizeof(g_init_err), "fxg_init: device %d not present (%d CUDA devices)", device, count);
+        return FXG_ERR_CUDA;
+    }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) INIT_FAIL("cudaSetDevice", e);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) INIT_FAIL("cudaGetDeviceProperties", e);
+    if (prop.major != 10) {
+        snprintf(g_init_err, sizeof(g_init_err), "fxg_init: device %d is sm_%d%d; this build is sm_100a only", device, prop.major, prop.minor);
+        return FXG_ERR_CUDA;
+    }
     fxg_ctx *ctx = (fxg_ctx *)calloc(1, sizeof(fxg_ctx));
     if (!ctx) return FXG_ERR_NOMEM;
     ctx->device = device;
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { free(ctx); return FXG_ERR_CUDA; }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->cc_major = prop.major;
     ctx->cc_minor = prop.minor;
     ctx->hbm_bytes = prop.totalGlobalMem;
-    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { free(ctx); return FXG_ERR_CUDA; }
+    if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { free(ctx); INIT_FAIL("cudaStreamCreate", e); }
     ctx->stream = ctx->own_stream;
     for (int l = 0; l < PIPE_LANES; l++)
-        if (cudaStreamCreateWithFlags(&ctx->lane_stream[l], cudaStreamNonBlocking) != cudaSuccess) { free(ctx); return FXG_ERR_CUDA; }
-    if (cudaMalloc(&ctx->d_counters, CNT_WORDS * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMallocHost(&ctx->h_counters, CNT_WORDS * sizeof(unsigned long long)) != cudaSuccess) { free(ctx); return FXG_ERR_CUDA; }
-    if (kernels_set_smem_attrs() != cudaSuccess) {
-        // the image built for sm_100a cannot run on this device
-        cudaGetLastError();
-        free(ctx);
-        return FXG_ERR_CUDA;
-    }
+        if ((e = cudaStreamCreateWithFlags(&ctx->lane_stream[l], cudaStreamNonBlocking)) != cudaSuccess) { free(ctx); INIT_FAIL("cudaStreamCreate", e); }
+    if ((e = cudaMalloc(&ctx->d_counters, CNT_WORDS * sizeof(unsigned long long))) != cudaSuccess) { free(ctx); INIT_FAIL("cudaMalloc", e); }
+    if ((e = cudaMallocHost(&ctx->h_counters, CNT_WORDS * sizeof(unsigned long long))) != cudaSuccess) { free(ctx); INIT_FAIL("cudaMallocHost", e); }
+    if ((e = kernels_set_smem_attrs()) != cudaSuccess) { free(ctx); INIT_FAIL("cudaFuncSetAttribute(max dynamic smem)", e); }
     *out = ctx;
     return fxg_report_reset(ctx);
 }
@@ -245,7 +257,7 @@ static int make_plan(fxg_ctx *ctx, const fxg_batch *b, int nslabs, int extra_sta
     const int g = choose_g(S);
     const int rpp = THREADS / g;
     const size_t per_read = (size_t)S * (size_t)nslabs;
-    const size_t smem_max = 227 * 1024 - 1024;       // static smem (barriers) + margin
+    const size_t smem_max = MAX_DYN_SMEM;
     int stages = ctx->tune_stages ? ctx->tune_stages : 3;
     size_t target = 32 * 1024;                        // bytes per stage
     int tr = ctx->tune_tile_reads ? ctx->tune_tile_reads : (int)(target / per_read);

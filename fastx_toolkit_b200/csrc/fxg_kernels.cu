@@ -468,7 +468,7 @@ cudaError_t launch_synth(const SynthParams &p, cudaStream_t st)
 
 template <typename K> static cudaError_t set_max_smem(K kernel)
 {
-    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
 }
 
 cudaError_t kernels_set_smem_attrs()

@@ -9,6 +9,7 @@ namespace fxg {
 
 constexpr int THREADS = 256;     // threads per CTA for the tile-pipeline kernels
 constexpr int MAX_STAGES = 8;
+constexpr int MAX_DYN_SMEM = 227 * 1024 - 1024;   // per-CTA opt-in limit minus the kernels' static smem (barriers)
 
 enum { MODE_TRIM = 0, MODE_FILTER = 1 };
 
