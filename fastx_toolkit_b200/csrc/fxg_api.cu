@@ -251,14 +251,64 @@ static int choose_g(int stride)
     return g;
 }
 
-static int make_plan(fxg_ctx *ctx, const fxg_batch *b, int nslabs, int extra_stage_bufs, TilePlan *plan)
+static int gcd8(int c) { return (c & 1) ? 1 : (c & 2) ? 2 : (c & 4) ? 4 : 8; }
+
+// FXG_TUNE="ring,g,stages,ctas" (ring: 1 warp-private kernel, 0 CTA-tile kernel; 0 = default for any
+// field) — an experimentation knob for bench/profiling runs; production uses the defaults below.
+static void env_tune(int *ring, int *g, int *stages, int *ctas)
+{
+    *ring = -1; *g = 0; *stages = 0; *ctas = 0;
+    const char *e = getenv("FXG_TUNE");
+    if (!e) return;
+    int r = -1, a = 0, b = 0, c = 0;
+    if (sscanf(e, "%d,%d,%d,%d", &r, &a, &b, &c) >= 1) { *ring = r; *g = a; *stages = b; *ctas = c; }
+}
+
+static int make_plan(fxg_ctx *ctx, const fxg_batch *b, int nslabs, int extra_stage_bufs, TilePlan *plan, bool allow_ring = true)
 {
     const int S = b->stride;
-    const int g = choose_g(S);
-    const int rpp = THREADS / g;
     const size_t per_read = (size_t)S * (size_t)nslabs;
     const size_t smem_max = MAX_DYN_SMEM;
-    int stages = ctx->tune_stages ? ctx->tune_stages : 3;
+    int t_ring, t_g, t_stages, t_ctas;
+    env_tune(&t_ring, &t_g, &t_stages, &t_ctas);
+    if (ctx->tune_stages) t_stages = ctx->tune_stages;
+    if (ctx->tune_ctas) t_ctas = ctx->tune_ctas;
+    memset(plan, 0, sizeof(*plan));
+
+    // ---- warp-private pipeline: a warp's tile (32/g reads) must stay small enough that many warps fit
+    if (allow_ring && t_ring != 0 && ctx->tune_tile_reads == 0) {
+        int g = 0;
+        for (int cand = 1; cand <= 8; cand <<= 1) {
+            if (t_g && cand != t_g) continue;
+            if ((size_t)(32 / cand) * per_read <= 12 * 1024) { g = cand; break; }
+        }
+        if (g) {
+            const size_t wstage = (size_t)(32 / g) * per_read;
+            int stages = t_stages ? t_stages : 2;
+            while (stages > 1 && (size_t)(stages + extra_stage_bufs) * wstage * W_WARPS > smem_max) stages--;
+            const size_t smem = (size_t)(stages + extra_stage_bufs) * wstage * W_WARPS;
+            if (smem <= smem_max) {
+                int ctas = t_ctas ? t_ctas : (int)((smem_max + 1024) / (smem + 1024));
+                if (ctas < 1) ctas = 1;
+                if (ctas > 12) ctas = 12;                       // 48 warps per SM is plenty
+                const int64_t ntiles = (b->n + (32 / g) - 1) / (32 / g);
+                int64_t grid = (int64_t)ctx->sm_count * ctas;
+                const int64_t need = (ntiles + W_WARPS - 1) / W_WARPS;
+                if (grid > need) grid = need;
+                if (grid < 1) grid = 1;
+                plan->g = g; plan->tile_reads = 32 / g; plan->stages = stages; plan->grid = (int)grid;
+                plan->smem_bytes = (uint32_t)smem; plan->warp_ring = 1;
+                const int d = gcd8(S >> 4);
+                plan->rot_shift = d == 1 ? 3 : d == 2 ? 2 : d == 4 ? 1 : 0;
+                return FXG_OK;
+            }
+        }
+    }
+
+    // ---- CTA-tile kernel (long reads, or forced)
+    const int g = t_g ? t_g : choose_g(S);
+    const int rpp = THREADS / g;
+    int stages = t_stages ? t_stages : 3;
     size_t target = 32 * 1024;                        // bytes per stage
     int tr = ctx->tune_tile_reads ? ctx->tune_tile_reads : (int)(target / per_read);
     if (tr >= rpp) tr -= tr % rpp; else if (tr < 1) tr = 1;
@@ -267,7 +317,7 @@ static int make_plan(fxg_ctx *ctx, const fxg_batch *b, int nslabs, int extra_sta
     while (tr > 1 && (size_t)(stages + extra_stage_bufs) * per_read * tr > smem_max) tr--;
     const size_t smem = (size_t)(stages + extra_stage_bufs) * per_read * tr;
     if (smem > smem_max || per_read * tr >= (1u << 20)) return arg_error(ctx, "read stride too large for shared memory");
-    int ctas = ctx->tune_ctas ? ctx->tune_ctas : (int)(smem_max / (smem + 1024));
+    int ctas = t_ctas ? t_ctas : (int)(smem_max / (smem + 1024));
     if (ctas < 1) ctas = 1;
     if (ctas > 4) ctas = 4;
     const int64_t ntiles = (b->n + tr - 1) / tr;
@@ -326,7 +376,7 @@ static int scan_enqueue(fxg_ctx *ctx, int mode, const fxg_batch *b, int q_offset
     if (rc) return rc;
     ScanParams p;
     p.seq = b->seq; p.qual = b->qual; p.len = b->len; p.uniform_len = b->uniform_len; p.stride = b->stride; p.n = b->n;
-    p.tile_reads = plan.tile_reads; p.stages = plan.stages;
+    p.tile_reads = plan.tile_reads; p.stages = plan.stages; p.rot_shift = plan.rot_shift;
     p.qk = make_qualk(q_offset, thr_q);
     p.min_len = min_len;
     p.pct_keep = 100 - min_percent;
@@ -366,7 +416,7 @@ static int revcomp_enqueue(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint8
     if (b->n == 0) return FXG_OK;
     const bool has_qual = b->qual != NULL;
     TilePlan plan;
-    int rc = make_plan(ctx, b, has_qual ? 2 : 1, 2, &plan);
+    int rc = make_plan(ctx, b, has_qual ? 2 : 1, 2, &plan, false);
     if (rc) return rc;
     RevcompParams p;
     p.seq = b->seq; p.qual = b->qual; p.len = b->len; p.uniform_len = b->uniform_len; p.stride = b->stride; p.n = b->n;

@@ -67,7 +67,7 @@ __device__ __forceinline__ void scan_chunk(ScanAcc &a, const uint4 &q, const uin
         if (MODE == MODE_TRIM) anyge |= ge;
         else a.lowb += (~(ge >> 7)) & ONES;
     }
-    if (MODE == MODE_TRIM) { if (anyge & HI) a.lastc = c; }
+    if (MODE == MODE_TRIM) { if (anyge & HI) a.lastc = max(a.lastc, c); }
     if (HAS_SEQ) {
         a.bads |= seq_bad_bits(s.x) | seq_bad_bits(s.y);
         a.bads |= seq_bad_bits(s.z) | seq_bad_bits(s.w);
@@ -91,9 +91,78 @@ __device__ __forceinline__ void scan_tail(ScanAcc &a, const uint4 &q, const uint
         else a.lowb += (~(ge >> 7)) & ONES & m;
         if (HAS_SEQ) a.bads |= seq_bad_bits(sw[w]) & m;
     }
-    if (MODE == MODE_TRIM) { if (anyge & HI) a.lastc = c; }
+    if (MODE == MODE_TRIM) { if (anyge & HI) a.lastc = max(a.lastc, c); }
 }
 
+// One read (or this lane's share of it): full 16-byte chunks, then the masked partial chunk.
+//   G == 1: the lane owns the whole read and visits its full chunks in an order rotated by `rot`
+//           (conflict-free LDS.128 when the row pitch is an even number of 16-byte units);
+//   G  > 1: lane j of the group takes chunks j, j+G, ...
+template <int G, int MODE, bool HAS_SEQ>
+__device__ __forceinline__ void scan_read(ScanAcc &a, const uint8_t *qrow, const uint8_t *srow, int L, int j, int rot,
+                                          const QualK &qk)
+{
+    const int nfull = L >> 4, rem = L & 15;
+    int since_flush = 0;
+    if (G == 1) {
+        const int o = rot < nfull ? rot : 0;
+#pragma unroll 2
+        for (int k = 0; k < nfull; k++) {
+            int c = k + o;
+            if (c >= nfull) c -= nfull;
+            const uint4 q = lds128(qrow + c * 16);
+            uint4 sq = make_uint4(0, 0, 0, 0);
+            if (HAS_SEQ) sq = lds128(srow + c * 16);
+            scan_chunk<MODE, HAS_SEQ>(a, q, sq, qk, c);
+            if (MODE == MODE_FILTER) {
+                if (++since_flush == 32) {   // byte lanes hold <= 128: flush before they can wrap
+                    a.low += __dp4a(a.lowb, ONES, 0u);
+                    a.lowb = 0; since_flush = 0;
+                }
+            }
+        }
+    } else {
+#pragma unroll 2
+        for (int c = j; c < nfull; c += G) {
+            const uint4 q = lds128(qrow + c * 16);
+            uint4 sq = make_uint4(0, 0, 0, 0);
+            if (HAS_SEQ) sq = lds128(srow + c * 16);
+            scan_chunk<MODE, HAS_SEQ>(a, q, sq, qk, c);
+            if (MODE == MODE_FILTER) {
+                if (++since_flush == 32) {
+                    a.low += __dp4a(a.lowb, ONES, 0u);
+                    a.lowb = 0; since_flush = 0;
+                }
+            }
+        }
+    }
+    if (rem && (nfull & (G - 1)) == j) {
+        const uint4 q = lds128(qrow + nfull * 16);
+        uint4 sq = make_uint4(0, 0, 0, 0);
+        if (HAS_SEQ) sq = lds128(srow + nfull * 16);
+        scan_tail<MODE, HAS_SEQ>(a, q, sq, qk, nfull, rem);
+    }
+    if (MODE == MODE_FILTER) a.low += __dp4a(a.lowb, ONES, 0u);
+}
+
+// trimmer decision for one read once the last chunk holding a base with q >= t is known:
+// exact byte position inside that chunk -> surviving length (fastq_quality_trimmer.c:93-101)
+__device__ __forceinline__ int trim_newlen(const uint8_t *qrow, int lastc, int L, const QualK &qk)
+{
+    if (lastc < 0) return 0;
+    const uint4 q = lds128(qrow + lastc * 16);
+    const uint32_t qw[4] = { q.x, q.y, q.z, q.w };
+    const int valid = (lastc == (L >> 4)) ? (L & 15) : 16;
+    int pos = -1;
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        const uint32_t f = qual_ge_bits(qw[w] | HI, qk) & HI & head_mask(valid - 4 * w);
+        if (f) pos = 4 * w + ((31 - __clz(f)) >> 3);
+    }
+    return lastc * 16 + pos + 1;
+}
+
+// ---- CTA-tile variant: any stride up to the smem limit (long reads); one tile ring per CTA ----------
 template <int G, int MODE, bool HAS_SEQ>
 __global__ void __launch_bounds__(THREADS) k_scan(const __grid_constant__ ScanParams P)
 {
@@ -158,55 +227,21 @@ __global__ void __launch_bounds__(THREADS) k_scan(const __grid_constant__ ScanPa
             if (lenbad) L = 0;
             const uint8_t *qrow = stage + (size_t)rr * S;
             const uint8_t *srow = qrow + slab_bytes;
-            const int nfull = L >> 4, rem = L & 15;
 
             ScanAcc a;
             a.badq = 0; a.bads = 0; a.lastc = -1; a.lowb = 0; a.low = 0;
-            int since_flush = 0;
-#pragma unroll 2
-            for (int c = j; c < nfull; c += G) {
-                const uint4 q = lds128(qrow + c * 16);
-                uint4 sq = make_uint4(0, 0, 0, 0);
-                if (HAS_SEQ) sq = lds128(srow + c * 16);
-                scan_chunk<MODE, HAS_SEQ>(a, q, sq, qk, c);
-                if (MODE == MODE_FILTER) {
-                    if (++since_flush == 32) {   // byte lanes hold <= 128: flush before they can wrap
-                        a.low += __dp4a(a.lowb, ONES, 0u);
-                        a.lowb = 0; since_flush = 0;
-                    }
-                }
-            }
-            if (rem && (nfull & (G - 1)) == j) {
-                const uint4 q = lds128(qrow + nfull * 16);
-                uint4 sq = make_uint4(0, 0, 0, 0);
-                if (HAS_SEQ) sq = lds128(srow + nfull * 16);
-                scan_tail<MODE, HAS_SEQ>(a, q, sq, qk, nfull, rem);
-            }
-
+            scan_read<G, MODE, HAS_SEQ>(a, qrow, srow, L, j, 0, qk);
             if (((a.badq & HI) | a.bads) != 0 || lenbad) note_bad(P.counters, P.index_base + g);
 
             if (MODE == MODE_TRIM) {
                 const int lastc = group_max<G>(a.lastc);
                 if (j == 0 && active) {
-                    int newlen = 0;
-                    if (lastc >= 0) {
-                        const uint4 q = lds128(qrow + lastc * 16);
-                        const uint32_t qw[4] = { q.x, q.y, q.z, q.w };
-                        const int valid = (lastc == nfull) ? rem : 16;
-                        int pos = -1;
-#pragma unroll
-                        for (int w = 0; w < 4; w++) {
-                            const uint32_t f = qual_ge_bits(qw[w] | HI, qk) & HI & head_mask(valid - 4 * w);
-                            if (f) pos = 4 * w + ((31 - __clz(f)) >> 3);
-                        }
-                        newlen = lastc * 16 + pos + 1;
-                    }
+                    const int newlen = trim_newlen(qrow, lastc, L, qk);
                     const bool keep = newlen >= 1 && newlen >= P.min_len;
                     reinterpret_cast<int32_t *>(P.out)[g] = keep ? newlen : -1;
                     kept_local += keep ? 1u : 0u;
                 }
             } else {
-                a.low += __dp4a(a.lowb, ONES, 0u);
                 const uint32_t low = group_sum<G>(a.low);
                 if (j == 0 && active) {
                     const bool keep = !P.force_drop && !lenbad &&
@@ -230,6 +265,105 @@ __global__ void __launch_bounds__(THREADS) k_scan(const __grid_constant__ ScanPa
     if ((tid & 31) == 0 && kept_local) atomicAdd(&s_kept, kept_local);
     __syncthreads();
     if (tid == 0 && s_kept) atomicAdd(&P.counters[CNT_OUT], (unsigned long long)s_kept);
+}
+
+// ---- warp-private variant (the fast path for short reads) ----------------------------------------
+// Every warp owns a private ring of `stages` tiles of R = 32/G reads and its own mbarriers; lane 0
+// issues the TMA bulk copies.  No CTA-wide barrier exists: warps drift freely, so one warp's wait for
+// HBM is covered by the others' SWAR work, and with G == 1 a lane owns a whole read (no cross-lane
+// reduction, and the masked-tail and exact-position steps run with all 32 lanes busy).
+template <int G, int MODE, bool HAS_SEQ>
+__global__ void __launch_bounds__(W_THREADS) k_scan_w(const __grid_constant__ ScanParams P)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full_bar[W_WARPS][MAX_STAGES];
+
+    constexpr int R = 32 / G;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int S = P.stride;
+    const int stages = P.stages;
+    const uint32_t slab_bytes = (uint32_t)R * (uint32_t)S;
+    const uint32_t stage_bytes = slab_bytes * (HAS_SEQ ? 2u : 1u);
+    uint8_t *wbase = smem + (size_t)w * stages * stage_bytes;
+    uint64_t *bars = full_bar[w];
+    const int64_t ntiles = (P.n + R - 1) / R;
+    const int64_t gw = (int64_t)blockIdx.x * W_WARPS + w, GW = (int64_t)gridDim.x * W_WARPS;
+    const QualK qk = P.qk;
+
+    if (lane == 0) {
+        for (int s = 0; s < stages; s++) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+
+    auto issue = [&](int64_t tile, int s) {
+        const int64_t r0 = tile * R;
+        const int64_t left = P.n - r0;
+        const uint32_t bytes = (uint32_t)(left < R ? left : R) * (uint32_t)S;
+        uint8_t *dst = wbase + (size_t)s * stage_bytes;
+        mbar_arrive_expect_tx(&bars[s], bytes * (HAS_SEQ ? 2u : 1u));
+        bulk_g2s(dst, P.qual + r0 * S, bytes, &bars[s]);
+        if (HAS_SEQ) bulk_g2s(dst + slab_bytes, P.seq + r0 * S, bytes, &bars[s]);
+    };
+    if (lane == 0) {
+        for (int i = 0; i < stages; i++) {
+            const int64_t t = gw + (int64_t)i * GW;
+            if (t < ntiles) issue(t, i);
+        }
+    }
+
+    const int j = lane & (G - 1);
+    const int rr = lane / G;
+    const int rot = (G == 1) ? ((lane & 7) >> P.rot_shift) : 0;
+    const uint32_t row_off = (uint32_t)rr * (uint32_t)S;
+    unsigned kept_local = 0;
+    int s = 0;
+    uint32_t parity = 0;
+
+    for (int64_t tile = gw; tile < ntiles; tile += GW) {
+        mbar_wait(&bars[s], parity);
+        const uint8_t *qrow = wbase + (size_t)s * stage_bytes + row_off;
+        const uint8_t *srow = qrow + slab_bytes;
+        const int64_t g = tile * R + rr;
+        const bool active = g < P.n;
+        int L = 0;
+        if (active) L = P.len ? __ldg(P.len + g) : P.uniform_len;
+        const bool lenbad = active && (L <= 0 || L > S);
+        if (lenbad) L = 0;
+
+        ScanAcc a;
+        a.badq = 0; a.bads = 0; a.lastc = -1; a.lowb = 0; a.low = 0;
+        scan_read<G, MODE, HAS_SEQ>(a, qrow, srow, L, j, rot, qk);
+        if (((a.badq & HI) | a.bads) != 0 || lenbad) note_bad(P.counters, P.index_base + g);
+
+        if (MODE == MODE_TRIM) {
+            const int lastc = group_max<G>(a.lastc);
+            if (j == 0 && active) {
+                const int newlen = trim_newlen(qrow, lastc, L, qk);
+                const bool keep = newlen >= 1 && newlen >= P.min_len;
+                reinterpret_cast<int32_t *>(P.out)[g] = keep ? newlen : -1;
+                kept_local += keep ? 1u : 0u;
+            }
+        } else {
+            const uint32_t low = group_sum<G>(a.low);
+            if (j == 0 && active) {
+                const bool keep = !P.force_drop && !lenbad &&
+                                  (100ll * (long long)low <= (long long)L * (long long)P.pct_keep);
+                reinterpret_cast<uint8_t *>(P.out)[g] = keep ? 1 : 0;
+                kept_local += keep ? 1u : 0u;
+            }
+        }
+
+        __syncwarp();      // all lanes are done reading stage s -> lane 0 may refill it
+        if (lane == 0) {
+            const int64_t nt = tile + (int64_t)stages * GW;
+            if (nt < ntiles) issue(nt, s);
+        }
+        if (++s == stages) { s = 0; parity ^= 1u; }
+    }
+
+    kept_local = __reduce_add_sync(0xffffffffu, kept_local);
+    if (lane == 0 && kept_local) atomicAdd(&P.counters[CNT_OUT], (unsigned long long)kept_local);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -430,8 +564,27 @@ static cudaError_t launch_scan_g(const TilePlan &plan, const ScanParams &p, cuda
     return cudaGetLastError();
 }
 
+template <int MODE, bool HAS_SEQ>
+static cudaError_t launch_scan_w(const TilePlan &plan, const ScanParams &p, cudaStream_t st)
+{
+#define FXG_SCANW_CASE(GV)                                                                         \
+    case GV:                                                                                       \
+        k_scan_w<GV, MODE, HAS_SEQ><<<plan.grid, W_THREADS, plan.smem_bytes, st>>>(p);             \
+        break;
+    switch (plan.g) {
+        FXG_SCANW_CASE(1) FXG_SCANW_CASE(2) FXG_SCANW_CASE(4) FXG_SCANW_CASE(8)
+    default: return cudaErrorInvalidValue;
+    }
+#undef FXG_SCANW_CASE
+    return cudaGetLastError();
+}
+
 cudaError_t launch_scan(int mode, bool has_seq, const TilePlan &plan, const ScanParams &p, cudaStream_t st)
 {
+    if (plan.warp_ring) {
+        if (mode == MODE_TRIM) return has_seq ? launch_scan_w<MODE_TRIM, true>(plan, p, st) : launch_scan_w<MODE_TRIM, false>(plan, p, st);
+        return has_seq ? launch_scan_w<MODE_FILTER, true>(plan, p, st) : launch_scan_w<MODE_FILTER, false>(plan, p, st);
+    }
     if (mode == MODE_TRIM) return has_seq ? launch_scan_g<MODE_TRIM, true>(plan, p, st) : launch_scan_g<MODE_TRIM, false>(plan, p, st);
     return has_seq ? launch_scan_g<MODE_FILTER, true>(plan, p, st) : launch_scan_g<MODE_FILTER, false>(plan, p, st);
 }
@@ -483,6 +636,13 @@ cudaError_t kernels_set_smem_attrs()
     if (e == cudaSuccess) e = set_max_smem(k_revcomp<GV, false>);
     FXG_ATTR_G(1) FXG_ATTR_G(2) FXG_ATTR_G(4) FXG_ATTR_G(8) FXG_ATTR_G(16) FXG_ATTR_G(32)
 #undef FXG_ATTR_G
+#define FXG_ATTR_W(GV)                                                                             \
+    if (e == cudaSuccess) e = set_max_smem(k_scan_w<GV, MODE_TRIM, true>);                         \
+    if (e == cudaSuccess) e = set_max_smem(k_scan_w<GV, MODE_TRIM, false>);                        \
+    if (e == cudaSuccess) e = set_max_smem(k_scan_w<GV, MODE_FILTER, true>);                       \
+    if (e == cudaSuccess) e = set_max_smem(k_scan_w<GV, MODE_FILTER, false>);
+    FXG_ATTR_W(1) FXG_ATTR_W(2) FXG_ATTR_W(4) FXG_ATTR_W(8)
+#undef FXG_ATTR_W
     return e;
 }
 

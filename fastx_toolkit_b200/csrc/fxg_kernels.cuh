@@ -9,6 +9,8 @@ namespace fxg {
 
 constexpr int THREADS = 256;     // threads per CTA for the tile-pipeline kernels
 constexpr int MAX_STAGES = 8;
+constexpr int W_WARPS = 4;       // warps per CTA in the warp-private pipeline kernels
+constexpr int W_THREADS = W_WARPS * 32;
 constexpr int MAX_DYN_SMEM = 227 * 1024 - 1024;   // per-CTA opt-in limit minus the kernels' static smem (barriers)
 
 enum { MODE_TRIM = 0, MODE_FILTER = 1 };
@@ -22,6 +24,8 @@ struct TilePlan {
     int32_t stages;       // smem ring depth
     int32_t grid;         // persistent CTAs
     uint32_t smem_bytes;  // dynamic shared memory per CTA
+    int32_t warp_ring;    // 1: warp-private pipeline kernel (tile = 32/g reads per warp), 0: CTA-tile kernel
+    int32_t rot_shift;    // warp-ring, g == 1: lane (l&7)>>rot_shift starts that many chunks into its read
 };
 
 struct ScanParams {
@@ -33,6 +37,7 @@ struct ScanParams {
     int64_t n;
     int32_t tile_reads;
     int32_t stages;
+    int32_t rot_shift;
     QualK qk;
     int32_t min_len;      // trim: -l
     int32_t pct_keep;     // filter: 100 - p   (keep iff 100*low <= L*pct_keep)

@@ -1,0 +1,56 @@
+#!/usr/bin/env python
+"""GPU tuning sweep for K-TRIM / K-FILTER / K-REVCOMP (FXG_TUNE=ring,g,stages,ctas). Prints GB/s (algorithmic)."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import fastx_toolkit_b200 as F  # noqa: E402
+
+L, S = int(os.environ.get("TL", 150)), None
+S = (L + 15) // 16 * 16
+n = int(os.environ.get("TN", 50_000_000))
+ctx = F.Context(0)
+st = torch.cuda.current_stream()
+ctx.set_stream(st.cuda_stream)
+dseq = torch.empty((n, S), dtype=torch.uint8, device="cuda")
+dqual = torch.empty((n, S), dtype=torch.uint8, device="cuda")
+ctx.synth_dev(dseq, dqual, n, L, S, 20260926, 0, 33)
+out = torch.empty(n, dtype=torch.int32, device="cuda")
+keep = torch.empty(n, dtype=torch.uint8, device="cuda")
+b = ctx.batch(dseq, dqual, n, S, L)
+torch.cuda.synchronize()
+ref = None
+
+
+def timeit(fn, reps=5):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(reps):
+        fn()
+    e1.record(st)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+configs = sys.argv[1:] or ["0,0,0,0", "1,1,1,0", "1,1,2,0", "1,1,3,0", "1,2,1,0", "1,2,2,0", "1,2,3,0", "1,1,1,3", "1,1,1,4", "1,1,2,2", "1,2,2,4", "1,2,2,6"]
+for cfg in configs:
+    os.environ["FXG_TUNE"] = cfg
+    try:
+        ms = timeit(lambda: ctx.trim_dev(b, 33, 20, 20, out))
+        cur = out.clone()
+        if ref is None:
+            ref = cur
+        ok = bool(torch.equal(cur, ref))
+        msf = timeit(lambda: ctx.filter_dev(b, 33, 20, 90, keep))
+        print("FXG_TUNE=%-10s trim %.3f ms %7.1f GB/s (%.2f Gr/s) same=%s | filter %.3f ms %7.1f GB/s" %
+              (cfg, ms, n * (2 * L + 4) / ms / 1e6, n / ms / 1e6, ok, msf, n * (2 * L + 1) / msf / 1e6), flush=True)
+    except Exception as e:  # noqa: BLE001
+        print("FXG_TUNE=%s failed: %s" % (cfg, e), flush=True)
+rep = ctx.sync()
+print("first_bad", rep.first_bad_read)
