@@ -208,7 +208,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     ctx = F.Context(local_rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # all timed launches and the timing events share this stream
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
 
     n = args.reads

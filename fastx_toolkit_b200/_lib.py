@@ -48,6 +48,7 @@ def lib():
         "fxg_last_error": (C.c_char_p, [vp]),
         "fxg_device_info": (i32, [vp, C.POINTER(i32), C.POINTER(sz), C.POINTER(i32), C.POINTER(i32)]),
         "fxg_set_stream": (i32, [vp, vp]),
+        "fxg_use_own_stream": (i32, [vp]),
         "fxg_sync": (i32, [vp]),
         "fxg_get_report": (i32, [vp, RP]),
         "fxg_report_reset": (i32, [vp]),
@@ -117,7 +118,11 @@ class Context:
 
     # ---- plumbing
     def set_stream(self, stream_handle):
-        self._ck(self.L.fxg_set_stream(self.h, stream_handle))
+        """Adopt a cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream; 0 = default stream)."""
+        self._ck(self.L.fxg_set_stream(self.h, C.c_void_p(stream_handle)))
+
+    def use_own_stream(self):
+        self._ck(self.L.fxg_use_own_stream(self.h))
 
     def set_tuning(self, tile_reads=0, stages=0, ctas_per_sm=0):
         self._ck(self.L.fxg_set_tuning(self.h, tile_reads, stages, ctas_per_sm))

@@ -138,7 +138,14 @@ extern "C" int fxg_device_info(fxg_ctx *ctx, int *sm_count, size_t *hbm_bytes, i
 extern "C" int fxg_set_stream(fxg_ctx *ctx, void *cuda_stream)
 {
     if (!ctx) return FXG_ERR_ARG;
-    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return FXG_OK;
+}
+
+extern "C" int fxg_use_own_stream(fxg_ctx *ctx)
+{
+    if (!ctx) return FXG_ERR_ARG;
+    ctx->stream = ctx->own_stream;
     return FXG_OK;
 }
 

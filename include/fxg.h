@@ -66,7 +66,9 @@ void        fxg_destroy(fxg_ctx *ctx);
 const char *fxg_strerror(int code);
 const char *fxg_last_error(const fxg_ctx *ctx);          /* detail of the last failure           */
 int         fxg_device_info(fxg_ctx *ctx, int *sm_count, size_t *hbm_bytes, int *cc_major, int *cc_minor);
-int         fxg_set_stream(fxg_ctx *ctx, void *cuda_stream);  /* adopt caller's stream (NULL = own) */
+int         fxg_set_stream(fxg_ctx *ctx, void *cuda_stream);  /* adopt the caller's cudaStream_t for *_dev calls
+                                                                 (NULL is the legacy default stream)      */
+int         fxg_use_own_stream(fxg_ctx *ctx);                 /* back to the context's private stream  */
 int         fxg_sync(fxg_ctx *ctx);                      /* wait, then refresh the report        */
 int         fxg_get_report(fxg_ctx *ctx, fxg_report *out);
 int         fxg_report_reset(fxg_ctx *ctx);

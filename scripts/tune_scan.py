@@ -13,7 +13,8 @@ L, S = int(os.environ.get("TL", 150)), None
 S = (L + 15) // 16 * 16
 n = int(os.environ.get("TN", 50_000_000))
 ctx = F.Context(0)
-st = torch.cuda.current_stream()
+st = torch.cuda.Stream()
+torch.cuda.set_stream(st)
 ctx.set_stream(st.cuda_stream)
 dseq = torch.empty((n, S), dtype=torch.uint8, device="cuda")
 dqual = torch.empty((n, S), dtype=torch.uint8, device="cuda")
