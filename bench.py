@@ -306,7 +306,7 @@ def main():
             "timing": "CUDA events on the launch stream, barrier+synchronize both sides, max over ranks",
         },
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "fxg::k_scan<G=2,TRIM,HAS_SEQ>", "algorithmic_bytes_per_read": ALGO_BYTES_PER_READ,
+                     "traffic": None, "kernel": "fxg::k_scan_w<G=1,TRIM,HAS_SEQ> (warp-private TMA ring, lane per read)", "algorithmic_bytes_per_read": ALGO_BYTES_PER_READ,
                      "kernel_ms": kernel_ms, "peak_source": peak_src},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * ne * 2 * STRIDE, "d2h_bytes_per_step": world * ne * 4,
                 "reads_per_step_per_gpu": ne, "api": "fxg_trim_host (pinned host slabs -> H2D -> K-TRIM -> D2H int32 per read)",

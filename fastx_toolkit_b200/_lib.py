@@ -21,6 +21,13 @@ class Batch(C.Structure):
                 ("uniform_len", C.c_int32), ("stride", C.c_int32), ("n", C.c_int64)]
 
 
+class ClipOpts(C.Structure):
+    """struct fxg_clip_opts"""
+    _fields_ = [("adapter", C.c_char_p), ("min_length", C.c_int32), ("keep_delta", C.c_int32),
+                ("discard_non_clipped", C.c_int32), ("discard_clipped", C.c_int32), ("discard_unknown", C.c_int32),
+                ("min_adapter_len", C.c_int32)]
+
+
 class Report(C.Structure):
     """struct fxg_report"""
     _fields_ = [("n_in", C.c_int64), ("n_out", C.c_int64), ("first_bad_read", C.c_int64), ("aux", C.c_int64 * 6)]
@@ -70,6 +77,10 @@ def lib():
         "fxg_filter_host": (i32, [vp, BP, i32, i32, i32, vp, RP]),
         "fxg_revcomp_dev": (i32, [vp, BP, i32, vp, vp, i64]),
         "fxg_revcomp_host": (i32, [vp, BP, i32, vp, vp, RP]),
+        "fxg_stats_accum_dev": (i32, [vp, BP, i32, vp, C.c_int32, vp, i64]),
+        "fxg_stats_accum_host": (i32, [vp, BP, i32, vp, C.c_int32, vp, RP]),
+        "fxg_clip_dev": (i32, [vp, BP, vp, i32, C.POINTER(ClipOpts), vp, vp, vp, i64]),
+        "fxg_clip_host": (i32, [vp, BP, vp, i32, C.POINTER(ClipOpts), vp, vp, RP]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -165,7 +176,25 @@ class Context:
     def revcomp_dev(self, b, q_offset, out_seq, out_qual, index_base=0):
         self._ck(self.L.fxg_revcomp_dev(self.h, C.byref(b), q_offset, _ptr(out_seq), _ptr(out_qual), index_base))
 
+    def stats_accum_dev(self, b, q_offset, hist, max_cycles, weight=None, index_base=0):
+        self._ck(self.L.fxg_stats_accum_dev(self.h, C.byref(b), q_offset, _ptr(hist), max_cycles, _ptr(weight), index_base))
+
+    def clip_dev(self, b, widths, q_offset, opts, out_len, out_class=None, out_cut=None, index_base=0):
+        self._ck(self.L.fxg_clip_dev(self.h, C.byref(b), _ptr(widths), q_offset, C.byref(opts), _ptr(out_len),
+                                     _ptr(out_class), _ptr(out_cut), index_base))
+
     # ---- ops (host pointers; copies are inside the call)
+    def stats_accum_host(self, b, q_offset, hist_dev, max_cycles, weight=None):
+        r = Report()
+        self._ck(self.L.fxg_stats_accum_host(self.h, C.byref(b), q_offset, _ptr(hist_dev), max_cycles, _ptr(weight), C.byref(r)))
+        return r
+
+    def clip_host(self, b, widths, q_offset, opts, out_len, out_class=None):
+        r = Report()
+        self._ck(self.L.fxg_clip_host(self.h, C.byref(b), _ptr(widths), q_offset, C.byref(opts), _ptr(out_len),
+                                      _ptr(out_class), C.byref(r)))
+        return r
+
     def trim_host(self, b, q_offset, threshold, min_len, out_len):
         r = Report()
         self._ck(self.L.fxg_trim_host(self.h, C.byref(b), q_offset, threshold, min_len, _ptr(out_len), C.byref(r)))

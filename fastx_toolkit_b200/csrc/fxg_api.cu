@@ -31,8 +31,8 @@ struct fxg_ctx {
     char err[256];
     // host-pipeline resources (grow-only)
     cudaStream_t lane_stream[PIPE_LANES];
-    void *lane_buf[PIPE_LANES][4];     // seq, qual, out0, out1
-    size_t lane_cap[PIPE_LANES][4];
+    void *lane_buf[PIPE_LANES][6];     // seq, qual, len, aux, out0, out1
+    size_t lane_cap[PIPE_LANES][6];
 };
 
 #define CK(ctx, call)                                                                              \
@@ -105,7 +105,7 @@ extern "C" int fxg_init(int device, fxg_ctx **out)
         if ((e = cudaStreamCreateWithFlags(&ctx->lane_stream[l], cudaStreamNonBlocking)) != cudaSuccess) { free(ctx); INIT_FAIL("cudaStreamCreate", e); }
     if ((e = cudaMalloc(&ctx->d_counters, CNT_WORDS * sizeof(unsigned long long))) != cudaSuccess) { free(ctx); INIT_FAIL("cudaMalloc", e); }
     if ((e = cudaMallocHost(&ctx->h_counters, CNT_WORDS * sizeof(unsigned long long))) != cudaSuccess) { free(ctx); INIT_FAIL("cudaMallocHost", e); }
-    if ((e = kernels_set_smem_attrs()) != cudaSuccess) { free(ctx); INIT_FAIL("cudaFuncSetAttribute(max dynamic smem)", e); }
+    if ((e = kernels_set_smem_attrs()) != cudaSuccess || (e = stats_set_smem_attrs()) != cudaSuccess) { free(ctx); INIT_FAIL("cudaFuncSetAttribute(max dynamic smem)", e); }
     *out = ctx;
     return fxg_report_reset(ctx);
 }
@@ -116,7 +116,7 @@ extern "C" void fxg_destroy(fxg_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (int l = 0; l < PIPE_LANES; l++) {
-        for (int b = 0; b < 4; b++) if (ctx->lane_buf[l][b]) cudaFree(ctx->lane_buf[l][b]);
+        for (int b = 0; b < 6; b++) if (ctx->lane_buf[l][b]) cudaFree(ctx->lane_buf[l][b]);
         cudaStreamDestroy(ctx->lane_stream[l]);
     }
     cudaFree(ctx->d_counters);
@@ -291,13 +291,16 @@ static int make_plan(fxg_ctx *ctx, const fxg_batch *b, int nslabs, int extra_sta
         }
         if (g) {
             const size_t wstage = (size_t)(32 / g) * per_read;
-            int stages = t_stages ? t_stages : 2;
+            // one stage per warp: the other warps of the SM (16 with 4 CTAs) cover a warp's wait for HBM;
+            // measured on B200 (150 bp): 1 stage x 4 CTAs 6276 GB/s, 2 stages x 2 CTAs 6082 GB/s
+            int stages = t_stages ? t_stages : 1;
             while (stages > 1 && (size_t)(stages + extra_stage_bufs) * wstage * W_WARPS > smem_max) stages--;
             const size_t smem = (size_t)(stages + extra_stage_bufs) * wstage * W_WARPS;
             if (smem <= smem_max) {
                 int ctas = t_ctas ? t_ctas : (int)((smem_max + 1024) / (smem + 1024));
                 if (ctas < 1) ctas = 1;
-                if (ctas > 12) ctas = 12;                       // 48 warps per SM is plenty
+                if (!t_ctas && ctas > 4) ctas = 4;
+                if (ctas > 12) ctas = 12;
                 const int64_t ntiles = (b->n + (32 / g) - 1) / (32 / g);
                 int64_t grid = (int64_t)ctx->sm_count * ctas;
                 const int64_t need = (ntiles + W_WARPS - 1) / W_WARPS;
@@ -447,10 +450,104 @@ extern "C" int fxg_revcomp_dev(fxg_ctx *ctx, const fxg_batch *b, int q_offset, u
     return revcomp_enqueue(ctx, b, q_offset, out_seq, out_qual, index_base, ctx->stream);
 }
 
+// ---- quality stats ---------------------------------------------------------------------------------
+static int stats_enqueue(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint64_t *hist, int32_t max_cycles,
+                         const int32_t *weight, int64_t index_base, cudaStream_t st)
+{
+    if (b->n == 0) return FXG_OK;
+    StatsParams p;
+    memset(&p, 0, sizeof(p));
+    p.seq = b->seq; p.qual = b->qual; p.len = b->len; p.weight = weight; p.uniform_len = b->uniform_len;
+    p.stride = b->stride; p.n = b->n; p.qk = make_qualk(q_offset, 0); p.max_cycles = max_cycles;
+    p.hist = (unsigned long long *)hist; p.index_base = index_base; p.counters = ctx->d_counters;
+    const int lmax = b->len ? b->stride : b->uniform_len;
+    const int words = (lmax + 3) / 4;
+    const int nw_pass = words < ST_MAXW ? words : ST_MAXW;
+    const size_t hist_al = (((size_t)nw_pass * ST_WBLK) + 127) & ~(size_t)127;
+    int t_ring, t_g, t_stages, t_ctas;
+    env_tune(&t_ring, &t_g, &t_stages, &t_ctas);
+    const int stages = t_stages > 0 ? t_stages : 1;
+    long rfit = ((long)MAX_DYN_SMEM - (long)hist_al) / ST_WARPS / stages / (2L * b->stride);
+    if (rfit > 32) rfit = 32;
+    const bool fast = b->qual && !weight && rfit >= 8 && t_ring != 0;
+    if (!fast) {
+        CK(ctx, launch_stats_simple(p, ctx->sm_count, st));
+        ctx->launches++;
+    } else {
+        p.tile_reads = (int)rfit; p.stages = stages;
+        const uint32_t smem = (uint32_t)(hist_al + (size_t)ST_WARPS * stages * 2 * b->stride * rfit);
+        const int64_t ntiles = (b->n + rfit - 1) / rfit;
+        int64_t grid = ctx->sm_count;
+        const int64_t need = (ntiles + ST_WARPS - 1) / ST_WARPS;
+        if (grid > need) grid = need;
+        for (int w0 = 0; w0 < words; w0 += nw_pass) {     // reads longer than 160 bases: one pass per 160 cycles
+            p.w0 = w0; p.nw = (words - w0 < nw_pass) ? (words - w0) : nw_pass;
+            CK(ctx, launch_stats(p, (int)grid, smem, st));
+            ctx->launches++;
+        }
+    }
+    ctx->report.n_in += b->n;
+    return FXG_OK;
+}
+
+extern "C" int fxg_stats_accum_dev(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint64_t *hist, int32_t max_cycles,
+                                   const int32_t *weight, int64_t index_base)
+{
+    int rc = check_batch(ctx, b, true, false, q_offset);
+    if (rc) return rc;
+    if (!hist || max_cycles <= 0) return arg_error(ctx, "hist is NULL or max_cycles <= 0");
+    CK(ctx, cudaSetDevice(ctx->device));
+    return stats_enqueue(ctx, b, q_offset, hist, max_cycles, weight, index_base, ctx->stream);
+}
+
+// ---- clipper ---------------------------------------------------------------------------------------
+static int clip_enqueue(fxg_ctx *ctx, const fxg_batch *b, const int32_t *width, int q_offset, const fxg_clip_opts *o,
+                        int32_t *out_len, uint8_t *out_class, int32_t *out_cut, int64_t index_base, cudaStream_t st)
+{
+    if (b->n == 0) return FXG_OK;
+    ClipParams p;
+    memset(&p, 0, sizeof(p));
+    p.seq = b->seq; p.qual = b->qual; p.len = b->len; p.width = width; p.uniform_len = b->uniform_len;
+    p.stride = b->stride; p.n = b->n; p.qk = make_qualk(q_offset, 0);
+    p.alen = (int)strlen(o->adapter);
+    memcpy(p.adapter, o->adapter, (size_t)p.alen);
+    p.min_length = o->min_length; p.keep_delta = o->keep_delta; p.discard_non_clipped = o->discard_non_clipped;
+    p.discard_clipped = o->discard_clipped; p.discard_unknown = o->discard_unknown; p.min_adapter_len = o->min_adapter_len;
+    p.out_len = out_len; p.out_class = out_class; p.out_cut = out_cut; p.index_base = index_base; p.counters = ctx->d_counters;
+    CK(ctx, launch_clip(p, ctx->sm_count, st));
+    ctx->launches++;
+    ctx->report.n_in += b->n;
+    return FXG_OK;
+}
+
+static int check_clip_opts(fxg_ctx *ctx, const fxg_clip_opts *o)
+{
+    if (!o || !o->adapter) return arg_error(ctx, "clip options / adapter is NULL");
+    const size_t al = strlen(o->adapter);
+    if (al == 0 || al >= FXG_MAX_ADAPTER) return arg_error(ctx, "adapter length must be 1..99");
+    if (o->keep_delta < 0) return arg_error(ctx, "keep_delta < 0");
+    return FXG_OK;
+}
+
+extern "C" int fxg_clip_dev(fxg_ctx *ctx, const fxg_batch *b, const int32_t *width, int q_offset, const fxg_clip_opts *o,
+                            int32_t *out_len, uint8_t *out_class, int32_t *out_cut, int64_t index_base)
+{
+    int rc = check_batch(ctx, b, true, false, q_offset);
+    if (rc) return rc;
+    if ((rc = check_clip_opts(ctx, o))) return rc;
+    if (!out_len) return arg_error(ctx, "out_len is NULL");
+    CK(ctx, cudaSetDevice(ctx->device));
+    return clip_enqueue(ctx, b, width, q_offset, o, out_len, out_class, out_cut, index_base, ctx->stream);
+}
+
 // ---- host-buffer pipelines ---------------------------------------------------------------------------
+// Chunks of the host slab travel H2D -> kernel -> D2H on PIPE_LANES side streams, so the copy of one
+// chunk overlaps the kernel and the result copy of its neighbours (both copy engines busy).
+enum { SLOT_SEQ = 0, SLOT_QUAL, SLOT_LEN, SLOT_AUX, SLOT_OUT0, SLOT_OUT1 };
+
 static int lane_reserve(fxg_ctx *ctx, int lane, int slot, size_t bytes)
 {
-    if (ctx->lane_cap[lane][slot] >= bytes) return FXG_OK;
+    if (bytes == 0 || ctx->lane_cap[lane][slot] >= bytes) return FXG_OK;
     if (ctx->lane_buf[lane][slot]) cudaFree(ctx->lane_buf[lane][slot]);
     ctx->lane_buf[lane][slot] = NULL;
     ctx->lane_cap[lane][slot] = 0;
@@ -469,58 +566,76 @@ static int64_t chunk_reads(const fxg_batch *b)
     return cr;
 }
 
-enum { HOST_TRIM, HOST_FILTER, HOST_REVCOMP };
+enum { HOST_TRIM, HOST_FILTER, HOST_REVCOMP, HOST_STATS, HOST_CLIP };
 
-static int host_pipeline(fxg_ctx *ctx, int op, const fxg_batch *b, int q_offset, int a0, int a1,
-                         void *out0, void *out1, fxg_report *report)
+struct HostOp {
+    int op;
+    int q_offset, a0, a1;
+    void *out0, *out1;                 // host result arrays (op specific)
+    const int32_t *aux_host;           // stats: weights, clip: matrix widths (may be NULL)
+    uint64_t *hist_dev; int32_t max_cycles;
+    const fxg_clip_opts *clip;
+};
+
+static int host_pipeline(fxg_ctx *ctx, const fxg_batch *b, const HostOp &h, fxg_report *report)
 {
     CK(ctx, cudaSetDevice(ctx->device));
     int rc = fxg_report_reset(ctx);
     if (rc) return rc;
     const int64_t cr = chunk_reads(b);
     const size_t S = (size_t)b->stride;
+    const bool has_seq = b->seq != NULL, has_qual = b->qual != NULL;
     int lane = 0;
     for (int64_t r0 = 0; r0 < b->n; r0 += cr, lane = (lane + 1) % PIPE_LANES) {
         const int64_t nr = (b->n - r0 < cr) ? (b->n - r0) : cr;
-        cudaStream_t st = ctx->lane_stream[lane];
-        // the lane's previous chunk must be fully drained before its buffers are reused:
-        // stream order already guarantees that (copies and kernels of one lane are serialized).
-        const bool has_seq = b->seq != NULL, has_qual = b->qual != NULL;
-        if (has_seq && (rc = lane_reserve(ctx, lane, 0, (size_t)cr * S))) return rc;
-        if (has_qual && (rc = lane_reserve(ctx, lane, 1, (size_t)cr * S))) return rc;
+        cudaStream_t st = ctx->lane_stream[lane];   // one lane's copies and kernels are stream-ordered
         size_t o0 = 0, o1 = 0;
-        if (op == HOST_TRIM) o0 = (size_t)cr * sizeof(int32_t);
-        else if (op == HOST_FILTER) o0 = (size_t)cr;
-        else { o0 = (size_t)cr * S; o1 = has_qual ? (size_t)cr * S : 0; }
-        const size_t o1_al = (o1 + 15) & ~(size_t)15;
-        const size_t slot3 = o1_al + (b->len ? (size_t)cr * sizeof(int32_t) + 16 : 0);   // out1 | lengths
-        if ((rc = lane_reserve(ctx, lane, 2, o0))) return rc;
-        if (slot3 && (rc = lane_reserve(ctx, lane, 3, slot3))) return rc;
+        if (h.op == HOST_TRIM) o0 = (size_t)cr * sizeof(int32_t);
+        else if (h.op == HOST_FILTER) o0 = (size_t)cr;
+        else if (h.op == HOST_REVCOMP) { o0 = (size_t)cr * S; o1 = has_qual ? (size_t)cr * S : 0; }
+        else if (h.op == HOST_CLIP) { o0 = (size_t)cr * sizeof(int32_t); o1 = h.out1 ? (size_t)cr : 0; }
+        if (has_seq && (rc = lane_reserve(ctx, lane, SLOT_SEQ, (size_t)cr * S))) return rc;
+        if (has_qual && (rc = lane_reserve(ctx, lane, SLOT_QUAL, (size_t)cr * S))) return rc;
+        if (b->len && (rc = lane_reserve(ctx, lane, SLOT_LEN, (size_t)cr * sizeof(int32_t)))) return rc;
+        if (h.aux_host && (rc = lane_reserve(ctx, lane, SLOT_AUX, (size_t)cr * sizeof(int32_t)))) return rc;
+        if ((rc = lane_reserve(ctx, lane, SLOT_OUT0, o0))) return rc;
+        if ((rc = lane_reserve(ctx, lane, SLOT_OUT1, o1))) return rc;
 
-        uint8_t *dseq = (uint8_t *)ctx->lane_buf[lane][0], *dqual = (uint8_t *)ctx->lane_buf[lane][1];
+        uint8_t *dseq = (uint8_t *)ctx->lane_buf[lane][SLOT_SEQ], *dqual = (uint8_t *)ctx->lane_buf[lane][SLOT_QUAL];
+        int32_t *dlen = (int32_t *)ctx->lane_buf[lane][SLOT_LEN], *daux = (int32_t *)ctx->lane_buf[lane][SLOT_AUX];
+        void *d0 = ctx->lane_buf[lane][SLOT_OUT0], *d1 = ctx->lane_buf[lane][SLOT_OUT1];
         if (has_seq) CK(ctx, cudaMemcpyAsync(dseq, b->seq + (size_t)r0 * S, (size_t)nr * S, cudaMemcpyHostToDevice, st));
         if (has_qual) CK(ctx, cudaMemcpyAsync(dqual, b->qual + (size_t)r0 * S, (size_t)nr * S, cudaMemcpyHostToDevice, st));
-        int32_t *dlen = NULL;
+        if (b->len) CK(ctx, cudaMemcpyAsync(dlen, b->len + r0, (size_t)nr * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        if (h.aux_host) CK(ctx, cudaMemcpyAsync(daux, h.aux_host + r0, (size_t)nr * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         fxg_batch db = *b;
         db.seq = has_seq ? dseq : NULL;
         db.qual = has_qual ? dqual : NULL;
+        db.len = b->len ? dlen : NULL;
         db.n = nr;
-        if (b->len) {
-            dlen = (int32_t *)((uint8_t *)ctx->lane_buf[lane][3] + o1_al);   // lengths ride behind out1
-            CK(ctx, cudaMemcpyAsync(dlen, b->len + r0, (size_t)nr * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-            db.len = dlen;
-        }
-        void *d0 = ctx->lane_buf[lane][2], *d1 = ctx->lane_buf[lane][3];
-        if (op == HOST_TRIM) {
-            if ((rc = scan_enqueue(ctx, MODE_TRIM, &db, q_offset, a0, a1, 0, d0, r0, st))) return rc;
-            CK(ctx, cudaMemcpyAsync((int32_t *)out0 + r0, d0, (size_t)nr * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        } else if (op == HOST_FILTER) {
-            if ((rc = scan_enqueue(ctx, MODE_FILTER, &db, q_offset, a0, 0, a1, d0, r0, st))) return rc;
-            CK(ctx, cudaMemcpyAsync((uint8_t *)out0 + r0, d0, (size_t)nr, cudaMemcpyDeviceToHost, st));
-        } else {
-            if ((rc = revcomp_enqueue(ctx, &db, q_offset, (uint8_t *)d0, has_qual ? (uint8_t *)d1 : NULL, r0, st))) return rc;
-            CK(ctx, cudaMemcpyAsync((uint8_t *)out0 + (size_t)r0 * S, d0, (size_t)nr * S, cudaMemcpyDeviceToHost, st));
-            if (has_qual) CK(ctx, cudaMemcpyAsync((uint8_t *)out1 + (size_t)r0 * S, d1, (size_t)nr * S, cudaMemcpyDeviceToHost, st));
+        switch (h.op) {
+        case HOST_TRIM:
+            if ((rc = scan_enqueue(ctx, MODE_TRIM, &db, h.q_offset, h.a0, h.a1, 0, d0, r0, st))) return rc;
+            CK(ctx, cudaMemcpyAsync((int32_t *)h.out0 + r0, d0, (size_t)nr * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            break;
+        case HOST_FILTER:
+            if ((rc = scan_enqueue(ctx, MODE_FILTER, &db, h.q_offset, h.a0, 0, h.a1, d0, r0, st))) return rc;
+            CK(ctx, cudaMemcpyAsync((uint8_t *)h.out0 + r0, d0, (size_t)nr, cudaMemcpyDeviceToHost, st));
+            break;
+        case HOST_REVCOMP:
+            if ((rc = revcomp_enqueue(ctx, &db, h.q_offset, (uint8_t *)d0, has_qual ? (uint8_t *)d1 : NULL, r0, st))) return rc;
+            CK(ctx, cudaMemcpyAsync((uint8_t *)h.out0 + (size_t)r0 * S, d0, (size_t)nr * S, cudaMemcpyDeviceToHost, st));
+            if (has_qual) CK(ctx, cudaMemcpyAsync((uint8_t *)h.out1 + (size_t)r0 * S, d1, (size_t)nr * S, cudaMemcpyDeviceToHost, st));
+            break;
+        case HOST_STATS:
+            if ((rc = stats_enqueue(ctx, &db, h.q_offset, h.hist_dev, h.max_cycles, h.aux_host ? daux : NULL, r0, st))) return rc;
+            break;
+        case HOST_CLIP:
+            if ((rc = clip_enqueue(ctx, &db, h.aux_host ? daux : NULL, h.q_offset, h.clip, (int32_t *)d0, h.out1 ? (uint8_t *)d1 : NULL,
+                                   NULL, r0, st))) return rc;
+            CK(ctx, cudaMemcpyAsync((int32_t *)h.out0 + r0, d0, (size_t)nr * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            if (h.out1) CK(ctx, cudaMemcpyAsync((uint8_t *)h.out1 + r0, d1, (size_t)nr, cudaMemcpyDeviceToHost, st));
+            break;
         }
     }
     for (int l = 0; l < PIPE_LANES; l++) CK(ctx, cudaStreamSynchronize(ctx->lane_stream[l]));
@@ -536,7 +651,9 @@ extern "C" int fxg_trim_host(fxg_ctx *ctx, const fxg_batch *b, int q_offset, int
     int rc = check_batch(ctx, b, false, true, q_offset);
     if (rc) return rc;
     if (!out_len) return arg_error(ctx, "out_len is NULL");
-    return host_pipeline(ctx, HOST_TRIM, b, q_offset, threshold, min_len, out_len, NULL, report);
+    HostOp h = {};
+    h.op = HOST_TRIM; h.q_offset = q_offset; h.a0 = threshold; h.a1 = min_len; h.out0 = out_len;
+    return host_pipeline(ctx, b, h, report);
 }
 
 extern "C" int fxg_filter_host(fxg_ctx *ctx, const fxg_batch *b, int q_offset, int min_quality, int min_percent,
@@ -546,7 +663,9 @@ extern "C" int fxg_filter_host(fxg_ctx *ctx, const fxg_batch *b, int q_offset, i
     if (rc) return rc;
     if (!keep) return arg_error(ctx, "keep is NULL");
     if (min_percent < 0 || min_percent > 100) return arg_error(ctx, "min_percent must be 0..100");
-    return host_pipeline(ctx, HOST_FILTER, b, q_offset, min_quality, min_percent, keep, NULL, report);
+    HostOp h = {};
+    h.op = HOST_FILTER; h.q_offset = q_offset; h.a0 = min_quality; h.a1 = min_percent; h.out0 = keep;
+    return host_pipeline(ctx, b, h, report);
 }
 
 extern "C" int fxg_revcomp_host(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint8_t *out_seq, uint8_t *out_qual,
@@ -555,5 +674,30 @@ extern "C" int fxg_revcomp_host(fxg_ctx *ctx, const fxg_batch *b, int q_offset, 
     int rc = check_batch(ctx, b, true, false, q_offset);
     if (rc) return rc;
     if (!out_seq || (b->qual && !out_qual)) return arg_error(ctx, "output slab is NULL");
-    return host_pipeline(ctx, HOST_REVCOMP, b, q_offset, 0, 0, out_seq, out_qual, report);
+    HostOp h = {};
+    h.op = HOST_REVCOMP; h.q_offset = q_offset; h.out0 = out_seq; h.out1 = out_qual;
+    return host_pipeline(ctx, b, h, report);
+}
+
+extern "C" int fxg_stats_accum_host(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint64_t *hist_dev, int32_t max_cycles,
+                                    const int32_t *weight_host, fxg_report *report)
+{
+    int rc = check_batch(ctx, b, true, false, q_offset);
+    if (rc) return rc;
+    if (!hist_dev || max_cycles <= 0) return arg_error(ctx, "hist is NULL or max_cycles <= 0");
+    HostOp h = {};
+    h.op = HOST_STATS; h.q_offset = q_offset; h.hist_dev = hist_dev; h.max_cycles = max_cycles; h.aux_host = weight_host;
+    return host_pipeline(ctx, b, h, report);
+}
+
+extern "C" int fxg_clip_host(fxg_ctx *ctx, const fxg_batch *b, const int32_t *width_host, int q_offset, const fxg_clip_opts *o,
+                             int32_t *out_len, uint8_t *out_class, fxg_report *report)
+{
+    int rc = check_batch(ctx, b, true, false, q_offset);
+    if (rc) return rc;
+    if ((rc = check_clip_opts(ctx, o))) return rc;
+    if (!out_len) return arg_error(ctx, "out_len is NULL");
+    HostOp h = {};
+    h.op = HOST_CLIP; h.q_offset = q_offset; h.clip = o; h.aux_host = width_host; h.out0 = out_len; h.out1 = out_class;
+    return host_pipeline(ctx, b, h, report);
 }

@@ -72,6 +72,60 @@ struct SynthParams {
     int32_t kind, q_offset;
 };
 
+// ---- K-STATS (fxg_stats.cu) ------------------------------------------------------------------------
+// shared-memory histogram geometry: [word w][byte k][nuc A,C,G,T][q' 0..63] u32 counters; a word block
+// is padded by 36 bytes so that lanes working on consecutive words with equal q' hit distinct banks
+constexpr int ST_WARPS = 6;
+constexpr int ST_THREADS = ST_WARPS * 32;
+constexpr int ST_QWIN = 64;                       // q' = q+15 in [0,64) lives in shared memory
+constexpr int ST_KBLK = 4 * ST_QWIN * 4;          // bytes per (word, byte k): 4 nucs x 64 x u32 = 1024
+constexpr int ST_WBLK = 4 * ST_KBLK + 36;         // bytes per word block
+constexpr int ST_MAXW = 40;                       // words (4 cycles each) per pass: 160 cycles
+
+struct StatsParams {
+    const uint8_t *seq;
+    const uint8_t *qual;      // NULL: FASTA (simple kernel only)
+    const int32_t *len;
+    const int32_t *weight;    // NULL: 1 per read (simple kernel only)
+    int32_t uniform_len;
+    int32_t stride;
+    int64_t n;
+    int32_t tile_reads;       // reads per warp tile (<= 32)
+    int32_t stages;
+    QualK qk;
+    int32_t w0;               // first 4-cycle word covered by this pass
+    int32_t nw;               // words covered (<= ST_MAXW)
+    int32_t max_cycles;
+    unsigned long long *hist; // u64 [max_cycles][5][109]
+    int64_t index_base;
+    unsigned long long *counters;
+};
+
+// ---- K-CLIP (fxg_clip.cu) ---------------------------------------------------------------------------
+struct ClipParams {
+    const uint8_t *seq;
+    const uint8_t *qual;      // may be NULL
+    const int32_t *len;
+    const int32_t *width;     // DP matrix width per read (>= len); NULL: width = len
+    int32_t uniform_len;
+    int32_t stride;
+    int64_t n;
+    QualK qk;
+    uint8_t adapter[104];
+    int32_t alen;
+    int32_t min_length, keep_delta, discard_non_clipped, discard_clipped, discard_unknown, min_adapter_len;
+    int32_t *out_len;         // emitted length, -1 when discarded
+    uint8_t *out_class;       // may be NULL
+    int32_t *out_cut;         // may be NULL
+    int64_t index_base;
+    unsigned long long *counters;
+};
+
+cudaError_t launch_stats(const StatsParams &p, int grid, uint32_t smem_bytes, cudaStream_t st);
+cudaError_t launch_stats_simple(const StatsParams &p, int sm_count, cudaStream_t st);
+cudaError_t launch_clip(const ClipParams &p, int sm_count, cudaStream_t st);
+cudaError_t stats_set_smem_attrs();
+
 cudaError_t launch_scan(int mode, bool has_seq, const TilePlan &plan, const ScanParams &p, cudaStream_t st);
 cudaError_t launch_revcomp(bool has_qual, const TilePlan &plan, const RevcompParams &p, cudaStream_t st);
 cudaError_t launch_synth(const SynthParams &p, cudaStream_t st);

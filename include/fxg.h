@@ -114,6 +114,44 @@ int fxg_revcomp_dev (fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint8_t *ou
 int fxg_revcomp_host(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint8_t *out_seq_host,
                      uint8_t *out_qual_host, fxg_report *report);
 
+/* ---- a5: fastx_quality_stats accumulation (src/fastx_quality_stats/fastx_quality_stats.c:166-216)
+ * hist[cycle][nuc][q+15] += 1 (u64, nuc order A,C,G,T,N, FXG_QBINS bins) for every base of every read;
+ * the table lives in device memory (fxg_alloc_device, zeroed by the caller) and is ACCUMULATED, so it can
+ * be all-reduced across GPUs before the host derives count/min/max/sum/quartiles from it.  For FASTA
+ * batches (qual == NULL) every count lands in the q = 0 bin.  weight (may be NULL) = per-read count for
+ * collapsed FASTA ids (get_reads_count, src/libfastx/fastx.c:475-497). */
+int fxg_stats_accum_dev (fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint64_t *hist_dev, int32_t max_cycles,
+                         const int32_t *weight_dev, int64_t index_base);
+int fxg_stats_accum_host(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint64_t *hist_dev, int32_t max_cycles,
+                         const int32_t *weight_host, fxg_report *report);
+
+/* ---- a6/a7: fastx_clipper loop body: HalfLocalSequenceAlignment::align (src/libfastx/sequence_alignment.cpp:
+ * 113-129,340-428,496-650) + adapter_cutoff_index (src/fastx_clipper/fastx_clipper.cpp:159-241) + the discard
+ * cascade (:280-319).  width[i] (may be NULL => len) is the DP matrix width of read i: the reference's matrix
+ * only grows, so for mixed-length input it is the running maximum length and the row must hold the bytes the
+ * reference would read there (NUL at len, then stale bytes of earlier reads — SURVEY.md Appendix D.1).
+ * out_len[i] = length to emit, or -1 when discarded; out_class[i] (may be NULL) = FXG_CLIP_* class. */
+#define FXG_CLIP_WRITE        0
+#define FXG_CLIP_ADAPTER_ONLY 1
+#define FXG_CLIP_TOO_SHORT    2
+#define FXG_CLIP_NON_CLIPPED  3
+#define FXG_CLIP_CLIPPED      4
+#define FXG_CLIP_HAS_N        5
+typedef struct {
+    const char *adapter;          /* -a, NUL terminated, 1..99 characters                              */
+    int32_t min_length;           /* -l (default 5)                                                    */
+    int32_t keep_delta;           /* -d N > 0 ? N + strlen(adapter) : 0   (fastx_clipper.cpp:153-154)  */
+    int32_t discard_non_clipped;  /* -c                                                                */
+    int32_t discard_clipped;      /* -C                                                                */
+    int32_t discard_unknown;      /* 1 unless -n                                                       */
+    int32_t min_adapter_len;      /* -M                                                                */
+} fxg_clip_opts;
+/* report.n_out = reads written; report.aux[FXG_CLIP_*] = reads in each discard class */
+int fxg_clip_dev (fxg_ctx *ctx, const fxg_batch *b, const int32_t *width_dev, int q_offset, const fxg_clip_opts *o,
+                  int32_t *out_len_dev, uint8_t *out_class_dev, int32_t *out_cut_dev, int64_t index_base);
+int fxg_clip_host(fxg_ctx *ctx, const fxg_batch *b, const int32_t *width_host, int q_offset, const fxg_clip_opts *o,
+                  int32_t *out_len_host, uint8_t *out_class_host, fxg_report *report);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,197 @@
+"""GPU parity (-m gpu): K-STATS histograms and K-CLIP decisions vs the CPU oracle, through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+from test_gpu_parity import ctx, dev  # noqa: F401  (module-scoped fixture + helper)
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def gpu_hist(ctx, seq, qual, lens, L, Q, max_cycles, weight=None, host=False):
+    import fastx_toolkit_b200 as F  # noqa: F401
+    n, stride = seq.shape
+    hist = torch.zeros((max_cycles, 5, 109), dtype=torch.int64, device="cuda")
+    ctx.report_reset()
+    if host:
+        rep = ctx.stats_accum_host(ctx.batch(seq, qual, n, stride, L, lens), Q, hist, max_cycles, weight)
+    else:
+        ctx.stats_accum_dev(ctx.batch(dev(seq), dev(qual), n, stride, L, dev(lens)), Q, hist, max_cycles, dev(weight))
+        rep = ctx.sync()
+    return hist.cpu().numpy().astype(np.uint64), rep
+
+
+@pytest.mark.parametrize("L,n,kind", [(150, 50001, H.WITH_N), (100, 20000, H.PLAIN), (36, 9000, H.WITH_N), (250, 6000, H.WITH_N),
+                                      (1000, 700, H.WITH_N), (3, 500, H.PLAIN), (161, 3000, H.WITH_N)])
+def test_stats_hist_uniform(ctx, L, n, kind):
+    seq, qual = H.synth_slab(H.SEED_BASE + 3, n, L, kind)
+    exp, cyc = H.o_stats_hist(seq, qual, None, L, seq.shape[1], 33, L)
+    got, rep = gpu_hist(ctx, seq, qual, None, L, 33, L)
+    assert cyc == L and rep.first_bad_read == -1 and rep.n_in == n
+    assert np.array_equal(got, exp)
+    assert int(got.sum()) == n * L
+
+
+def test_stats_full_quality_range_and_ragged(ctx):
+    n, L = 30000, 150
+    seq, qual = H.synth_slab(H.SEED_BASE + 3, n, L, H.WITH_N)
+    rng = np.random.default_rng(7)
+    for Q in (33, 64):
+        lo, hi = Q - 15, min(Q + 93, 127)
+        qual2 = np.zeros_like(qual)
+        qual2[:, :L] = rng.integers(lo, hi + 1, size=(n, L), dtype=np.uint8)
+        seq2 = seq.copy()
+        lens = H.ragged(seq2, qual2, rng, min_len=1)
+        exp, cyc = H.o_stats_hist(seq2, qual2, lens, 0, seq.shape[1], Q, L)
+        got, rep = gpu_hist(ctx, seq2, qual2, lens, 0, Q, L)
+        assert rep.first_bad_read == -1 and np.array_equal(got, exp)
+        got2, rep2 = gpu_hist(ctx, seq2, qual2, lens, 0, Q, L, host=True)
+        assert np.array_equal(got2, exp) and rep2.n_in == n
+        # max_cycles smaller than the reads: cycles beyond it are dropped
+        got3, _ = gpu_hist(ctx, seq2, qual2, lens, 0, Q, 40)
+        assert np.array_equal(got3, exp[:40])
+
+
+def test_stats_fasta_weights_and_bad_read(ctx):
+    n, L = 5000, 50
+    seq, qual = H.synth_slab(H.SEED_BASE + 4, n, L, H.WITH_N)
+    w = np.random.default_rng(2).integers(1, 9, size=n).astype(np.int32)
+    got, rep = gpu_hist(ctx, seq, None, None, L, 33, L, weight=w)
+    exp = np.zeros((L, 5, 109), np.uint64)
+    for k, ch in enumerate(b"ACGTN"):
+        exp[:, k, 15] = ((seq[:, :L] == ch) * w[:, None]).sum(axis=0)
+    assert np.array_equal(got, exp)
+    s2 = seq.copy(); s2[4000, 17] = ord("X")
+    q2 = qual.copy(); q2[1234, 49] = 5
+    _, rep = gpu_hist(ctx, s2, q2, None, L, 33, L)
+    assert rep.first_bad_read == 1234
+
+
+def test_stats_golden_fixture_hist(ctx):
+    recs = H.read_fastx(os.path.join(H.GOLDEN, "fastq_stats1.fastq"))
+    seq, qual, lens, stride, _ = H.slab_from_records(recs, 64)
+    exp, cyc = H.o_stats_hist(seq, qual, lens, 0, stride, 64, 36)
+    got, rep = gpu_hist(ctx, seq, qual, lens, 0, 64, 36)
+    assert cyc == 36 and np.array_equal(got, exp) and rep.first_bad_read == -1
+
+
+# ------------------------------------------------------------------------------------------ clipper
+
+def gpu_clip(ctx, seq, qual, lens, widths, L, adapter, opts_kw, host=False):
+    import fastx_toolkit_b200 as F
+    n, stride = seq.shape
+    base = dict(min_length=5, keep_delta=0, discard_non_clipped=0, discard_clipped=0, discard_unknown=1, min_adapter_len=0)
+    base.update(opts_kw)
+    o = F.ClipOpts(adapter=adapter, **base)
+    oo = H.FxoClipOpts(**base)
+    exp = H.o_clip(seq, lens, widths, L, stride, adapter, oo)
+    ctx.report_reset()
+    if host:
+        out_len, out_cls = np.empty(n, np.int32), np.empty(n, np.uint8)
+        rep = ctx.clip_host(ctx.batch(seq, qual, n, stride, L, lens), widths, 33, o, out_len, out_cls)
+        out_cut = None
+    else:
+        d_len = torch.empty(n, dtype=torch.int32, device="cuda")
+        d_cls = torch.empty(n, dtype=torch.uint8, device="cuda")
+        d_cut = torch.empty(n, dtype=torch.int32, device="cuda")
+        ctx.clip_dev(ctx.batch(dev(seq), dev(qual), n, stride, L, dev(lens)), dev(widths), 33, o, d_len, d_cls, d_cut)
+        rep = ctx.sync()
+        out_len, out_cls, out_cut = d_len.cpu().numpy(), d_cls.cpu().numpy(), d_cut.cpu().numpy()
+    e_len, e_cls, e_cut = exp
+    assert np.array_equal(out_cls, e_cls)
+    if out_cut is not None:
+        assert np.array_equal(out_cut, e_cut)
+    assert np.array_equal(out_len, np.where(e_cls == 0, e_len, -1))
+    assert rep.n_out == int((e_cls == 0).sum())
+    for c in range(1, 6):
+        assert rep.aux[c] == int((e_cls == c).sum())
+    return rep
+
+
+CASES = [
+    (b"AGATCGGAAGAGC", dict(min_length=20)),
+    (b"AGATCGGAAGAGC", dict(min_length=20, discard_unknown=0)),
+    (b"AGATCGGAAGAGC", dict(min_length=5, discard_non_clipped=1)),
+    (b"AGATCGGAAGAGC", dict(min_length=5, discard_clipped=1, discard_unknown=0)),
+    (b"AGATCGGAAGAGC", dict(min_length=10, keep_delta=3 + 13, discard_unknown=0)),
+    (b"AGATCGGAAGAGC", dict(min_length=10, min_adapter_len=8)),
+    (b"AGNTCGGAAGNGCTTGA", dict(min_length=12, discard_unknown=0)),
+    (b"CCTTAAGG", dict()),
+    (b"CAATTGGTTAATCCCCCTATATA", dict(min_length=15, discard_unknown=0, discard_non_clipped=1)),
+    (b"AGATCGGAAGAGCACACGTCTGAACTCCAGTCACATCACGATCTCGTATGCC", dict(min_length=10)),   # 52 nt: local-memory column path
+    (b"A", dict(min_length=1)),
+]
+
+
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_clip_uniform(ctx, case):
+    adapter, kw = CASES[case]
+    for L, n, kind in ((60, 6000, H.ADAPTER), (150, 4000, H.ADAPTER), (33, 3000, H.WITH_N)):
+        seq, qual = H.synth_slab(H.SEED_BASE + 2, n, L, kind)
+        rng = np.random.default_rng(case * 7 + L)
+        for i in rng.choice(n, n // 3, replace=False):   # plant (possibly truncated / mutated) adapters
+            st = int(rng.integers(0, L))
+            m = min(len(adapter), L - st)
+            ad = np.frombuffer(adapter[:m], np.uint8).copy()
+            if m > 4 and rng.random() < 0.4:
+                ad[int(rng.integers(0, m))] = ord("ACGT"[int(rng.integers(0, 4))])
+            seq[i, st:st + m] = ad
+        gpu_clip(ctx, seq, qual, None, None, L, adapter, kw)
+
+
+def test_clip_tiny_and_host_and_fasta(ctx):
+    for L in (1, 2, 3, 5):
+        seq, qual = H.synth_slab(H.SEED_BASE + 8, 2000, L, H.WITH_N)
+        gpu_clip(ctx, seq, qual, None, None, L, b"AGATCGGAAGAGC", dict(min_length=1, discard_unknown=0))
+        gpu_clip(ctx, seq, None, None, None, L, b"CCTTAAGG", dict(min_length=0))
+    seq, qual = H.synth_slab(H.SEED_BASE + 2, 300000, 150, H.ADAPTER)
+    gpu_clip(ctx, seq, qual, None, None, 150, b"AGATCGGAAGAGC", dict(min_length=20), host=True)
+    s2 = seq[:5000].copy(); q2 = qual[:5000].copy()
+    s2[77, 3] = ord("n"); q2[12, 100] = 3
+    import fastx_toolkit_b200 as F
+    o = F.ClipOpts(adapter=b"AGATCGGAAGAGC", min_length=20, keep_delta=0, discard_non_clipped=0, discard_clipped=0,
+                   discard_unknown=1, min_adapter_len=0)
+    d_len = torch.empty(5000, dtype=torch.int32, device="cuda")
+    ctx.report_reset()
+    ctx.clip_dev(ctx.batch(dev(s2), dev(q2), 5000, 160, 150), None, 33, o, d_len)
+    assert ctx.sync().first_bad_read == 12
+
+
+def test_clip_mixed_length_stale_tail(ctx):
+    """Bug-compatible mode: rows carry NUL + stale bytes, widths = running max."""
+    n, L = 5000, 60
+    seq, qual = H.synth_slab(H.SEED_BASE + 7, n, L, H.ADAPTER)
+    lens = H.ragged(seq, qual, np.random.default_rng(3), min_len=8)
+    stride = seq.shape[1]
+    rows = np.zeros_like(seq)
+    widths = np.zeros(n, np.int32)
+    shadow = np.zeros(stride + 1, np.uint8)
+    wmax = 0
+    for i in range(n):
+        l = int(lens[i])
+        shadow[:l] = seq[i, :l]; shadow[l] = 0
+        wmax = max(wmax, l)
+        rows[i, :wmax] = shadow[:wmax]
+        widths[i] = wmax
+    gpu_clip(ctx, rows, qual, lens, widths, 0, b"AGATCGGAAGAGC", dict(min_length=5, discard_clipped=1, discard_unknown=0))
+    gpu_clip(ctx, rows, qual, lens, widths, 0, b"AGATCGGAAGAGC", dict(min_length=5, discard_non_clipped=1))
+    gpu_clip(ctx, seq, qual, lens, None, 0, b"AGATCGGAAGAGC", dict(min_length=5))     # clean mode: width = len
+
+
+def test_clip_golden_fixture(ctx):
+    from test_oracle_golden import emit, golden
+    import fastx_toolkit_b200 as F
+    recs = H.read_fastx(os.path.join(H.GOLDEN, "fastx_clipper1.fastq"))
+    seq, qual, lens, stride, _ = H.slab_from_records(recs, 64)
+    o = F.ClipOpts(adapter=b"CAATTGGTTAATCCCCCTATATA", min_length=15, keep_delta=0, discard_non_clipped=1, discard_clipped=0,
+                   discard_unknown=0, min_adapter_len=0)
+    n = len(recs)
+    d_len = torch.empty(n, dtype=torch.int32, device="cuda")
+    ctx.report_reset()
+    ctx.clip_dev(ctx.batch(dev(seq), dev(qual), n, stride, 0, dev(lens)), None, 64, o, d_len)
+    rep = ctx.sync()
+    assert rep.first_bad_read == -1
+    assert emit(recs, d_len.cpu().numpy(), 64) == golden("fastx_clipper1a.out")
