@@ -271,7 +271,7 @@ static void env_tune(int *ring, int *g, int *stages, int *ctas)
     if (sscanf(e, "%d,%d,%d,%d", &r, &a, &b, &c) >= 1) { *ring = r; *g = a; *stages = b; *ctas = c; }
 }
 
-static int make_plan(fxg_ctx *ctx, const fxg_batch *b, int nslabs, int extra_stage_bufs, TilePlan *plan, bool allow_ring = true)
+static int make_plan(fxg_ctx *ctx, const fxg_batch *b, int nslabs, int extra_stage_bufs, TilePlan *plan, bool revcomp = false)
 {
     const int S = b->stride;
     const size_t per_read = (size_t)S * (size_t)nslabs;
@@ -283,19 +283,20 @@ static int make_plan(fxg_ctx *ctx, const fxg_batch *b, int nslabs, int extra_sta
     memset(plan, 0, sizeof(*plan));
 
     // ---- warp-private pipeline: a warp's tile (32/g reads) must stay small enough that many warps fit
-    if (allow_ring && t_ring != 0 && ctx->tune_tile_reads == 0) {
+    if (t_ring != 0 && ctx->tune_tile_reads == 0) {
         int g = 0;
         for (int cand = 1; cand <= 8; cand <<= 1) {
-            if (t_g && cand != t_g) continue;
-            if ((size_t)(32 / cand) * per_read <= 12 * 1024) { g = cand; break; }
+            if (t_g ? cand == t_g : (size_t)(32 / cand) * per_read * (revcomp ? 2 : 1) <= 12 * 1024) { g = cand; break; }
         }
         if (g) {
             const size_t wstage = (size_t)(32 / g) * per_read;
             // one stage per warp: the other warps of the SM (16 with 4 CTAs) cover a warp's wait for HBM;
             // measured on B200 (150 bp): 1 stage x 4 CTAs 6276 GB/s, 2 stages x 2 CTAs 6082 GB/s
             int stages = t_stages ? t_stages : 1;
-            while (stages > 1 && (size_t)(stages + extra_stage_bufs) * wstage * W_WARPS > smem_max) stages--;
-            const size_t smem = (size_t)(stages + extra_stage_bufs) * wstage * W_WARPS;
+            if (revcomp) stages = 1;                          // k_revcomp_w: one input + one output tile per warp
+            const int bufs = revcomp ? 2 : stages;
+            while (!revcomp && stages > 1 && (size_t)stages * wstage * W_WARPS > smem_max) stages--;
+            const size_t smem = (size_t)(revcomp ? bufs : stages) * wstage * W_WARPS;
             if (smem <= smem_max) {
                 int ctas = t_ctas ? t_ctas : (int)((smem_max + 1024) / (smem + 1024));
                 if (ctas < 1) ctas = 1;
@@ -426,7 +427,7 @@ static int revcomp_enqueue(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint8
     if (b->n == 0) return FXG_OK;
     const bool has_qual = b->qual != NULL;
     TilePlan plan;
-    int rc = make_plan(ctx, b, has_qual ? 2 : 1, 2, &plan, false);
+    int rc = make_plan(ctx, b, has_qual ? 2 : 1, 2, &plan, true);
     if (rc) return rc;
     RevcompParams p;
     p.seq = b->seq; p.qual = b->qual; p.len = b->len; p.uniform_len = b->uniform_len; p.stride = b->stride; p.n = b->n;

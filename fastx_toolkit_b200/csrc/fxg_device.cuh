@@ -133,6 +133,15 @@ __device__ __forceinline__ uint32_t seq_complement(uint32_t x, uint32_t &bad)
     return __byte_perm(CLUT_LO, CLUT_HI, sel);
 }
 
+// raw PRMT (PTX default mode): selector nibble bit 3 replicates the selected byte's sign bit instead of
+// copying the byte — __byte_perm() only documents the low 3 bits of each nibble, so spell it in PTX.
+__device__ __forceinline__ uint32_t prmt_raw(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
 // byte mask with 0xFF for the first `nbytes` (0..4) bytes of a word
 __device__ __forceinline__ uint32_t head_mask(int nbytes)
 {

@@ -391,6 +391,54 @@ __device__ __forceinline__ uint4 reverse_window(const uint4 &A, const uint4 &B, 
     return o;
 }
 
+// Reverse-complement this lane's share (output chunks j, j+G, ...) of one read from the input rows into
+// the output rows (all in shared memory); the whole stride is written so the tile can be bulk-stored.
+template <int G, bool HAS_QUAL>
+__device__ __forceinline__ void revcomp_read(const uint8_t *srow, const uint8_t *qrow, uint8_t *osrow, uint8_t *oqrow,
+                                             int L, int nchunks, int j, const QualK &qk, uint32_t &bads, uint32_t &badq)
+{
+    const int re = L & 15;
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    for (int oc = j; oc < nchunks; oc += G) {
+        const int e = L - 16 * oc;     // exclusive end of the input bytes for this chunk
+        uint4 os = zero, oq = zero;
+        if (e > 0) {
+            const int ce = e >> 4;
+            const uint4 A = (ce >= 1) ? lds128(srow + (ce - 1) * 16) : zero;
+            const uint4 B = (re != 0) ? lds128(srow + ce * 16) : zero;
+            const uint4 r = reverse_window(A, B, re);
+            const int nreal = e < 16 ? e : 16;
+            const uint32_t rw[4] = { r.x, r.y, r.z, r.w };
+            uint32_t cw[4];
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                uint32_t b = 0;
+                cw[w] = seq_complement(rw[w], b);
+                const uint32_t m = head_mask(nreal - 4 * w);
+                bads |= b & m;
+                cw[w] &= m;
+            }
+            os = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+            if (HAS_QUAL) {
+                const uint4 QA = (ce >= 1) ? lds128(qrow + (ce - 1) * 16) : zero;
+                const uint4 QB = (re != 0) ? lds128(qrow + ce * 16) : zero;
+                const uint4 rq = reverse_window(QA, QB, re);
+                uint32_t qv[4] = { rq.x, rq.y, rq.z, rq.w };
+#pragma unroll
+                for (int w = 0; w < 4; w++) {
+                    const uint32_t m = head_mask(nreal - 4 * w);
+                    badq |= qual_bad_bits(qv[w], qv[w] | HI, qk) & m;
+                    qv[w] &= m;
+                }
+                oq = make_uint4(qv[0], qv[1], qv[2], qv[3]);
+            }
+        }
+        *reinterpret_cast<uint4 *>(osrow + oc * 16) = os;
+        if (HAS_QUAL) *reinterpret_cast<uint4 *>(oqrow + oc * 16) = oq;
+    }
+}
+
+// ---- CTA-tile variant (any stride) ----------------------------------------------------------------------
 template <int G, bool HAS_QUAL>
 __global__ void __launch_bounds__(THREADS) k_revcomp(const __grid_constant__ RevcompParams P)
 {
@@ -452,50 +500,9 @@ __global__ void __launch_bounds__(THREADS) k_revcomp(const __grid_constant__ Rev
             const bool lenbad = (L <= 0 || L > S);
             if (lenbad) L = 0;
             const uint8_t *srow = stage + (size_t)rr * S;
-            const uint8_t *qrow = srow + slab_bytes;
             uint8_t *osrow = obuf + (size_t)rr * S;
-            uint8_t *oqrow = osrow + slab_bytes;
-            const int re = L & 15;
             uint32_t bads = 0, badq = 0;
-
-            for (int oc = j; oc < nchunks; oc += G) {
-                const int e = L - 16 * oc;     // exclusive end of the input bytes for this chunk
-                uint4 os = make_uint4(0, 0, 0, 0), oq = make_uint4(0, 0, 0, 0);
-                if (e > 0) {
-                    const int ce = e >> 4;
-                    const uint4 zero = make_uint4(0, 0, 0, 0);
-                    const uint4 A = (ce >= 1) ? lds128(srow + (ce - 1) * 16) : zero;
-                    const uint4 B = (re != 0) ? lds128(srow + ce * 16) : zero;
-                    const uint4 r = reverse_window(A, B, re);
-                    const int nreal = e < 16 ? e : 16;
-                    const uint32_t rw[4] = { r.x, r.y, r.z, r.w };
-                    uint32_t cw[4];
-#pragma unroll
-                    for (int w = 0; w < 4; w++) {
-                        uint32_t b = 0;
-                        cw[w] = seq_complement(rw[w], b);
-                        const uint32_t m = head_mask(nreal - 4 * w);
-                        bads |= b & m;
-                        cw[w] &= m;
-                    }
-                    os = make_uint4(cw[0], cw[1], cw[2], cw[3]);
-                    if (HAS_QUAL) {
-                        const uint4 QA = (ce >= 1) ? lds128(qrow + (ce - 1) * 16) : zero;
-                        const uint4 QB = (re != 0) ? lds128(qrow + ce * 16) : zero;
-                        const uint4 rq = reverse_window(QA, QB, re);
-                        uint32_t qv[4] = { rq.x, rq.y, rq.z, rq.w };
-#pragma unroll
-                        for (int w = 0; w < 4; w++) {
-                            const uint32_t m = head_mask(nreal - 4 * w);
-                            badq |= qual_bad_bits(qv[w], qv[w] | HI, qk) & m;
-                            qv[w] &= m;
-                        }
-                        oq = make_uint4(qv[0], qv[1], qv[2], qv[3]);
-                    }
-                }
-                *reinterpret_cast<uint4 *>(osrow + oc * 16) = os;
-                if (HAS_QUAL) *reinterpret_cast<uint4 *>(oqrow + oc * 16) = oq;
-            }
+            revcomp_read<G, HAS_QUAL>(srow, srow + slab_bytes, osrow, osrow + slab_bytes, L, nchunks, j, qk, bads, badq);
             if ((bads | (badq & HI)) != 0 || lenbad) note_bad(P.counters, P.index_base + g);
         }
 
@@ -514,6 +521,77 @@ __global__ void __launch_bounds__(THREADS) k_revcomp(const __grid_constant__ Rev
         if (++s == stages) { s = 0; parity ^= 1u; }
     }
     if (tid == 0) bulk_wait_all<0>();       // all stores complete before the CTA (and its smem) retires
+}
+
+// ---- warp-private variant: each warp owns one input tile and one output tile of R = 32/G reads --------
+// load (TMA) -> wait -> reverse/complement smem->smem -> bulk store (TMA) -> next load; the store of tile i
+// drains while the warp waits for tile i+1, and the SM's other warps cover both waits.
+template <int G, bool HAS_QUAL>
+__global__ void __launch_bounds__(W_THREADS) k_revcomp_w(const __grid_constant__ RevcompParams P)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full_bar[W_WARPS];
+
+    constexpr int R = 32 / G;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int S = P.stride;
+    const uint32_t slab_bytes = (uint32_t)R * (uint32_t)S;
+    const uint32_t stage_bytes = slab_bytes * (HAS_QUAL ? 2u : 1u);
+    uint8_t *ibuf = smem + (size_t)w * 2 * stage_bytes;
+    uint8_t *obuf = ibuf + stage_bytes;
+    uint64_t *bar = &full_bar[w];
+    const int64_t ntiles = (P.n + R - 1) / R;
+    const int64_t gw = (int64_t)blockIdx.x * W_WARPS + w, GW = (int64_t)gridDim.x * W_WARPS;
+    const QualK qk = P.qk;
+    const int nchunks = S >> 4;
+
+    if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    __syncwarp();
+
+    auto issue = [&](int64_t tile) {
+        const int64_t r0 = tile * R;
+        const int64_t left = P.n - r0;
+        const uint32_t bytes = (uint32_t)(left < R ? left : R) * (uint32_t)S;
+        mbar_arrive_expect_tx(bar, bytes * (HAS_QUAL ? 2u : 1u));
+        bulk_g2s(ibuf, P.seq + r0 * S, bytes, bar);
+        if (HAS_QUAL) bulk_g2s(ibuf + slab_bytes, P.qual + r0 * S, bytes, bar);
+    };
+    if (lane == 0 && gw < ntiles) issue(gw);
+
+    const int j = lane & (G - 1);
+    const int rr = lane / G;
+    uint32_t parity = 0;
+    for (int64_t tile = gw; tile < ntiles; tile += GW) {
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        const int64_t r0 = tile * R;
+        const int64_t g = r0 + rr;
+        const int64_t left = P.n - r0;
+        const int nr = (int)(left < R ? left : R);
+        if (lane == 0) bulk_wait_read<0>();     // the previous tile's store has finished reading obuf
+        __syncwarp();
+        if (rr < nr) {
+            int L = P.len ? __ldg(P.len + g) : P.uniform_len;
+            const bool lenbad = (L <= 0 || L > S);
+            if (lenbad) L = 0;
+            const uint8_t *srow = ibuf + (size_t)rr * S;
+            uint8_t *osrow = obuf + (size_t)rr * S;
+            uint32_t bads = 0, badq = 0;
+            revcomp_read<G, HAS_QUAL>(srow, srow + slab_bytes, osrow, osrow + slab_bytes, L, nchunks, j, qk, bads, badq);
+            if ((bads | (badq & HI)) != 0 || lenbad) note_bad(P.counters, P.index_base + g);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)nr * (uint32_t)S;
+            bulk_s2g(P.out_seq + r0 * S, obuf, bytes);
+            if (HAS_QUAL) bulk_s2g(P.out_qual + r0 * S, obuf + slab_bytes, bytes);
+            bulk_commit();
+            const int64_t nt = tile + GW;
+            if (nt < ntiles) issue(nt);
+        }
+    }
+    if (lane == 0) bulk_wait_all<0>();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -604,8 +682,24 @@ static cudaError_t launch_revcomp_g(const TilePlan &plan, const RevcompParams &p
     return cudaGetLastError();
 }
 
+template <bool HAS_QUAL>
+static cudaError_t launch_revcomp_w(const TilePlan &plan, const RevcompParams &p, cudaStream_t st)
+{
+#define FXG_RCW_CASE(GV)                                                                           \
+    case GV:                                                                                       \
+        k_revcomp_w<GV, HAS_QUAL><<<plan.grid, W_THREADS, plan.smem_bytes, st>>>(p);               \
+        break;
+    switch (plan.g) {
+        FXG_RCW_CASE(1) FXG_RCW_CASE(2) FXG_RCW_CASE(4) FXG_RCW_CASE(8)
+    default: return cudaErrorInvalidValue;
+    }
+#undef FXG_RCW_CASE
+    return cudaGetLastError();
+}
+
 cudaError_t launch_revcomp(bool has_qual, const TilePlan &plan, const RevcompParams &p, cudaStream_t st)
 {
+    if (plan.warp_ring) return has_qual ? launch_revcomp_w<true>(plan, p, st) : launch_revcomp_w<false>(plan, p, st);
     return has_qual ? launch_revcomp_g<true>(plan, p, st) : launch_revcomp_g<false>(plan, p, st);
 }
 
@@ -643,6 +737,11 @@ cudaError_t kernels_set_smem_attrs()
     if (e == cudaSuccess) e = set_max_smem(k_scan_w<GV, MODE_FILTER, false>);
     FXG_ATTR_W(1) FXG_ATTR_W(2) FXG_ATTR_W(4) FXG_ATTR_W(8)
 #undef FXG_ATTR_W
+#define FXG_ATTR_RW(GV)                                                                            \
+    if (e == cudaSuccess) e = set_max_smem(k_revcomp_w<GV, true>);                                 \
+    if (e == cudaSuccess) e = set_max_smem(k_revcomp_w<GV, false>);
+    FXG_ATTR_RW(1) FXG_ATTR_RW(2) FXG_ATTR_RW(4) FXG_ATTR_RW(8)
+#undef FXG_ATTR_RW
     return e;
 }
 

@@ -100,8 +100,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_stats(const __grid_constant__
                     const uint32_t qs4 = qp4 << 2;
                     const uint32_t blk = hs_addr + (uint32_t)rel * ST_WBLK;
                     // offset = q'*4 + nuc*256: byte0 <- qs4.k, byte1 <- nuc4.k, bytes 2,3 <- sign(nuc4.k) = 0
-                    const uint32_t o0 = __byte_perm(qs4, nuc4, 0xCC40u), o1 = __byte_perm(qs4, nuc4, 0xDD51u);
-                    const uint32_t o2 = __byte_perm(qs4, nuc4, 0xEE62u), o3 = __byte_perm(qs4, nuc4, 0xFF73u);
+                    const uint32_t o0 = prmt_raw(qs4, nuc4, 0xCC40u), o1 = prmt_raw(qs4, nuc4, 0xDD51u);
+                    const uint32_t o2 = prmt_raw(qs4, nuc4, 0xEE62u), o3 = prmt_raw(qs4, nuc4, 0xFF73u);
                     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(blk + o0) : "memory");
                     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(blk + o1 + ST_KBLK) : "memory");
                     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(blk + o2 + 2 * ST_KBLK) : "memory");

@@ -55,10 +55,14 @@ for cfg in configs:
         print("FXG_TUNE=%s failed: %s" % (cfg, e), flush=True)
 os.environ.pop("FXG_TUNE", None)
 oseq, oqual = torch.empty_like(dseq), torch.empty_like(dqual)
-for cfg in ["0,0,0,0", "0,0,2,0", "0,0,3,0", "0,0,2,2", "0,0,3,1"]:
+for cfg in ["0,0,0,0", "-1,0,0,0", "1,2,0,4", "1,2,0,5", "1,1,0,0", "1,4,0,5", "1,4,0,8"]:
     os.environ["FXG_TUNE"] = cfg
     try:
         ms = timeit(lambda: ctx.revcomp_dev(b, 33, oseq, oqual))
+        if cfg == "0,0,0,0":
+            rs, rq = oseq.clone(), oqual.clone()
+        else:
+            assert torch.equal(rs, oseq) and torch.equal(rq, oqual), "revcomp variants disagree"
         print("FXG_TUNE=%-10s revcomp %.3f ms %7.1f GB/s (%.2f Gr/s)" % (cfg, ms, n * 4 * L / ms / 1e6, n / ms / 1e6), flush=True)
     except Exception as e:  # noqa: BLE001
         print("revcomp FXG_TUNE=%s failed: %s" % (cfg, e), flush=True)
