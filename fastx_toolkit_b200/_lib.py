@@ -81,6 +81,15 @@ def lib():
         "fxg_stats_accum_host": (i32, [vp, BP, i32, vp, C.c_int32, vp, RP]),
         "fxg_clip_dev": (i32, [vp, BP, vp, i32, C.POINTER(ClipOpts), vp, vp, vp, i64]),
         "fxg_clip_host": (i32, [vp, BP, vp, i32, C.POINTER(ClipOpts), vp, vp, RP]),
+        "fxg_hash_dev": (i32, [vp, BP, vp]),
+        "fxg_collapse_new": (i32, [i32, i64, C.c_int32, C.POINTER(vp)]),
+        "fxg_collapse_free": (None, [vp]),
+        "fxg_collapse_add": (i32, [vp, BP, vp, vp, i64]),
+        "fxg_collapse_finish": (i32, [vp, i32, C.POINTER(i64), C.POINTER(i64)]),
+        "fxg_collapse_fetch": (i32, [vp, vp, vp, vp, vp, vp]),
+        "fxg_collapse_error": (C.c_char_p, [vp]),
+        "fxg_collapse_launches": (i64, [vp]),
+        "fxg_collapse_order_dev": (i32, [i32, vp, vp, vp, i64, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -101,6 +110,50 @@ def _ptr(x):
     if hasattr(x, "ctypes"):
         return x.ctypes.data
     raise TypeError(type(x))
+
+
+class Collapser:
+    """fxg_collapser: exact dedup + reference output order on one GPU."""
+
+    def __init__(self, device, max_reads, stride):
+        self.L = lib()
+        h = C.c_void_p()
+        rc = self.L.fxg_collapse_new(device, max_reads, stride, C.byref(h))
+        if rc != FXG_OK:
+            raise FxgError(rc, "fxg_collapse_new: " + self.L.fxg_strerror(rc).decode())
+        self.h, self.stride, self.n_unique, self.first_bad = h, stride, 0, -1
+
+    def _ck(self, rc):
+        if rc != FXG_OK:
+            raise FxgError(rc, self.L.fxg_collapse_error(self.h).decode() or self.L.fxg_strerror(rc).decode())
+
+    def add(self, b, weight=None, first=None, index_base=0):
+        self._ck(self.L.fxg_collapse_add(self.h, C.byref(b), _ptr(weight), _ptr(first), index_base))
+
+    def finish(self, order=True):
+        u, bad = C.c_int64(), C.c_int64()
+        self._ck(self.L.fxg_collapse_finish(self.h, 1 if order else 0, C.byref(u), C.byref(bad)))
+        self.n_unique, self.first_bad = u.value, bad.value
+        return u.value
+
+    def fetch(self, out_seq=None, out_len=None, out_count=None, out_first=None, out_hash=None):
+        self._ck(self.L.fxg_collapse_fetch(self.h, _ptr(out_seq), _ptr(out_len), _ptr(out_count), _ptr(out_first), _ptr(out_hash)))
+
+    def launches(self):
+        return int(self.L.fxg_collapse_launches(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.fxg_collapse_free(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+def collapse_order_dev(device, hash_dev, first_dev, count_dev, n_unique, perm_dev):
+    rc = lib().fxg_collapse_order_dev(device, _ptr(hash_dev), _ptr(first_dev), _ptr(count_dev), n_unique, _ptr(perm_dev))
+    if rc != FXG_OK:
+        raise FxgError(rc, "fxg_collapse_order_dev")
 
 
 class Context:
@@ -182,6 +235,9 @@ class Context:
     def clip_dev(self, b, widths, q_offset, opts, out_len, out_class=None, out_cut=None, index_base=0):
         self._ck(self.L.fxg_clip_dev(self.h, C.byref(b), _ptr(widths), q_offset, C.byref(opts), _ptr(out_len),
                                      _ptr(out_class), _ptr(out_cut), index_base))
+
+    def hash_dev(self, b, hash_out):
+        self._ck(self.L.fxg_hash_dev(self.h, C.byref(b), _ptr(hash_out)))
 
     # ---- ops (host pointers; copies are inside the call)
     def stats_accum_host(self, b, q_offset, hist_dev, max_cycles, weight=None):

@@ -300,7 +300,7 @@ static int make_plan(fxg_ctx *ctx, const fxg_batch *b, int nslabs, int extra_sta
             if (smem <= smem_max) {
                 int ctas = t_ctas ? t_ctas : (int)((smem_max + 1024) / (smem + 1024));
                 if (ctas < 1) ctas = 1;
-                if (!t_ctas && ctas > 4) ctas = 4;
+                if (!t_ctas && ctas > (revcomp ? 5 : 4)) ctas = revcomp ? 5 : 4;   // measured optima (150 bp)
                 if (ctas > 12) ctas = 12;
                 const int64_t ntiles = (b->n + (32 / g) - 1) / (32 / g);
                 int64_t grid = (int64_t)ctx->sm_count * ctas;
@@ -539,6 +539,19 @@ extern "C" int fxg_clip_dev(fxg_ctx *ctx, const fxg_batch *b, const int32_t *wid
     if (!out_len) return arg_error(ctx, "out_len is NULL");
     CK(ctx, cudaSetDevice(ctx->device));
     return clip_enqueue(ctx, b, width, q_offset, o, out_len, out_class, out_cut, index_base, ctx->stream);
+}
+
+// ---- K-HASH (std::hash<std::string> of every read; collapser routing key) ----------------------------------
+extern "C" int fxg_hash_dev(fxg_ctx *ctx, const fxg_batch *b, uint64_t *hash_dev)
+{
+    int rc = check_batch(ctx, b, true, false, 33);
+    if (rc) return rc;
+    if (!hash_dev) return arg_error(ctx, "hash_dev is NULL");
+    if (b->n == 0) return FXG_OK;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, launch_hash(b->seq, b->len, b->uniform_len, b->stride, b->n, hash_dev, ctx->stream));
+    ctx->launches++;
+    return FXG_OK;
 }
 
 // ---- host-buffer pipelines ---------------------------------------------------------------------------

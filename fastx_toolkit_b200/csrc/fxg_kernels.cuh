@@ -125,6 +125,7 @@ cudaError_t launch_stats(const StatsParams &p, int grid, uint32_t smem_bytes, cu
 cudaError_t launch_stats_simple(const StatsParams &p, int sm_count, cudaStream_t st);
 cudaError_t launch_clip(const ClipParams &p, int sm_count, cudaStream_t st);
 cudaError_t stats_set_smem_attrs();
+cudaError_t launch_hash(const uint8_t *seq, const int32_t *len, int uniform_len, int stride, int64_t n, uint64_t *out, cudaStream_t st);
 
 cudaError_t launch_scan(int mode, bool has_seq, const TilePlan &plan, const ScanParams &p, cudaStream_t st);
 cudaError_t launch_revcomp(bool has_qual, const TilePlan &plan, const RevcompParams &p, cudaStream_t st);

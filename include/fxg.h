@@ -152,6 +152,30 @@ int fxg_clip_dev (fxg_ctx *ctx, const fxg_batch *b, const int32_t *width_dev, in
 int fxg_clip_host(fxg_ctx *ctx, const fxg_batch *b, const int32_t *width_host, int q_offset, const fxg_clip_opts *o,
                   int32_t *out_len_host, uint8_t *out_class_host, fxg_report *report);
 
+/* ---- a8/a9: fastx_collapser (src/fastx_collapser/fastx_collapser.cpp:51-54,80-91,112-122)
+ * K-HASH: hash_dev[i] = std::hash<std::string>(read i) (libstdc++ _Hash_bytes, seed 0xc70f6907) — the value
+ * that fixes both the owner GPU (hash mod G) and the reference's tie order. */
+int fxg_hash_dev(fxg_ctx *ctx, const fxg_batch *b, uint64_t *hash_dev);
+
+/* Exact dedup table resident on one GPU.  add(): append the batch's rows (HOST or DEVICE pointers) and count
+ * them: weight[i] (NULL = 1) is added to the key's count (collapsed-FASTA "N-COUNT" ids, or partial counts from
+ * another GPU); first[i] (NULL = index_base + i) is the key's first-occurrence index candidate (the minimum
+ * wins).  finish(order=1) computes the reference's output order (count descending, ties in reverse
+ * std::unordered_map iteration order); fetch() copies the uniques out in that order. */
+typedef struct fxg_collapser fxg_collapser;
+int         fxg_collapse_new(int device, int64_t max_reads, int32_t stride, fxg_collapser **out);
+void        fxg_collapse_free(fxg_collapser *c);
+int         fxg_collapse_add(fxg_collapser *c, const fxg_batch *b, const int32_t *weight, const int64_t *first, int64_t index_base);
+int         fxg_collapse_finish(fxg_collapser *c, int order, int64_t *n_unique, int64_t *first_bad_read);
+int         fxg_collapse_fetch(fxg_collapser *c, uint8_t *out_seq, int32_t *out_len, uint64_t *out_count, int64_t *out_first,
+                               uint64_t *out_hash);
+const char *fxg_collapse_error(const fxg_collapser *c);
+int64_t     fxg_collapse_launches(const fxg_collapser *c);
+/* K-ORDER alone: perm_dev[k] = index of the unique printed at rank k, from (hash, first, count) triples that
+ * may have been gathered from several GPUs (device pointers on `device`). */
+int         fxg_collapse_order_dev(int device, const uint64_t *hash_dev, const uint64_t *first_dev, const uint64_t *count_dev,
+                                   int64_t n_unique, uint32_t *perm_dev);
+
 #ifdef __cplusplus
 }
 #endif

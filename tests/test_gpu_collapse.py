@@ -1,0 +1,172 @@
+"""GPU parity (-m gpu): K-HASH, exact dedup and the libstdc++-order emulation vs the CPU oracle (which itself
+is pinned to the real fastx_collapser binary in test_oracle_golden.py)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+from test_gpu_parity import ctx, dev  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def gpu_collapse(seq, lens, L, weight=None, first=None, splits=1):
+    import fastx_toolkit_b200 as F
+    n, stride = seq.shape
+    col = F.Collapser(0, max(n, 1), stride)
+    bounds = np.linspace(0, n, splits + 1).astype(np.int64)
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        if b == a:
+            continue
+        bt = F.Batch(seq[a:b].ctypes.data, None, None if lens is None else lens[a:b].ctypes.data, L, stride, int(b - a))
+        col.add(bt, None if weight is None else weight[a:b], None if first is None else first[a:b], int(a))
+    u = col.finish(True)
+    oseq = np.zeros((u, stride), np.uint8); olen = np.zeros(u, np.int32)
+    ocnt = np.zeros(u, np.uint64); ofirst = np.zeros(u, np.int64); ohash = np.zeros(u, np.uint64)
+    col.fetch(oseq, olen, ocnt, ofirst, ohash)
+    assert col.first_bad == -1 and col.launches() > 0
+    col.close()
+    return oseq, olen, ocnt, ofirst, ohash
+
+
+def check_against_oracle(seq, lens, L, splits=1):
+    n, stride = seq.shape
+    efirst, ecnt = H.o_collapse(seq, lens, L, stride)
+    oseq, olen, ocnt, ofirst, ohash = gpu_collapse(seq, lens, L, splits=splits)
+    assert len(ocnt) == len(ecnt)
+    assert np.array_equal(ocnt, ecnt)
+    assert np.array_equal(ofirst, efirst), "output order differs from the reference's unordered_map order"
+    ll = lens if lens is not None else np.full(n, L, np.int32)
+    assert np.array_equal(olen, ll[efirst])
+    for k in (0, len(efirst) // 2, len(efirst) - 1):
+        assert oseq[k, :olen[k]].tobytes() == seq[efirst[k], :olen[k]].tobytes()
+    return len(ecnt)
+
+
+def test_hash_matches_std_hash(ctx):
+    n, L = 20000, 50
+    seq, _ = H.synth_slab(H.SEED_BASE + 4, n, L, H.WITH_N)
+    lens = H.ragged(seq, None, np.random.default_rng(1), min_len=1)
+    out = torch.empty(n, dtype=torch.int64, device="cuda")
+    ctx.hash_dev(ctx.batch(dev(seq), None, n, seq.shape[1], 0, dev(lens)), out)
+    ctx.sync()
+    got = out.cpu().numpy().astype(np.uint64)
+    O = H.oracle()
+    for i in list(range(50)) + [n - 1, n // 2]:
+        row = np.ascontiguousarray(seq[i])
+        assert got[i] == O.fxo_hash_bytes(row.ctypes.data_as(C.c_void_p), int(lens[i]), 0xc70f6907)
+
+
+@pytest.mark.parametrize("n,L", [(300000, 50), (40000, 23), (2000000, 36), (5000, 150)])
+def test_collapse_order_matches_reference_map(ctx, n, L):
+    seq, _ = H.synth_slab(H.SEED_BASE + 4, n, L, H.DUPS)
+    u = check_against_oracle(seq, None, L)
+    assert 0.5 * n < u < 0.95 * n
+
+
+@pytest.mark.parametrize("u", [1, 2, 12, 13, 14, 28, 29, 30, 59, 60, 127, 128, 10273, 10274, 20754])
+def test_collapse_epoch_boundaries(ctx, u):
+    """exactly u distinct keys (+ some repeats): bucket-count ladder edges 13/29/59/... are where rehashes fire"""
+    L = 40
+    base, _ = H.synth_slab(H.SEED_BASE + 6, u, L, H.PLAIN)
+    rng = np.random.default_rng(u)
+    extra = base[rng.integers(0, u, size=u // 2 + 3)]
+    seq = np.concatenate([base[: u // 2 + 1], extra[: u // 3], base[u // 2 + 1:], extra[u // 3:]])
+    check_against_oracle(np.ascontiguousarray(seq), None, L, splits=3)
+
+
+def test_collapse_ragged_prefix_keys_and_weights(ctx):
+    L = 30
+    rng = np.random.default_rng(9)
+    seq, _ = H.synth_slab(H.SEED_BASE + 6, 4000, L, H.WITH_N)
+    seq[1000:2000] = seq[:1000]            # same bytes, different lengths => different keys
+    lens = rng.integers(1, L + 1, size=4000).astype(np.int32)
+    lens[1000:1500] = lens[:500]           # ... except these, which are true duplicates
+    mask = np.arange(seq.shape[1])[None, :] >= lens[:, None]
+    seq[mask] = 0
+    check_against_oracle(seq, lens, 0, splits=2)
+    # weights and explicit first indices (what an owner GPU receives from its peers)
+    n = 4000
+    w = rng.integers(1, 50, size=n).astype(np.int32)
+    f = rng.permutation(n).astype(np.int64) * 3
+    oseq, olen, ocnt, ofirst, ohash = gpu_collapse(seq, lens, 0, weight=w, first=f)
+    keys = {}
+    for i in range(n):
+        k = seq[i, :lens[i]].tobytes()
+        c, fm = keys.get(k, (0, 1 << 62))
+        keys[k] = (c + int(w[i]), min(fm, int(f[i])))
+    got = {oseq[k, :olen[k]].tobytes(): (int(ocnt[k]), int(ofirst[k])) for k in range(len(ocnt))}
+    assert got == keys
+    assert all(ocnt[k] >= ocnt[k + 1] for k in range(len(ocnt) - 1))
+
+
+def test_collapse_golden_fixture(ctx):
+    recs = H.read_fastx(os.path.join(H.GOLDEN, "fasta_collapser1.fasta"))
+    seq, _, lens, stride, _ = H.slab_from_records(recs)
+    check_against_oracle(seq, lens, 0)
+    exp = H.read_fastx(os.path.join(H.GOLDEN, "fasta_collapser1.out"))
+    oseq, olen, ocnt, ofirst, _ = gpu_collapse(seq, lens, 0)
+    assert [int(c) for c in ocnt] == [int(r[0].split(b"-")[1]) for r in exp]
+    for k in range(4):
+        assert oseq[k, :olen[k]].tobytes() == exp[k][1]
+
+
+def test_collapse_bad_read_detected(ctx):
+    import fastx_toolkit_b200 as F
+    seq, _ = H.synth_slab(H.SEED_BASE + 4, 3000, 50, H.DUPS)
+    seq[1234, 7] = ord("x")
+    col = F.Collapser(0, 3000, seq.shape[1])
+    col.add(F.Batch(seq.ctypes.data, None, None, 50, seq.shape[1], 3000))
+    col.finish(False)
+    assert col.first_bad == 1234
+    col.close()
+
+
+def test_collapse_sharded_like_multi_gpu(ctx):
+    """The multi-GPU algorithm on one GPU: G shards dedup locally, uniques are routed to owner = hash mod G,
+    owners merge (weights + first indices), the triples are gathered and ordered once.  Must equal the
+    single-table result (and therefore the reference)."""
+    import fastx_toolkit_b200 as F
+    n, L, G = 400000, 50, 3
+    seq, _ = H.synth_slab(H.SEED_BASE + 4, n, L, H.DUPS)
+    stride = seq.shape[1]
+    efirst, ecnt = H.o_collapse(seq, None, L, stride)
+    bounds = np.linspace(0, n, G + 1).astype(np.int64)
+    parts = []
+    for g in range(G):
+        a, b = int(bounds[g]), int(bounds[g + 1])
+        col = F.Collapser(0, b - a, stride)
+        col.add(F.Batch(seq[a:b].ctypes.data, None, None, L, stride, b - a), None, None, a)   # first = global index
+        u = col.finish(False)
+        s = np.zeros((u, stride), np.uint8); ln = np.zeros(u, np.int32)
+        c = np.zeros(u, np.uint64); f = np.zeros(u, np.int64); h = np.zeros(u, np.uint64)
+        col.fetch(s, ln, c, f, h)
+        col.close()
+        parts.append((s, ln, c, f, h))
+    trip = []
+    for owner in range(G):
+        s = np.concatenate([p[0][p[4] % np.uint64(G) == owner] for p in parts])
+        ln = np.concatenate([p[1][p[4] % np.uint64(G) == owner] for p in parts])
+        c = np.concatenate([p[2][p[4] % np.uint64(G) == owner] for p in parts]).astype(np.int32)
+        f = np.concatenate([p[3][p[4] % np.uint64(G) == owner] for p in parts])
+        col = F.Collapser(0, max(len(ln), 1), stride)
+        col.add(F.Batch(s.ctypes.data, None, ln.ctypes.data, 0, stride, len(ln)), c, f, 0)
+        u = col.finish(False)
+        oc = np.zeros(u, np.uint64); of = np.zeros(u, np.int64); oh = np.zeros(u, np.uint64)
+        col.fetch(None, None, oc, of, oh)
+        col.close()
+        trip.append((oh, of, oc))
+    hh = torch.from_numpy(np.concatenate([t[0] for t in trip]).view(np.int64)).cuda()
+    ff = torch.from_numpy(np.concatenate([t[1] for t in trip])).cuda()
+    cc = torch.from_numpy(np.concatenate([t[2] for t in trip]).view(np.int64)).cuda()
+    U = hh.numel()
+    perm = torch.empty(U, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    F.collapse_order_dev(0, hh, ff, cc, U, perm)
+    p = perm.cpu().numpy().astype(np.int64)
+    assert U == len(ecnt)
+    assert np.array_equal(ff.cpu().numpy()[p], efirst)
+    assert np.array_equal(cc.cpu().numpy()[p].astype(np.uint64), ecnt)

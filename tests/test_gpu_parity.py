@@ -17,6 +17,8 @@ torch = pytest.importorskip("torch")
 def ctx():
     import fastx_toolkit_b200 as F
     c = F.Context(0)
+    # run the library on torch's current stream so that torch allocations/fills and our kernels are ordered
+    c.set_stream(torch.cuda.current_stream().cuda_stream)
     yield c
     c.close()
 

@@ -17,6 +17,7 @@ def gpu_hist(ctx, seq, qual, lens, L, Q, max_cycles, weight=None, host=False):
     hist = torch.zeros((max_cycles, 5, 109), dtype=torch.int64, device="cuda")
     ctx.report_reset()
     if host:
+        torch.cuda.synchronize()   # the *_host calls run on the library's own side streams
         rep = ctx.stats_accum_host(ctx.batch(seq, qual, n, stride, L, lens), Q, hist, max_cycles, weight)
     else:
         ctx.stats_accum_dev(ctx.batch(dev(seq), dev(qual), n, stride, L, dev(lens)), Q, hist, max_cycles, dev(weight))
