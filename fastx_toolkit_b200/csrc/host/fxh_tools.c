@@ -1,0 +1,502 @@
+/*
+ * fxh_tools.c — the six drop-in executables as one multi-call program (dispatch on basename(argv[0])):
+ *   fastq_quality_trimmer  fastq_quality_filter  fastx_reverse_complement
+ *   fastx_clipper          fastx_collapser       fastx_quality_stats
+ * Same flags, streams, messages and exit status as FASTX-Toolkit 0.0.14; the per-read loop bodies run on the
+ * GPU through include/fxg.h (no CPU fallback).  Reference mains:
+ *   src/fastq_quality_trimmer/fastq_quality_trimmer.c:52-123   src/fastq_quality_filter/fastq_quality_filter.c:54-178
+ *   src/fastx_reverse_complement/fastx_reverse_complement.c:106-128   src/fastx_clipper/fastx_clipper.cpp:90-350
+ *   src/fastx_collapser/fastx_collapser.cpp:93-138   src/fastx_quality_stats/fastx_quality_stats.c:420-463
+ */
+#define _GNU_SOURCE
+#include <err.h>
+#include <errno.h>
+#include <libgen.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+#include "fxh.h"
+#include "fxh_usage.h"
+
+static void *pinned(size_t bytes)
+{
+    void *p = fxg_alloc_pinned(bytes);
+    if (!p) errx(1, "cannot allocate %zu bytes of pinned host memory", bytes);
+    return p;
+}
+
+/* batch-sized pinned result arrays, grown on demand */
+typedef struct { void *p; size_t cap; } pbuf;
+static void *pbuf_get(pbuf *b, size_t bytes)
+{
+    if (bytes > b->cap) { fxg_free_pinned(b->p); b->p = pinned(bytes); b->cap = bytes; }
+    return b->p;
+}
+
+static int batch_q(const fxh_batch *b) { return b->numeric_qual ? 33 : fxh_q_offset(); }
+
+/* ================================================================================ fastq_quality_trimmer */
+static int tr_min_quality = 0, tr_min_length = 0;
+
+static int tr_args(int oi, int optc, char *oa)
+{
+    (void)oi;
+    switch (optc) {
+    case 'l':
+        if (oa == NULL) errx(1, "[-l] parameter requires an argument value");
+        tr_min_length = (int)strtoul(oa, NULL, 10);
+        if (tr_min_length < 0) errx(1, "Invalid minimum length value (-l %s)", oa);
+        break;
+    case 't':
+        if (oa == NULL) errx(1, "[-t] parameter requires an argument value");
+        tr_min_quality = (int)strtol(oa, NULL, 10);
+        break;
+    default: errx(1, "Unknown argument (%c)", optc);
+    }
+    return 1;
+}
+
+static int main_trimmer(int argc, char **argv)
+{
+    fxh_parse_cmdline(argc, argv, "t:l:", tr_args, fxh_usage_fastq_quality_trimmer);
+    if (tr_min_quality == 0) errx(1, "Missing minimum quality threshold value (-t)");
+    fxh_reader *rd = fxh_reader_open(fxh_input_filename(), FXH_FASTQ_ONLY, fxh_q_offset(), 0);
+    fxh_writer *wr = fxh_writer_open(fxh_output_filename(), 1, fxh_compress_output());
+    fxg_ctx *ctx = fxh_gpu_open();
+    pbuf out = { 0, 0 };
+    fxh_batch *b;
+    while ((b = fxh_reader_next(rd, fxh_batch_reads())) != NULL) {
+        int32_t *out_len = (int32_t *)pbuf_get(&out, (size_t)b->n * sizeof(int32_t));
+        fxg_batch gb = fxh_as_fxg_batch(b, 1);
+        fxg_report rep;
+        fxh_gpu_check(ctx, fxg_trim_host(ctx, &gb, batch_q(b), tr_min_quality, tr_min_length, out_len, &rep), "fxg_trim_host");
+        const int64_t lim = rep.first_bad_read >= 0 ? rep.first_bad_read : b->n;
+        for (int64_t i = 0; i < lim; i++)
+            if (out_len[i] >= 0)
+                fxh_write_record(wr, b, i, b->seq + (size_t)i * b->stride, b->qual + (size_t)i * b->stride, out_len[i]);
+        if (rep.first_bad_read >= 0) { fxh_writer_close(wr); fxh_die_bad_record(rd, b, rep.first_bad_read); }
+    }
+    fxh_writer_close(wr);
+    if (fxh_verbose()) {
+        FILE *f = fxh_report_file();
+        fprintf(f, "Minimum Quality Threshold: %d\n", tr_min_quality);
+        if (tr_min_length > 0) fprintf(f, "Minimum Length: %d\n", tr_min_length);
+        else fprintf(f, "No minimum Length\n");
+        fprintf(f, "Input: %zu reads.\n", fxh_num_input_reads(rd));
+        fprintf(f, "Output: %zu reads.\n", fxh_num_output_reads(wr));
+        size_t discarded = fxh_num_input_reads(rd) - fxh_num_output_reads(wr);
+        fprintf(f, "discarded %zu (%zu%%) too-short reads.\n", discarded, (discarded * 100) / fxh_num_input_reads(rd));
+    }
+    fxg_destroy(ctx);
+    return 0;
+}
+
+/* ================================================================================ fastq_quality_filter */
+static int fl_min_quality = 0, fl_min_percent = 0;
+
+static int fl_args(int oi, int optc, char *oa)
+{
+    (void)oi;
+    switch (optc) {
+    case 'q':
+        if (oa == NULL) errx(1, "[-q] parameter requires an argument value");
+        fl_min_quality = (int)strtoul(oa, NULL, 10);
+        break;
+    case 'p':
+        if (oa == NULL) errx(1, "[-l] parameter requires an argument value");
+        fl_min_percent = (int)strtoul(oa, NULL, 10);
+        if (fl_min_percent <= 0 || fl_min_percent > 100) errx(1, "Invalid percent value (-p %s)", oa);
+        break;
+    default: errx(1, "Unknown argument (%c)", optc);
+    }
+    return 1;
+}
+
+static int main_filter(int argc, char **argv)
+{
+    fxh_parse_cmdline(argc, argv, "q:p:", fl_args, fxh_usage_fastq_quality_filter);
+    fxh_reader *rd = fxh_reader_open(fxh_input_filename(), FXH_FASTQ_ONLY, fxh_q_offset(), 0);
+    fxh_writer *wr = fxh_writer_open(fxh_output_filename(), 1, fxh_compress_output());
+    fxg_ctx *ctx = fxh_gpu_open();
+    pbuf out = { 0, 0 };
+    fxh_batch *b;
+    while ((b = fxh_reader_next(rd, fxh_batch_reads())) != NULL) {
+        uint8_t *keep = (uint8_t *)pbuf_get(&out, (size_t)b->n);
+        fxg_batch gb = fxh_as_fxg_batch(b, 1);
+        fxg_report rep;
+        fxh_gpu_check(ctx, fxg_filter_host(ctx, &gb, batch_q(b), fl_min_quality, fl_min_percent, keep, &rep), "fxg_filter_host");
+        const int64_t lim = rep.first_bad_read >= 0 ? rep.first_bad_read : b->n;
+        for (int64_t i = 0; i < lim; i++)
+            if (keep[i])
+                fxh_write_record(wr, b, i, b->seq + (size_t)i * b->stride, b->qual + (size_t)i * b->stride, b->len[i]);
+        if (rep.first_bad_read >= 0) { fxh_writer_close(wr); fxh_die_bad_record(rd, b, rep.first_bad_read); }
+    }
+    fxh_writer_close(wr);
+    if (fxh_verbose()) {
+        FILE *f = fxh_report_file();
+        fprintf(f, "Quality cut-off: %d\n", fl_min_quality);
+        fprintf(f, "Minimum percentage: %d\n", fl_min_percent);
+        fprintf(f, "Input: %zu reads.\n", fxh_num_input_reads(rd));
+        fprintf(f, "Output: %zu reads.\n", fxh_num_output_reads(wr));
+        size_t discarded = fxh_num_input_reads(rd) - fxh_num_output_reads(wr);
+        fprintf(f, "discarded %zu (%zu%%) low-quality reads.\n", discarded, (discarded * 100) / fxh_num_input_reads(rd));
+    }
+    fxg_destroy(ctx);
+    return 0;
+}
+
+/* ================================================================================ fastx_reverse_complement */
+static int main_revcomp(int argc, char **argv)
+{
+    fxh_parse_cmdline(argc, argv, "", NULL, fxh_usage_fastx_reverse_complement);
+    fxh_reader *rd = fxh_reader_open(fxh_input_filename(), FXH_FASTA_OR_FASTQ, fxh_q_offset(), 0);
+    const int fastq = fxh_reader_is_fastq(rd);
+    fxh_writer *wr = fxh_writer_open(fxh_output_filename(), fastq, fxh_compress_output());
+    fxg_ctx *ctx = fxh_gpu_open();
+    pbuf os = { 0, 0 }, oq = { 0, 0 };
+    fxh_batch *b;
+    while ((b = fxh_reader_next(rd, fxh_batch_reads())) != NULL) {
+        const size_t bytes = (size_t)b->n * b->stride;
+        uint8_t *oseq = (uint8_t *)pbuf_get(&os, bytes), *oqual = fastq ? (uint8_t *)pbuf_get(&oq, bytes) : NULL;
+        fxg_batch gb = fxh_as_fxg_batch(b, fastq);
+        fxg_report rep;
+        fxh_gpu_check(ctx, fxg_revcomp_host(ctx, &gb, batch_q(b), oseq, oqual, &rep), "fxg_revcomp_host");
+        const int64_t lim = rep.first_bad_read >= 0 ? rep.first_bad_read : b->n;
+        for (int64_t i = 0; i < lim; i++)
+            fxh_write_record(wr, b, i, oseq + (size_t)i * b->stride, fastq ? oqual + (size_t)i * b->stride : NULL, b->len[i]);
+        if (rep.first_bad_read >= 0) { fxh_writer_close(wr); fxh_die_bad_record(rd, b, rep.first_bad_read); }
+    }
+    fxh_writer_close(wr);
+    if (fxh_verbose()) {
+        FILE *f = fxh_report_file();
+        fprintf(f, "Printing Reverse-Complement Sequences.\n");
+        fprintf(f, "Input: %zu reads.\n", fxh_num_input_reads(rd));
+        fprintf(f, "Output: %zu reads.\n", fxh_num_output_reads(wr));
+    }
+    fxg_destroy(ctx);
+    return 0;
+}
+
+/* ================================================================================ fastx_clipper */
+static char cl_adapter[FXG_MAX_ADAPTER] = "CCTTAAGG";
+static unsigned int cl_min_length = 5;
+static int cl_discard_unknown = 1, cl_keep_delta = 0, cl_discard_non_clipped = 0, cl_discard_clipped = 0;
+static int cl_show_adapter_only = 0, cl_debug = 0, cl_min_adapter_len = 0;
+
+static int cl_args(int oi, int optc, char *oa)
+{
+    (void)oi;
+    switch (optc) {
+    case 'M':
+        if (oa == NULL) errx(1, "[-M] parameter requires an argument value");
+        cl_min_adapter_len = atoi(oa);
+        if (cl_min_adapter_len <= 0) errx(1, "Invalid minimum adapter length (-M %s)", oa);
+        break;
+    case 'k': cl_show_adapter_only = 1; break;
+    case 'D': cl_debug++; break;
+    case 'c': cl_discard_non_clipped = 1; break;
+    case 'C': cl_discard_clipped = 1; break;
+    case 'd':
+        if (oa == NULL) errx(1, "[-d] parameter requires an argument value");
+        cl_keep_delta = (int)strtoul(oa, NULL, 10);
+        if (cl_keep_delta < 0) errx(1, "Invalid number bases to keep (-d %s)", oa);
+        break;
+    case 'a': strncpy(cl_adapter, oa, sizeof(cl_adapter) - 1); break;
+    case 'l':
+        if (oa == NULL) errx(1, "[-l] parameter requires an argument value");
+        cl_min_length = (unsigned int)strtoul(oa, NULL, 10);
+        break;
+    case 'n': cl_discard_unknown = 0; break;
+    case 's': break;        /* accepted and ignored, like the reference's getopt string (fastx_clipper.cpp:151) */
+    default: errx(1, "Unknown argument (%c)", optc);
+    }
+    return 1;
+}
+
+static int main_clipper(int argc, char **argv)
+{
+    fxh_parse_cmdline(argc, argv, "M:kDCcd:a:s:l:n", cl_args, fxh_usage_fastx_clipper);
+    if (cl_keep_delta > 0) cl_keep_delta += (int)strlen(cl_adapter);
+    if (cl_debug) warnx("[-D] alignment dumps are not produced by the GPU build; the flag is ignored");
+    fxh_reader *rd = fxh_reader_open(fxh_input_filename(), FXH_FASTA_OR_FASTQ, fxh_q_offset(), 1 /* aligner's stale rows */);
+    const int fastq = fxh_reader_is_fastq(rd);
+    fxh_writer *wr = fxh_writer_open(fxh_output_filename(), fastq, fxh_compress_output());
+    fxg_ctx *ctx = fxh_gpu_open();
+    fxg_clip_opts o;
+    o.adapter = cl_adapter; o.min_length = (int32_t)cl_min_length; o.keep_delta = cl_keep_delta;
+    o.discard_non_clipped = cl_discard_non_clipped; o.discard_clipped = cl_discard_clipped;
+    o.discard_unknown = cl_discard_unknown; o.min_adapter_len = cl_min_adapter_len;
+    unsigned int count_input = 0, cnt[6] = { 0, 0, 0, 0, 0, 0 };
+    pbuf ol = { 0, 0 }, oc = { 0, 0 };
+    fxh_batch *b;
+    while ((b = fxh_reader_next(rd, fxh_batch_reads())) != NULL) {
+        int32_t *out_len = (int32_t *)pbuf_get(&ol, (size_t)b->n * sizeof(int32_t));
+        uint8_t *out_cls = (uint8_t *)pbuf_get(&oc, (size_t)b->n);
+        fxg_batch gb = fxh_as_fxg_batch(b, fastq);
+        fxg_report rep;
+        fxh_gpu_check(ctx, fxg_clip_host(ctx, &gb, b->width, batch_q(b), &o, out_len, out_cls, &rep), "fxg_clip_host");
+        const int64_t lim = rep.first_bad_read >= 0 ? rep.first_bad_read : b->n;
+        for (int64_t i = 0; i < lim; i++) {
+            const uint8_t *s = b->seq + (size_t)i * b->stride, *q = b->qual + (size_t)i * b->stride;
+            count_input += (unsigned int)b->weight[i];
+            cnt[out_cls[i]] += (unsigned int)b->weight[i];
+            if (out_cls[i] == FXG_CLIP_ADAPTER_ONLY) {
+                if (cl_show_adapter_only) fxh_write_record(wr, b, i, s, q, b->len[i]);      /* untruncated */
+            } else if (out_cls[i] == FXG_CLIP_WRITE && !cl_show_adapter_only)
+                fxh_write_record(wr, b, i, s, q, out_len[i]);
+        }
+        if (rep.first_bad_read >= 0) { fxh_writer_close(wr); fxh_die_bad_record(rd, b, rep.first_bad_read); }
+    }
+    fxh_writer_close(wr);
+    if (fxh_verbose()) {
+        FILE *f = fxh_report_file();
+        fprintf(f, "Clipping Adapter: %s\n", cl_adapter);
+        fprintf(f, "Min. Length: %d\n", cl_min_length);
+        if (cl_discard_clipped) fprintf(f, "Clipped reads - discarded.\n");
+        if (cl_discard_non_clipped) fprintf(f, "Non-Clipped reads - discarded.\n");
+        fprintf(f, "Input: %u reads.\n", count_input);
+        fprintf(f, "Output: %u reads.\n", count_input - cnt[FXG_CLIP_TOO_SHORT] - cnt[FXG_CLIP_NON_CLIPPED] - cnt[FXG_CLIP_CLIPPED] -
+                                              cnt[FXG_CLIP_HAS_N] - cnt[FXG_CLIP_ADAPTER_ONLY]);
+        fprintf(f, "discarded %u too-short reads.\n", cnt[FXG_CLIP_TOO_SHORT]);
+        fprintf(f, "discarded %u adapter-only reads.\n", cnt[FXG_CLIP_ADAPTER_ONLY]);
+        if (cl_discard_non_clipped) fprintf(f, "discarded %u non-clipped reads.\n", cnt[FXG_CLIP_NON_CLIPPED]);
+        if (cl_discard_clipped) fprintf(f, "discarded %u clipped reads.\n", cnt[FXG_CLIP_CLIPPED]);
+        if (cl_discard_unknown) fprintf(f, "discarded %u N reads.\n", cnt[FXG_CLIP_HAS_N]);
+    }
+    fxg_destroy(ctx);
+    return 0;
+}
+
+/* ================================================================================ fastx_collapser */
+static int main_collapser(int argc, char **argv)
+{
+    fxh_parse_cmdline(argc, argv, "", NULL, fxh_usage_fastx_collapser);
+    fxh_reader *rd = fxh_reader_open(fxh_input_filename(), FXH_FASTA_OR_FASTQ, fxh_q_offset(), 0);
+    const int fastq = fxh_reader_is_fastq(rd);
+    FILE *out = stdout;
+    if (strcmp(fxh_output_filename(), "-") != 0) {
+        out = fopen(fxh_output_filename(), "w");
+        if (!out) errx(1, "Failed to create output file (%s)", fxh_output_filename());
+    }
+    fxg_ctx *ctx = fxh_gpu_open();
+    /* the whole input has to be resident before anything can be printed: keep the bases compactly on the host */
+    uint8_t *bases = NULL; size_t bases_len = 0, bases_cap = 0;
+    int32_t *lens = NULL, *weights = NULL; int64_t n = 0, cap = 0;
+    int maxlen = 0;
+    pbuf keep = { 0, 0 };
+    fxh_batch *b;
+    while ((b = fxh_reader_next(rd, fxh_batch_reads())) != NULL) {
+        int64_t lim = b->n;
+        if (fastq) {   /* FASTQ input: the reader also validates the qualities (K-VALIDATE fused in the filter kernel) */
+            fxg_batch gb = fxh_as_fxg_batch(b, 1);
+            fxg_report rep;
+            fxh_gpu_check(ctx, fxg_filter_host(ctx, &gb, batch_q(b), -100, 100, (uint8_t *)pbuf_get(&keep, (size_t)b->n), &rep), "fxg_filter_host");
+            if (rep.first_bad_read >= 0) fxh_die_bad_record(rd, b, rep.first_bad_read);
+        }
+        if (n + lim > cap) {
+            cap = (n + lim) * 2;
+            lens = (int32_t *)realloc(lens, (size_t)cap * sizeof(int32_t));
+            weights = (int32_t *)realloc(weights, (size_t)cap * sizeof(int32_t));
+            if (!lens || !weights) err(1, "out of memory");
+        }
+        for (int64_t i = 0; i < lim; i++) {
+            const int L = b->len[i];
+            if (bases_len + (size_t)L > bases_cap) {
+                bases_cap = (bases_len + (size_t)L) * 2 + (1u << 20);
+                bases = (uint8_t *)realloc(bases, bases_cap);
+                if (!bases) err(1, "out of memory");
+            }
+            memcpy(bases + bases_len, b->seq + (size_t)i * b->stride, (size_t)L);
+            bases_len += (size_t)L;
+            lens[n] = L; weights[n] = b->weight[i];
+            if (L > maxlen) maxlen = L;
+            n++;
+        }
+    }
+    const int stride = (maxlen + 15) & ~15;
+    fxg_collapser *col = NULL;
+    int rc = fxg_collapse_new(getenv("FASTX_GPU") ? atoi(getenv("FASTX_GPU")) : 0, n > 0 ? n : 1, stride > 0 ? stride : 16, &col);
+    if (rc != FXG_OK) errx(1, "fxg_collapse_new failed: %s", fxg_strerror(rc));
+    {   /* re-pack into fixed-stride rows, a pinned chunk at a time */
+        const int64_t chunk = 1 << 20;
+        uint8_t *rows = (uint8_t *)pinned((size_t)chunk * (size_t)(stride > 0 ? stride : 16));
+        size_t off = 0;
+        for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+            const int64_t nr = (n - r0 < chunk) ? (n - r0) : chunk;
+            for (int64_t i = 0; i < nr; i++) { memcpy(rows + (size_t)i * stride, bases + off, (size_t)lens[r0 + i]); off += (size_t)lens[r0 + i]; }
+            fxg_batch gb = { rows, NULL, lens + r0, 0, stride, nr };
+            rc = fxg_collapse_add(col, &gb, weights + r0, NULL, r0);
+            if (rc != FXG_OK) errx(1, "fxg_collapse_add failed: %s (%s)", fxg_strerror(rc), fxg_collapse_error(col));
+        }
+        fxg_free_pinned(rows);
+    }
+    int64_t U = 0, bad = -1;
+    rc = fxg_collapse_finish(col, 1, &U, &bad);
+    if (rc != FXG_OK) errx(1, "fxg_collapse_finish failed: %s (%s)", fxg_strerror(rc), fxg_collapse_error(col));
+    if (bad >= 0) {   /* an illegal base: line numbers are implied by the record index (the structure was verified) */
+        size_t off = 0;
+        for (int64_t i = 0; i < bad; i++) off += (size_t)lens[i];
+        errx(1, "found invalid nucleotide sequence (%.*s) on line %lld\n", lens[bad], (const char *)bases + off,
+             (long long)(bad * (fastq ? 4 : 2) + 2));
+    }
+    uint8_t *useq = (uint8_t *)malloc((size_t)(U > 0 ? U : 1) * (size_t)(stride > 0 ? stride : 16));
+    int32_t *ulen = (int32_t *)malloc((size_t)(U > 0 ? U : 1) * sizeof(int32_t));
+    uint64_t *ucnt = (uint64_t *)malloc((size_t)(U > 0 ? U : 1) * sizeof(uint64_t));
+    if (!useq || !ulen || !ucnt) err(1, "out of memory");
+    rc = fxg_collapse_fetch(col, useq, ulen, ucnt, NULL, NULL);
+    if (rc != FXG_OK) errx(1, "fxg_collapse_fetch failed: %s (%s)", fxg_strerror(rc), fxg_collapse_error(col));
+    static char obuf[1 << 22];
+    setvbuf(out, obuf, _IOFBF, sizeof obuf);
+    size_t total_reads = 0;
+    for (int64_t k = 0; k < U; k++) {   /* PrintCollapsedSequence, fastx_collapser.cpp:80-85 (count narrowed to int) */
+        const int c = (int)ucnt[k];
+        total_reads += (size_t)c;
+        fprintf(out, ">%zu-%d\n%.*s\n", (size_t)(k + 1), c, ulen[k], (const char *)useq + (size_t)k * stride);
+    }
+    if (out != stdout) fclose(out); else fflush(out);
+    if (fxh_verbose()) {
+        FILE *f = fxh_report_file();
+        fprintf(f, "Input: %zu sequences (representing %zu reads)\n", fxh_num_input_sequences(rd), fxh_num_input_reads(rd));
+        fprintf(f, "Output: %zu sequences (representing %zu reads)\n", (size_t)U, total_reads);
+    }
+    fxg_collapse_free(col);
+    fxg_destroy(ctx);
+    return 0;
+}
+
+/* ================================================================================ fastx_quality_stats */
+static int st_new_format = 0;
+static int st_args(int oi, int optc, char *oa)
+{
+    (void)oi; (void)oa;
+    if (optc == 'N') st_new_format = 1;
+    else errx(1, "Unknown argument (%c)", optc);
+    return 1;
+}
+
+/* Everything the tool prints is derived from one (cycle, nucleotide) histogram h[q+15]
+ * (fastx_quality_stats.c:218-247 get_nth_value, :276-417 printers). */
+typedef struct { int count, min, max; long long sum; const uint64_t *h; int fasta; } nucstat;
+
+static int st_nth(const nucstat *s, int n)
+{
+    if (n == 0) return s->min;
+    if (s->fasta) return 93;     /* no quality bins: the reference's walk stops on the next table's `min` sentinel */
+    int pos = 0;
+    while (n > 0) {
+        if ((long long)s->h[pos] > n) break;
+        n -= (int)s->h[pos];
+        pos++;
+        while (pos < FXG_QBINS && s->h[pos] == 0) pos++;
+    }
+    return pos - 15;
+}
+
+static void st_fill(nucstat *s, const uint64_t *h, int fasta)
+{
+    s->h = h; s->fasta = fasta; s->count = 0; s->min = 100; s->max = -100; s->sum = 0;
+    for (int b = 0; b < FXG_QBINS; b++) {
+        if (!h[b]) continue;
+        s->count += (int)h[b];
+        if (!fasta) {
+            if (s->min == 100) s->min = b - 15;
+            s->max = b - 15;
+            s->sum += (long long)(b - 15) * (long long)h[b];
+        }
+    }
+}
+
+static void st_print_fields(FILE *f, const nucstat *s, const char *lead)
+{
+    const int Q1 = st_nth(s, s->count / 4), Q3 = st_nth(s, s->count * 3 / 4), IQR = Q3 - Q1;
+    const int lw = ((Q1 - IQR * 3 / 2) < s->min) ? s->min : (Q1 - IQR * 3 / 2);
+    const int rw = ((Q3 + IQR * 3 / 2) > s->max) ? s->max : (Q3 + IQR * 3 / 2);
+    volatile double num = (double)s->sum, den = (double)s->count;     /* run-time 0/0 -> "-nan" like the reference */
+    fprintf(f, "%s%d\t%d\t%d\t%lld\t", lead, s->count, s->min, s->max, s->sum);
+    fprintf(f, "%3.2f\t%d\t%d\t%d\t", num / den, Q1, st_nth(s, s->count / 2), Q3);
+    fprintf(f, "%d\t%d\t%d", IQR, lw, rw);
+}
+
+static int main_stats(int argc, char **argv)
+{
+    fxh_parse_cmdline(argc, argv, "N", st_args, fxh_usage_fastx_quality_stats);
+    fxh_reader *rd = fxh_reader_open(fxh_input_filename(), FXH_FASTA_OR_FASTQ, fxh_q_offset(), 0);
+    const int fastq = fxh_reader_is_fastq(rd);
+    FILE *out = stdout;
+    if (strcmp(fxh_output_filename(), "-") != 0) {
+        out = fopen(fxh_output_filename(), "w+");
+        if (out == NULL) err(1, "Failed to create output file (%s)", fxh_output_filename());
+    }
+    fxg_ctx *ctx = fxh_gpu_open();
+    const int max_cycles = FXH_MAX_LINE;
+    const size_t hist_bytes = (size_t)max_cycles * 5 * FXG_QBINS * sizeof(uint64_t);
+    uint64_t *d_hist = (uint64_t *)fxg_alloc_device(ctx, hist_bytes);
+    if (!d_hist) errx(1, "cannot allocate the histogram on the GPU: %s", fxg_last_error(ctx));
+    fxh_gpu_check(ctx, fxg_memset_dev(ctx, d_hist, 0, hist_bytes), "fxg_memset_dev");
+    fxh_gpu_check(ctx, fxg_sync(ctx), "fxg_sync");
+    int maxlen = 0;
+    fxh_batch *b;
+    while ((b = fxh_reader_next(rd, fxh_batch_reads())) != NULL) {
+        fxg_batch gb = fxh_as_fxg_batch(b, fastq);
+        fxg_report rep;
+        fxh_gpu_check(ctx, fxg_stats_accum_host(ctx, &gb, batch_q(b), d_hist, max_cycles, fastq ? NULL : b->weight, &rep), "fxg_stats_accum_host");
+        if (rep.first_bad_read >= 0) fxh_die_bad_record(rd, b, rep.first_bad_read);
+        for (int64_t i = 0; i < b->n; i++) if (b->len[i] > maxlen) maxlen = b->len[i];
+    }
+    const size_t cyc_words = (size_t)5 * FXG_QBINS;
+    uint64_t *hist = (uint64_t *)calloc((size_t)(maxlen + 1) * cyc_words, sizeof(uint64_t));
+    if (!hist) err(1, "out of memory");
+    if (maxlen > 0) fxh_gpu_check(ctx, fxg_memcpy_d2h(ctx, hist, d_hist, (size_t)maxlen * cyc_words * sizeof(uint64_t)), "fxg_memcpy_d2h");
+
+    static const char *names[6] = { "ALL", "A", "C", "G", "T", "N" };
+    static const char *cols[11] = { "count", "min", "max", "sum", "mean", "Q1", "med", "Q3", "IQR", "lW", "rW" };
+    uint64_t all[FXG_QBINS];
+    nucstat s[6];
+    int max_count = 0;
+    if (st_new_format) {
+        fprintf(out, "cycle\tmax_count");
+        for (int nuc = 0; nuc < 6; nuc++) for (int k = 0; k < 11; k++) fprintf(out, "\t%s_%s", names[nuc], cols[k]);
+        fprintf(out, "\n");
+    } else {
+        fprintf(out, "column\tcount\tmin\tmax\tsum\tmean\tQ1\tmed\tQ3\tIQR\tlW\trW\tA_Count\tC_Count\tG_Count\tT_Count\tN_Count\tMax_count\n");
+    }
+    for (int c = 0; c < maxlen; c++) {
+        const uint64_t *hc = hist + (size_t)c * cyc_words;
+        for (int q = 0; q < FXG_QBINS; q++) all[q] = hc[q] + hc[FXG_QBINS + q] + hc[2 * FXG_QBINS + q] + hc[3 * FXG_QBINS + q] + hc[4 * FXG_QBINS + q];
+        st_fill(&s[0], all, !fastq);
+        for (int nuc = 0; nuc < 5; nuc++) st_fill(&s[1 + nuc], hc + (size_t)nuc * FXG_QBINS, !fastq);
+        if (s[0].count == 0) break;
+        if (c == 0) max_count = s[0].count;
+        if (st_new_format) {
+            fprintf(out, "%d\t%d", c + 1, max_count);
+            for (int nuc = 0; nuc < 6; nuc++) st_print_fields(out, &s[nuc], "\t");
+            fprintf(out, "\n");
+        } else {
+            fprintf(out, "%d\t", c + 1);
+            st_print_fields(out, &s[0], "");
+            fprintf(out, "\t%d\t%d\t%d\t%d\t%d\t%d\n", s[1].count, s[2].count, s[3].count, s[4].count, s[5].count, max_count);
+        }
+    }
+    if (out != stdout) fclose(out); else fflush(out);
+    fxg_free_device(ctx, d_hist);
+    fxg_destroy(ctx);
+    return 0;
+}
+
+/* ================================================================================ dispatch */
+int main(int argc, char **argv)
+{
+    char *self = strdup(argv[0]);
+    const char *name = basename(self);
+    if (!strcmp(name, "fastq_quality_trimmer")) return main_trimmer(argc, argv);
+    if (!strcmp(name, "fastq_quality_filter")) return main_filter(argc, argv);
+    if (!strcmp(name, "fastx_reverse_complement")) return main_revcomp(argc, argv);
+    if (!strcmp(name, "fastx_clipper")) return main_clipper(argc, argv);
+    if (!strcmp(name, "fastx_collapser")) return main_collapser(argc, argv);
+    if (!strcmp(name, "fastx_quality_stats")) return main_stats(argc, argv);
+    fprintf(stderr, "%s: multi-call binary; invoke it as fastq_quality_trimmer, fastq_quality_filter, fastx_reverse_complement, "
+                    "fastx_clipper, fastx_collapser or fastx_quality_stats\n", name);
+    return 1;
+}

@@ -51,7 +51,8 @@ def test_hash_matches_std_hash(ctx):
     seq, _ = H.synth_slab(H.SEED_BASE + 4, n, L, H.WITH_N)
     lens = H.ragged(seq, None, np.random.default_rng(1), min_len=1)
     out = torch.empty(n, dtype=torch.int64, device="cuda")
-    ctx.hash_dev(ctx.batch(dev(seq), None, n, seq.shape[1], 0, dev(lens)), out)
+    dseq, dlens = dev(seq), dev(lens)
+    ctx.hash_dev(ctx.batch(dseq, None, n, seq.shape[1], 0, dlens), out)
     ctx.sync()
     got = out.cpu().numpy().astype(np.uint64)
     O = H.oracle()

@@ -20,7 +20,8 @@ def gpu_hist(ctx, seq, qual, lens, L, Q, max_cycles, weight=None, host=False):
         torch.cuda.synchronize()   # the *_host calls run on the library's own side streams
         rep = ctx.stats_accum_host(ctx.batch(seq, qual, n, stride, L, lens), Q, hist, max_cycles, weight)
     else:
-        ctx.stats_accum_dev(ctx.batch(dev(seq), dev(qual), n, stride, L, dev(lens)), Q, hist, max_cycles, dev(weight))
+        keep = [dev(seq), dev(qual), dev(lens), dev(weight)]   # device copies must outlive the launch
+        ctx.stats_accum_dev(ctx.batch(keep[0], keep[1], n, stride, L, keep[2]), Q, hist, max_cycles, keep[3])
         rep = ctx.sync()
     return hist.cpu().numpy().astype(np.uint64), rep
 
@@ -98,7 +99,8 @@ def gpu_clip(ctx, seq, qual, lens, widths, L, adapter, opts_kw, host=False):
         d_len = torch.empty(n, dtype=torch.int32, device="cuda")
         d_cls = torch.empty(n, dtype=torch.uint8, device="cuda")
         d_cut = torch.empty(n, dtype=torch.int32, device="cuda")
-        ctx.clip_dev(ctx.batch(dev(seq), dev(qual), n, stride, L, dev(lens)), dev(widths), 33, o, d_len, d_cls, d_cut)
+        keep = [dev(seq), dev(qual), dev(lens), dev(widths)]
+        ctx.clip_dev(ctx.batch(keep[0], keep[1], n, stride, L, keep[2]), keep[3], 33, o, d_len, d_cls, d_cut)
         rep = ctx.sync()
         out_len, out_cls, out_cut = d_len.cpu().numpy(), d_cls.cpu().numpy(), d_cut.cpu().numpy()
     e_len, e_cls, e_cut = exp
@@ -157,7 +159,8 @@ def test_clip_tiny_and_host_and_fasta(ctx):
                    discard_unknown=1, min_adapter_len=0)
     d_len = torch.empty(5000, dtype=torch.int32, device="cuda")
     ctx.report_reset()
-    ctx.clip_dev(ctx.batch(dev(s2), dev(q2), 5000, 160, 150), None, 33, o, d_len)
+    ds2, dq2 = dev(s2), dev(q2)
+    ctx.clip_dev(ctx.batch(ds2, dq2, 5000, 160, 150), None, 33, o, d_len)
     assert ctx.sync().first_bad_read == 12
 
 
@@ -192,7 +195,8 @@ def test_clip_golden_fixture(ctx):
     n = len(recs)
     d_len = torch.empty(n, dtype=torch.int32, device="cuda")
     ctx.report_reset()
-    ctx.clip_dev(ctx.batch(dev(seq), dev(qual), n, stride, 0, dev(lens)), None, 64, o, d_len)
+    keep = [dev(seq), dev(qual), dev(lens)]
+    ctx.clip_dev(ctx.batch(keep[0], keep[1], n, stride, 0, keep[2]), None, 64, o, d_len)
     rep = ctx.sync()
     assert rep.first_bad_read == -1
     assert emit(recs, d_len.cpu().numpy(), 64) == golden("fastx_clipper1a.out")

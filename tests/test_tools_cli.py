@@ -1,0 +1,242 @@
+"""Drop-in executables (bin/, host C + libfxg.so) vs the unmodified reference binaries (oracle/_ref/).
+CPU part: everything that is decided before the GPU is touched (usage, flag errors, format sniffing).
+GPU part (-m gpu): byte-identical stdout / stderr / exit status on fixtures, synthetic and broken inputs."""
+import gzip
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+BIN = os.path.join(H.ROOT, "bin")
+TOOLS = ["fastq_quality_trimmer", "fastq_quality_filter", "fastx_reverse_complement", "fastx_clipper",
+         "fastx_collapser", "fastx_quality_stats"]
+
+needs_ref = pytest.mark.skipif(H.ref_tool("fastq_quality_trimmer") is None, reason="oracle/_ref not built")
+needs_bin = pytest.mark.skipif(not os.path.exists(os.path.join(BIN, "fastx_clipper")), reason="bin/ not built (make tools)")
+
+
+def run_tool(exe, args, stdin=None):
+    r = subprocess.run([exe] + args, input=stdin, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    return r.returncode, r.stdout, r.stderr
+
+
+def both(tool, args, stdin=None):
+    m, r = run_tool(os.path.join(BIN, tool), args, stdin), run_tool(H.ref_tool(tool), args, stdin)
+    # getopt prints argv[0] verbatim: strip the two install directories before comparing
+    m = (m[0], m[1], m[2].replace((BIN + "/").encode(), b""))
+    r = (r[0], r[1], r[2].replace((H.REF_BIN + "/").encode(), b""))
+    return m, r
+
+
+def assert_same(tool, args, stdin=None):
+    mine, ref = both(tool, args, stdin)
+    assert mine[0] == ref[0], (tool, args, mine[2][-300:], ref[2][-300:])
+    assert mine[1] == ref[1], (tool, args, "stdout differs")
+    assert mine[2] == ref[2], (tool, args, mine[2][-300:], ref[2][-300:])
+    return ref
+
+
+# ----------------------------------------------------------------------------------------- CPU part
+@needs_ref
+@needs_bin
+@pytest.mark.parametrize("tool", TOOLS)
+def test_usage_and_flag_errors_match_reference(tool, tmp_path):
+    assert_same(tool, ["-h"])
+    assert_same(tool, ["-Z"])                      # unknown flag: getopt message + "use '-h'..." + exit 1
+    assert_same(tool, ["-i", str(tmp_path / "does_not_exist.fq")] + (["-t", "5"] if tool == "fastq_quality_trimmer" else []))
+    empty = tmp_path / "empty.fq"
+    empty.write_bytes(b"")
+    assert_same(tool, ["-i", str(empty)] + (["-t", "5"] if tool == "fastq_quality_trimmer" else []))
+    junk = tmp_path / "junk.txt"
+    junk.write_bytes(b"hello\nworld\n")
+    assert_same(tool, ["-i", str(junk)] + (["-t", "5"] if tool == "fastq_quality_trimmer" else []))
+
+
+@needs_ref
+@needs_bin
+def test_tool_specific_argument_errors(tmp_path):
+    fa = tmp_path / "x.fa"
+    fa.write_bytes(b">a\nACGT\n")
+    assert_same("fastq_quality_trimmer", ["-i", str(fa)])                   # missing -t
+    assert_same("fastq_quality_trimmer", ["-t", "20", "-i", str(fa)])       # FASTA to a FASTQ-only tool
+    assert_same("fastq_quality_filter", ["-p", "0", "-i", str(fa)])
+    assert_same("fastq_quality_filter", ["-p", "101", "-i", str(fa)])
+    assert_same("fastq_quality_filter", ["-q", "20", "-p", "50", "-i", str(fa)])
+    assert_same("fastx_clipper", ["-M", "0", "-i", str(fa)])
+
+
+# ----------------------------------------------------------------------------------------- GPU part
+gpu = pytest.mark.gpu
+
+
+def synth_fastq(path, n, L, kind, lens_rng=None, crlf=False):
+    seq, qual = H.synth_slab(H.SEED_BASE + 11, n, L, kind)
+    lens = H.ragged(seq, qual, lens_rng, min_len=6) if lens_rng is not None else None
+    H.write_fastq(path, seq, qual, lens, L)
+    if crlf:
+        data = open(path, "rb").read().replace(b"\n", b"\r\n")
+        open(path, "wb").write(data)
+    return seq, qual, lens
+
+
+@gpu
+@needs_ref
+def test_golden_fixtures_through_the_binaries():
+    G = H.GOLDEN
+    cases = [
+        ("fastq_quality_trimmer", ["-Q", "64", "-t", "30", "-l", "16"], "fastq_quality_trimmer.fastq", "fastq_quality_trimmer.out"),
+        ("fastq_quality_filter", ["-Q", "64", "-q", "33", "-p", "100"], "fastq_qual_filter1.fastq", "fastq_qual_filter1a.out"),
+        ("fastq_quality_filter", ["-Q", "64", "-q", "20", "-p", "80"], "fastq_qual_filter1.fastq", "fastq_qual_filter1b.out"),
+        ("fastx_clipper", ["-Q", "64", "-l", "15", "-a", "CAATTGGTTAATCCCCCTATATA", "-d", "0", "-n", "-c"], "fastx_clipper1.fastq", "fastx_clipper1a.out"),
+        ("fastx_reverse_complement", [], "fastx_rev_comp1.fasta", "fastx_reverse_complement1.out"),
+        ("fastx_reverse_complement", ["-Q", "64"], "fastx_rev_comp2.fastq", "fastx_reverse_complement2.out"),
+        ("fastx_quality_stats", ["-Q", "64"], "fastq_stats1.fastq", "fastq_stats1.out"),
+    ]
+    for tool, args, fin, fout in cases:
+        rc, out, errs = run_tool(os.path.join(BIN, tool), args + ["-i", os.path.join(G, fin)])
+        assert rc == 0, errs
+        assert out == open(os.path.join(G, fout), "rb").read(), (tool, args)
+        assert_same(tool, args + ["-v", "-i", os.path.join(G, fin)])
+    # collapser: the fixture pins only the distinct-count ranks; the binary pins the rest
+    assert_same("fastx_collapser", ["-v", "-i", os.path.join(G, "fasta_collapser1.fasta")])
+
+
+@gpu
+@needs_ref
+@pytest.mark.parametrize("L,kind,ragged,crlf", [(100, H.PLAIN, False, False), (150, H.WITH_N, False, False),
+                                                 (75, H.WITH_N, True, False), (50, H.PLAIN, False, True)])
+def test_trim_filter_revcomp_stats_binaries(tmp_path, L, kind, ragged, crlf):
+    fq = str(tmp_path / "in.fq")
+    synth_fastq(fq, 30000, L, kind, np.random.default_rng(L) if ragged else None, crlf)
+    os.environ["FASTX_BATCH_READS"] = "7001"          # several batches, with a ragged last one
+    try:
+        assert_same("fastq_quality_trimmer", ["-t", "20", "-l", "20", "-v", "-i", fq])
+        assert_same("fastq_quality_trimmer", ["-t", "35", "-i", fq])
+        assert_same("fastq_quality_filter", ["-q", "20", "-p", "90", "-v", "-i", fq])
+        assert_same("fastq_quality_filter", ["-q", "30", "-i", fq])          # -p defaults to 0
+        assert_same("fastx_reverse_complement", ["-v", "-i", fq])
+        assert_same("fastx_quality_stats", ["-i", fq])
+        assert_same("fastx_quality_stats", ["-N", "-i", fq])
+        assert_same("fastq_quality_trimmer", ["-t", "20"], stdin=open(fq, "rb").read())   # stdin -> stdout
+    finally:
+        os.environ.pop("FASTX_BATCH_READS", None)
+
+
+@gpu
+@needs_ref
+def test_output_file_report_stream_and_gzip(tmp_path):
+    fq = str(tmp_path / "in.fq")
+    synth_fastq(fq, 5000, 100, H.PLAIN)
+    o1, o2 = str(tmp_path / "mine.fq"), str(tmp_path / "ref.fq")
+    m = run_tool(os.path.join(BIN, "fastq_quality_trimmer"), ["-t", "20", "-l", "20", "-v", "-i", fq, "-o", o1])
+    r = run_tool(H.ref_tool("fastq_quality_trimmer"), ["-t", "20", "-l", "20", "-v", "-i", fq, "-o", o2])
+    assert m == r and open(o1, "rb").read() == open(o2, "rb").read()       # report goes to stdout with -o
+    z1, z2 = str(tmp_path / "mine.gz"), str(tmp_path / "ref.gz")
+    m = run_tool(os.path.join(BIN, "fastq_quality_filter"), ["-q", "20", "-p", "80", "-z", "-i", fq, "-o", z1])
+    r = run_tool(H.ref_tool("fastq_quality_filter"), ["-q", "20", "-p", "80", "-z", "-i", fq, "-o", z2])
+    assert m[0] == r[0] == 0
+    import time
+    time.sleep(0.5)   # the reference does not wait for its gzip child
+    assert gzip.open(z1).read() == gzip.open(z2).read()
+
+
+@gpu
+@needs_ref
+def test_numeric_quality_and_fasta_inputs(tmp_path):
+    G = H.GOLDEN
+    num = os.path.join(G, "fastx_rev_comp2.fastq")
+    assert_same("fastq_quality_trimmer", ["-t", "20", "-l", "5", "-i", num])
+    assert_same("fastq_quality_filter", ["-q", "10", "-p", "50", "-v", "-i", num])
+    assert_same("fastx_quality_stats", ["-i", num])
+    assert_same("fastx_clipper", ["-a", "AGATCGG", "-l", "5", "-v", "-i", num])
+    assert_same("fastx_collapser", ["-i", num])
+    fa = str(tmp_path / "in.fa")
+    seq, _ = H.synth_slab(H.SEED_BASE + 4, 20000, 40, H.DUPS)
+    H.write_fasta(fa, seq, None, 40, prefix="5-")          # ids "5-<i>": collapsed-style counts (get_reads_count)
+    assert_same("fastx_reverse_complement", ["-v", "-i", fa])
+    assert_same("fastx_collapser", ["-v", "-i", fa])
+    assert_same("fastx_clipper", ["-a", "ACGTACGT", "-v", "-n", "-i", fa])
+    assert_same("fastx_quality_stats", ["-i", fa])
+    assert_same("fastx_quality_stats", ["-N", "-i", fa])
+
+
+@gpu
+@needs_ref
+def test_clipper_binaries(tmp_path):
+    fq = str(tmp_path / "in.fq")
+    synth_fastq(fq, 20000, 60, H.ADAPTER)
+    for args in (["-a", "AGATCGGAAGAGC", "-l", "20", "-v"], ["-a", "AGATCGGAAGAGC", "-l", "20", "-n", "-c", "-v"],
+                 ["-a", "AGATCGGAAGAGC", "-C", "-v"], ["-a", "AGATCGGAAGAGC", "-d", "3", "-n"], ["-a", "AGATCGGAAGAGC", "-k", "-v"],
+                 ["-a", "AGATCGGAAGAGC", "-M", "8", "-v"], ["-v"]):
+        assert_same("fastx_clipper", args + ["-i", fq])
+    # mixed lengths: the reference's grow-only matrix reads stale bytes of earlier reads
+    fq2 = str(tmp_path / "mixed.fq")
+    synth_fastq(fq2, 20000, 60, H.ADAPTER, np.random.default_rng(3))
+    os.environ["FASTX_BATCH_READS"] = "3001"
+    try:
+        for args in (["-a", "AGATCGGAAGAGC", "-l", "5", "-C", "-n", "-v"], ["-a", "AGATCGGAAGAGC", "-l", "5", "-c", "-v"],
+                     ["-a", "AGATCGGAAGAGC", "-l", "5", "-v"]):
+            assert_same("fastx_clipper", args + ["-i", fq2])
+    finally:
+        os.environ.pop("FASTX_BATCH_READS", None)
+
+
+@gpu
+@needs_ref
+def test_collapser_binary_large(tmp_path):
+    fa = str(tmp_path / "in.fa")
+    seq, _ = H.synth_slab(H.SEED_BASE + 4, 300000, 50, H.DUPS)
+    H.write_fasta(fa, seq, None, 50)
+    assert_same("fastx_collapser", ["-v", "-i", fa])
+    fq = str(tmp_path / "in.fq")
+    synth_fastq(fq, 50000, 36, H.DUPS)
+    assert_same("fastx_collapser", ["-i", fq])
+
+
+@gpu
+@needs_ref
+def test_broken_inputs_fail_like_the_reference(tmp_path):
+    """prefix of the output, then the reference's message and exit status 1"""
+    seq, qual = H.synth_slab(H.SEED_BASE + 12, 12000, 50, H.PLAIN)
+    base = str(tmp_path / "good.fq")
+    H.write_fastq(base, seq, qual, None, 50)
+    lines = open(base, "rb").read().split(b"\n")[:-1]
+
+    def variant(name, edit):
+        ls = list(lines)
+        edit(ls)
+        p = str(tmp_path / name)
+        open(p, "wb").write(b"\n".join(ls) + b"\n")
+        return p
+
+    def set_line(i, v):
+        return lambda ls: ls.__setitem__(i, v)
+
+    bad = [
+        variant("badbase.fq", set_line(4 * 9000 + 1, b"ACGTACGTxCGT" + b"A" * 38)),
+        variant("lower.fq", set_line(4 * 10 + 1, b"acgt" * 12 + b"AC")),
+        variant("badqual_low.fq", set_line(4 * 7000 + 3, b"I" * 49 + b"\x05")),
+        variant("badqual_hi.fq", set_line(4 * 3 + 3, b"I" * 20 + b"\x7f" + b"I" * 29)),
+        variant("noat.fq", set_line(4 * 5000, b"r5000")),
+        variant("emptyseq.fq", lambda ls: (ls.__setitem__(4 * 100 + 1, b""), ls.__setitem__(4 * 100 + 3, b""))),
+        variant("trunc3.fq", lambda ls: ls.__delitem__(slice(4 * 11000 + 2, None))),
+        variant("trunc4.fq", lambda ls: ls.__delitem__(slice(4 * 11000 + 3, None))),
+        variant("blankend.fq", lambda ls: ls.append(b"")),
+        variant("qualshort.fq", set_line(4 * 8000 + 3, b"I" * 30)),
+        variant("two_errors.fq", lambda ls: (ls.__setitem__(4 * 6000 + 3, b"I" * 49 + b"\x01"), ls.__setitem__(4 * 2000 + 1, b"N" * 49 + b"U"))),
+        variant("base_and_trunc.fq", lambda ls: (ls.__setitem__(4 * 11000 + 1, b"ACGU" + b"A" * 46), ls.__delitem__(slice(4 * 11000 + 3, None)))),
+    ]
+    os.environ["FASTX_BATCH_READS"] = "2500"
+    try:
+        for p in bad:
+            assert_same("fastq_quality_trimmer", ["-t", "20", "-l", "10", "-i", p])
+            assert_same("fastq_quality_filter", ["-q", "20", "-p", "50", "-i", p])
+            assert_same("fastx_reverse_complement", ["-i", p])
+            assert_same("fastx_clipper", ["-a", "AGATCGGAAGAGC", "-n", "-i", p])
+            assert_same("fastx_quality_stats", ["-i", p])
+            assert_same("fastx_collapser", ["-i", p])
+    finally:
+        os.environ.pop("FASTX_BATCH_READS", None)
