@@ -431,6 +431,7 @@ void fxh_die_bad_record(const fxh_reader *r, const fxh_batch *b, int64_t idx)
  * ---------------------------------------------------------------------------------------------- */
 struct fxh_writer {
     int fd;
+    int closed;
     pid_t gzip_pid;
     int fastq;
     char *buf;
@@ -461,10 +462,20 @@ static int open_output_compressor(const char *filename, pid_t *pid)
     return 0;
 }
 
+/* errx()/exit() must not lose buffered records: the reference's stdio buffers are flushed at exit too */
+static fxh_writer *g_open_writer = NULL;
+static void writer_flush(fxh_writer *w);
+static void flush_at_exit(void)
+{
+    if (g_open_writer) fxh_writer_close(g_open_writer);
+}
+
 fxh_writer *fxh_writer_open(const char *filename, int fastq, int compress)
 {
     fxh_writer *w = (fxh_writer *)calloc(1, sizeof *w);
     if (!w) err(1, "out of memory");
+    if (!g_open_writer) atexit(flush_at_exit);
+    g_open_writer = w;
     w->fd = compress ? open_output_compressor(filename, &w->gzip_pid) : open_output_file(filename);
     w->fastq = fastq;
     w->cap = (size_t)16 << 20;
@@ -519,6 +530,9 @@ void fxh_write_record(fxh_writer *w, const fxh_batch *b, int64_t i, const uint8_
 
 void fxh_writer_close(fxh_writer *w)
 {
+    if (w->closed) return;
+    w->closed = 1;
+    if (g_open_writer == w) g_open_writer = NULL;
     writer_flush(w);
     if (w->fd != STDOUT_FILENO) close(w->fd);
     if (w->gzip_pid > 0) { int st; waitpid(w->gzip_pid, &st, 0); }   /* let gzip finish before we exit */
