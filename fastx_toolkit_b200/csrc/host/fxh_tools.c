@@ -413,7 +413,9 @@ static void st_print_fields(FILE *f, const nucstat *s, const char *lead)
     const int Q1 = st_nth(s, s->count / 4), Q3 = st_nth(s, s->count * 3 / 4), IQR = Q3 - Q1;
     const int lw = ((Q1 - IQR * 3 / 2) < s->min) ? s->min : (Q1 - IQR * 3 / 2);
     const int rw = ((Q3 + IQR * 3 / 2) > s->max) ? s->max : (Q3 + IQR * 3 / 2);
-    volatile double num = (double)s->sum, den = (double)s->count;     /* run-time 0/0 -> "-nan" like the reference */
+    /* the reference keeps `sum` in an unsigned long long: a negative total becomes a huge mean (kept); the
+     * division happens at run time so that 0/0 prints "-nan" like the reference binary */
+    volatile double num = (double)(unsigned long long)s->sum, den = (double)s->count;
     fprintf(f, "%s%d\t%d\t%d\t%lld\t", lead, s->count, s->min, s->max, s->sum);
     fprintf(f, "%3.2f\t%d\t%d\t%d\t", num / den, Q1, st_nth(s, s->count / 2), Q3);
     fprintf(f, "%d\t%d\t%d", IQR, lw, rw);
