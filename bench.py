@@ -31,6 +31,9 @@ METRIC = "Mreads/sec fastq_quality_trimmer 150bp"
 UNIT = "Mreads/s"
 L, STRIDE, Q, T, MINLEN = 150, 160, 33, 20, 20
 ALGO_BYTES_PER_READ = 2 * L + 4          # validate seq + scan qual + 4 B result
+# dram__bytes_read.sum + dram__bytes_write.sum of K-TRIM in profiles/r01_ncu_trim_full.txt (6.4826 GB per 20 M reads):
+# both rows are fetched with their 10 padding bytes (stride 160) plus the 4-byte result.
+NCU_TRAFFIC_BYTES_PER_READ = 324.13
 SEED = 20260925 + 1
 
 
@@ -306,7 +309,8 @@ def main():
             "timing": "CUDA events on the launch stream, barrier+synchronize both sides, max over ranks",
         },
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "fxg::k_scan_w<G=1,TRIM,HAS_SEQ> (warp-private TMA ring, lane per read)", "algorithmic_bytes_per_read": ALGO_BYTES_PER_READ,
+                     "traffic": n * NCU_TRAFFIC_BYTES_PER_READ, "traffic_source": "ncu --set full capture of the same kernel (profiles/r01_ncu_trim_full.txt), bytes/read x reads per launch",
+                     "kernel": "fxg::k_scan_w<G=1,TRIM,HAS_SEQ> (warp-private TMA ring, lane per read)", "algorithmic_bytes_per_read": ALGO_BYTES_PER_READ,
                      "kernel_ms": kernel_ms, "peak_source": peak_src},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * ne * 2 * STRIDE, "d2h_bytes_per_step": world * ne * 4,
                 "reads_per_step_per_gpu": ne, "api": "fxg_trim_host (pinned host slabs -> H2D -> K-TRIM -> D2H int32 per read)",

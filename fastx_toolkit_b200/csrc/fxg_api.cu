@@ -467,23 +467,25 @@ static int stats_enqueue(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint64_
     const size_t hist_al = (((size_t)nw_pass * ST_WBLK) + 127) & ~(size_t)127;
     int t_ring, t_g, t_stages, t_ctas;
     env_tune(&t_ring, &t_g, &t_stages, &t_ctas);
-    const int stages = t_stages > 0 ? t_stages : 1;
-    long rfit = ((long)MAX_DYN_SMEM - (long)hist_al) / ST_WARPS / stages / (2L * b->stride);
-    if (rfit > 32) rfit = 32;
-    const bool fast = b->qual && !weight && rfit >= 8 && t_ring != 0;
+    const int stages = (t_stages > 0 && t_stages <= 2) ? t_stages : 1;
+    const int g = (t_g == 1 || t_g == 2 || t_g == 4) ? t_g : 2;     // lanes per read; 6*g warps per CTA
+    const int warps = ST_WARPS * g;
+    long rfit = ((long)MAX_DYN_SMEM - (long)hist_al) / warps / stages / (2L * b->stride);
+    if (rfit > 32 / g) rfit = 32 / g;
+    const bool fast = b->qual && !weight && rfit * g >= 8 && t_ring != 0;
     if (!fast) {
         CK(ctx, launch_stats_simple(p, ctx->sm_count, st));
         ctx->launches++;
     } else {
         p.tile_reads = (int)rfit; p.stages = stages;
-        const uint32_t smem = (uint32_t)(hist_al + (size_t)ST_WARPS * stages * 2 * b->stride * rfit);
+        const uint32_t smem = (uint32_t)(hist_al + (size_t)warps * stages * 2 * b->stride * rfit);
         const int64_t ntiles = (b->n + rfit - 1) / rfit;
         int64_t grid = ctx->sm_count;
-        const int64_t need = (ntiles + ST_WARPS - 1) / ST_WARPS;
+        const int64_t need = (ntiles + warps - 1) / warps;
         if (grid > need) grid = need;
         for (int w0 = 0; w0 < words; w0 += nw_pass) {     // reads longer than 160 bases: one pass per 160 cycles
             p.w0 = w0; p.nw = (words - w0 < nw_pass) ? (words - w0) : nw_pass;
-            CK(ctx, launch_stats(p, (int)grid, smem, st));
+            CK(ctx, launch_stats(p, g, (int)grid, smem, st));
             ctx->launches++;
         }
     }
@@ -515,7 +517,7 @@ static int clip_enqueue(fxg_ctx *ctx, const fxg_batch *b, const int32_t *width, 
     p.min_length = o->min_length; p.keep_delta = o->keep_delta; p.discard_non_clipped = o->discard_non_clipped;
     p.discard_clipped = o->discard_clipped; p.discard_unknown = o->discard_unknown; p.min_adapter_len = o->min_adapter_len;
     p.out_len = out_len; p.out_class = out_class; p.out_cut = out_cut; p.index_base = index_base; p.counters = ctx->d_counters;
-    CK(ctx, launch_clip(p, ctx->sm_count, st));
+    CK(ctx, launch_clip(p, ctx->sm_count, (width || b->len) ? b->stride : b->uniform_len, st));
     ctx->launches++;
     ctx->report.n_in += b->n;
     return FXG_OK;

@@ -13,6 +13,8 @@
 // arithmetic is the reference's: fp32 adds of {+1, -1, 0.1f, 0, -5} in the same order, strict '>' in the
 // same candidate order (diagonal, up, left), first maximum in (x outer, y inner) scan order wins.
 // ALU-bound (13*L dependent cell updates per ~L bytes): reported as cell updates/s, not against HBM.
+#include <stdlib.h>
+
 #include "fxg_kernels.cuh"
 
 namespace fxg {
@@ -173,15 +175,148 @@ __global__ void __launch_bounds__(128) k_clip(const __grid_constant__ ClipParams
     }
 }
 
-cudaError_t launch_clip(const ClipParams &p, int sm_count, cudaStream_t st)
+// ------------------------------------------------------------------------------------------------
+// Fast variant: score column in registers + a bit-packed ORIGIN matrix (2 bits per cell, one word per
+// query column, in per-thread local memory) + the reference's own backtrace from the best cell
+// (sequence_alignment.cpp:496-604).  ~3x fewer instructions per cell than carrying the payload forward,
+// because a cell costs three fp32 adds, two compares and their selects, nothing else.
+// Used when the matrix width fits MAXW columns and the adapter fits one word per column.
+// ------------------------------------------------------------------------------------------------
+template <int HMAX, typename WordT, bool FIRST>
+__device__ __forceinline__ WordT clip_column_bits(const ClipParams &P, int H, int x, uint32_t qc, float (&ps)[HMAX],
+                                                  float &best, int &bx, int &by)
+{
+    const bool qn = qc == (uint32_t)'N';
+    WordT word = 0;
+    float up_s = 0.0f;      // score (x, y-1)
+    float diag_s = 0.0f;    // score (x-1, y-1)
+#pragma unroll
+    for (int y = 0; y < HMAX; y++) {
+        if (y >= H) break;
+        const uint32_t tc = P.adapter[y];
+        const bool tn = tc == (uint32_t)'N';
+        const float ms = (qn && tn) ? 0.0f : ((qn || tn) ? 0.1f : ((qc == tc) ? 1.0f : -1.0f));
+        float left = (FIRST ? target_border(y) : ps[y]) + GAP;
+        if (y > 3 && y - 3 > x) left = -100000.0f;
+        const float up = (y == 0 ? 0.0f : up_s) + GAP;
+        const float ul = ((y == 0) ? 0.0f : (FIRST ? target_border(y - 1) : diag_s)) + ms;
+        if (!FIRST) diag_s = ps[y];
+        float sc = ul;
+        WordT o = 3;                                   // FROM_UPPER_LEFT
+        if (up > sc) { sc = up; o = 1; }               // FROM_UPPER
+        if (left > sc) { sc = left; o = 2; }           // FROM_LEFT
+        word |= o << (2 * y);
+        ps[y] = sc;
+        up_s = sc;
+        if (sc > best) { best = sc; bx = x; by = y; }
+    }
+    return word;
+}
+
+template <int HMAX, int MAXW, typename WordT>
+__global__ void __launch_bounds__(128) k_clip_bits(const __grid_constant__ ClipParams P)
+{
+    const int H = P.alen;
+    const int lane = threadIdx.x & 31;
+    for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ll; base < P.n; base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t g = base + lane;
+        const bool active = g < P.n;
+        int cls = -1;
+        if (active) {
+            int L = P.len ? __ldg(P.len + g) : P.uniform_len;
+            int W = P.width ? __ldg(P.width + g) : L;
+            const bool bad = (L <= 0 || L > P.stride || W < L || W > P.stride || W > MAXW);
+            if (bad) { L = 0; W = 0; }
+            const uint8_t *row = P.seq + (size_t)g * P.stride;
+
+            float ps[HMAX];
+            WordT origin[MAXW];
+            float best = -1000000.0f;
+            int bx = 0, by = 0, firstN = 0x7FFFFFFF;
+            uint32_t badbits = 0;
+            for (int x0 = 0; x0 < W; x0 += 4) {
+                uint32_t wq = __ldg(reinterpret_cast<const uint32_t *>(row + x0));
+                const int nb = (W - x0 < 4) ? (W - x0) : 4;
+                for (int k = 0; k < nb; k++) {
+                    const uint32_t qc = wq & 0xFFu;
+                    wq >>= 8;
+                    const int x = x0 + k;
+                    if (x < L) {
+                        const bool ok = qc == 'A' || qc == 'C' || qc == 'G' || qc == 'T' || qc == 'N';
+                        if (!ok) badbits = 1;
+                        if (qc == 'N' && x < firstN) firstN = x;
+                    }
+                    origin[x] = (x == 0) ? clip_column_bits<HMAX, WordT, true>(P, H, x, qc, ps, best, bx, by)
+                                         : clip_column_bits<HMAX, WordT, false>(P, H, x, qc, ps, best, bx, by);
+                }
+            }
+            // backtrace from the best cell: find_optimal_alignment_from_point, sequence_alignment.cpp:496-604
+            uint32_t lo = 0, hi = 0;
+            if (!bad) {
+                int qi = bx, ti = by, matches = 0, mism = 0, neutral = 0, gaps = 0, qstart = bx, tstart = by;
+                while (qi >= 0 && ti >= 0) {
+                    qstart = qi; tstart = ti;
+                    const uint32_t o = (uint32_t)(origin[qi] >> (2 * ti)) & 3u;
+                    if (o == 2u) { gaps++; qi--; }
+                    else if (o == 3u) {
+                        const uint32_t q = __ldg(row + qi), t = P.adapter[ti];
+                        if (q == 'N' || t == 'N') neutral++; else if (q == t) matches++; else mism++;
+                        qi--; ti--;
+                    } else { gaps++; ti--; }
+                }
+                lo = (uint32_t)matches | ((uint32_t)mism << 7) | ((uint32_t)neutral << 14) | ((uint32_t)tstart << TSTART_SHIFT);
+                hi = (uint32_t)gaps | ((uint32_t)qstart << QSTART_SHIFT);
+            }
+            if (P.qual && !bad) {
+                const uint8_t *qrow = P.qual + (size_t)g * P.stride;
+                for (int c = 0; c * 16 < L; c++) {
+                    const uint4 q = __ldg(reinterpret_cast<const uint4 *>(qrow + c * 16));
+                    const uint32_t qw[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+                    for (int wd = 0; wd < 4; wd++)
+                        badbits |= qual_bad_bits(qw[wd], qw[wd] | HI, P.qk) & HI & head_mask(L - 16 * c - 4 * wd);
+                }
+            }
+            if (badbits || bad) atomicMin(&P.counters[CNT_FIRST_BAD], (unsigned long long)(P.index_base + g));
+
+            const int cut = bad ? -1 : cutoff_index(lo, hi, bx, L, P.min_adapter_len);
+            int newL = L;
+            if (cut > 0) { const int at = cut + P.keep_delta; if (at < newL) newL = at; }
+            if (cut == 0) cls = CLS_ADAPTER_ONLY;
+            else if ((unsigned)newL < (unsigned)P.min_length) cls = CLS_TOO_SHORT;
+            else if (cut == -1 && P.discard_non_clipped) cls = CLS_NON_CLIPPED;
+            else if (cut > 0 && P.discard_clipped) cls = CLS_CLIPPED;
+            else if (P.discard_unknown && firstN < newL) cls = CLS_HAS_N;
+            else cls = CLS_WRITE;
+            P.out_len[g] = (cls == CLS_WRITE) ? newL : -1;
+            if (P.out_class) P.out_class[g] = (uint8_t)cls;
+            if (P.out_cut) P.out_cut[g] = cut;
+        }
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+            const unsigned m = __ballot_sync(0xffffffffu, cls == c);
+            if (lane == 0 && m) atomicAdd(&P.counters[c == 0 ? CNT_OUT : CNT_AUX0 + c], (unsigned long long)__popc(m));
+        }
+    }
+}
+
+cudaError_t launch_clip(const ClipParams &p, int sm_count, int max_width, cudaStream_t st)
 {
     int64_t blocks = (p.n + 127) / 128;
     if (blocks < 1) blocks = 1;
     const int64_t cap = (int64_t)sm_count * 16;
     if (blocks > cap) blocks = cap;
-    if (p.alen <= 16) k_clip<16><<<(unsigned)blocks, 128, 0, st>>>(p);
-    else if (p.alen <= 32) k_clip<32><<<(unsigned)blocks, 128, 0, st>>>(p);
-    else k_clip<100><<<(unsigned)blocks, 128, 0, st>>>(p);   // column spills to local memory: slow but exact
+    const unsigned b = (unsigned)blocks;
+    const char *force = getenv("FXG_CLIP_PAYLOAD");   // experimentation: force the forward-payload kernels
+    if (!(force && force[0] == '1')) {
+        if (p.alen <= 16 && max_width <= 256) { k_clip_bits<16, 256, uint32_t><<<b, 128, 0, st>>>(p); return cudaGetLastError(); }
+        if (p.alen <= 16 && max_width <= 1024) { k_clip_bits<16, 1024, uint32_t><<<b, 128, 0, st>>>(p); return cudaGetLastError(); }
+        if (p.alen <= 32 && max_width <= 256) { k_clip_bits<32, 256, unsigned long long><<<b, 128, 0, st>>>(p); return cudaGetLastError(); }
+        if (p.alen <= 32 && max_width <= 1024) { k_clip_bits<32, 1024, unsigned long long><<<b, 128, 0, st>>>(p); return cudaGetLastError(); }
+    }
+    if (p.alen <= 16) k_clip<16><<<b, 128, 0, st>>>(p);
+    else if (p.alen <= 32) k_clip<32><<<b, 128, 0, st>>>(p);
+    else k_clip<100><<<b, 128, 0, st>>>(p);   // column spills to local memory: slow but exact
     return cudaGetLastError();
 }
 

@@ -76,7 +76,6 @@ struct SynthParams {
 // shared-memory histogram geometry: [word w][byte k][nuc A,C,G,T][q' 0..63] u32 counters; a word block
 // is padded by 36 bytes so that lanes working on consecutive words with equal q' hit distinct banks
 constexpr int ST_WARPS = 6;
-constexpr int ST_THREADS = ST_WARPS * 32;
 constexpr int ST_QWIN = 64;                       // q' = q+15 in [0,64) lives in shared memory
 constexpr int ST_KBLK = 4 * ST_QWIN * 4;          // bytes per (word, byte k): 4 nucs x 64 x u32 = 1024
 constexpr int ST_WBLK = 4 * ST_KBLK + 36;         // bytes per word block
@@ -121,9 +120,9 @@ struct ClipParams {
     unsigned long long *counters;
 };
 
-cudaError_t launch_stats(const StatsParams &p, int grid, uint32_t smem_bytes, cudaStream_t st);
+cudaError_t launch_stats(const StatsParams &p, int g, int grid, uint32_t smem_bytes, cudaStream_t st);
 cudaError_t launch_stats_simple(const StatsParams &p, int sm_count, cudaStream_t st);
-cudaError_t launch_clip(const ClipParams &p, int sm_count, cudaStream_t st);
+cudaError_t launch_clip(const ClipParams &p, int sm_count, int max_width, cudaStream_t st);
 cudaError_t stats_set_smem_attrs();
 cudaError_t launch_hash(const uint8_t *seq, const int32_t *len, int uniform_len, int stride, int64_t n, uint64_t *out, cudaStream_t st);
 

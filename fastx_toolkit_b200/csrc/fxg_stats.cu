@@ -24,11 +24,52 @@ __device__ __forceinline__ void hist_global_add(unsigned long long *hist, int ma
     if (cycle < max_cycles) atomicAdd(&hist[((size_t)cycle * 5 + nuc) * 109 + qp], w);
 }
 
-template <int DUMMY>
-__global__ void __launch_bounds__(ST_THREADS, 1) k_stats(const __grid_constant__ StatsParams P)
+// one 4-byte word (4 consecutive cycles) of one read
+template <bool TAIL>
+__device__ __forceinline__ void stats_word(const StatsParams &P, const QualK &qk, uint32_t sw, uint32_t qw, int wi, int remb,
+                                           uint32_t hs_addr, uint32_t &bads, uint32_t &badq)
+{
+    const uint32_t m = TAIL ? head_mask(remb) : 0xFFFFFFFFu;
+    const uint32_t sel = base_selector(sw);
+    const uint32_t wbad_s = (sw ^ __byte_perm(VLUT_LO, VLUT_HI, sel)) & m;
+    const uint32_t nuc4 = __byte_perm(NLUT_LO, NLUT_HI, sel);
+    const uint32_t wbad_q = qual_bad_bits(qw, qw | HI, qk) & HI & m;
+    bads |= wbad_s;
+    badq |= wbad_q;
+    const int rel = wi - P.w0;
+    if ((wbad_s | wbad_q) != 0 || rel < 0 || rel >= P.nw) return;
+    const uint32_t qp4 = qw - qk.lo4;                     // q+15 per byte (legal bytes: no borrow)
+    const uint32_t blk = hs_addr + (uint32_t)rel * ST_WBLK;
+    if (!TAIL && ((qp4 & 0xC0C0C0C0u) | (nuc4 & 0xFCFCFCFCu)) == 0) {
+        const uint32_t qs4 = qp4 << 2;
+        // offset = q'*4 + nuc*256: byte0 <- qs4.k, byte1 <- nuc4.k, bytes 2,3 <- sign(nuc4.k) = 0
+        const uint32_t o0 = prmt_raw(qs4, nuc4, 0xCC40u), o1 = prmt_raw(qs4, nuc4, 0xDD51u);
+        const uint32_t o2 = prmt_raw(qs4, nuc4, 0xEE62u), o3 = prmt_raw(qs4, nuc4, 0xFF73u);
+        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(blk + o0) : "memory");
+        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(blk + o1 + ST_KBLK) : "memory");
+        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(blk + o2 + 2 * ST_KBLK) : "memory");
+        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(blk + o3 + 3 * ST_KBLK) : "memory");
+    } else {
+        const int nk = TAIL ? remb : 4;
+        for (int k = 0; k < nk; k++) {                    // tail bytes, 'N', or q' >= 64
+            const uint32_t nuc = (nuc4 >> (8 * k)) & 0xFFu, qp = (qp4 >> (8 * k)) & 0xFFu;
+            if (nuc < 4u && qp < (uint32_t)ST_QWIN)
+                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(blk + k * ST_KBLK + nuc * 256u + qp * 4u) : "memory");
+            else
+                hist_global_add(P.hist, P.max_cycles, 4 * wi + k, (int)nuc, (int)qp, 1ull);
+        }
+    }
+}
+
+// G lanes per read (lane j takes words j, j+G, ...), 6*G warps per CTA: the tiles of all warps together always
+// hold 192 reads, so more lanes per read means more resident warps (better latency hiding) for the same smem.
+template <int G>
+__global__ void __launch_bounds__(ST_WARPS * G * 32, 1) k_stats(const __grid_constant__ StatsParams P)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t full_bar[ST_WARPS][MAX_STAGES];
+    constexpr int WARPS = ST_WARPS * G;
+    constexpr int NTHREADS = WARPS * 32;
+    __shared__ __align__(8) uint64_t full_bar[WARPS][2];
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int S = P.stride, stages = P.stages, R = P.tile_reads;
@@ -39,10 +80,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_stats(const __grid_constant__
     uint8_t *wbase = smem + ((hist_bytes + 127u) & ~127u) + (size_t)w * stages * stage_bytes;
     uint64_t *bars = full_bar[w];
     const int64_t ntiles = (P.n + R - 1) / R;
-    const int64_t gw = (int64_t)blockIdx.x * ST_WARPS + w, GW = (int64_t)gridDim.x * ST_WARPS;
+    const int64_t gw = (int64_t)blockIdx.x * WARPS + w, GW = (int64_t)gridDim.x * WARPS;
     const QualK qk = P.qk;
 
-    for (uint32_t i = tid * 4; i < hist_bytes; i += ST_THREADS * 4) *reinterpret_cast<uint32_t *>(hs + i) = 0u;
+    for (uint32_t i = tid * 4; i < hist_bytes; i += NTHREADS * 4) *reinterpret_cast<uint32_t *>(hs + i) = 0u;
     if (lane == 0) {
         for (int s = 0; s < stages; s++) mbar_init(&bars[s], 1);
         mbar_fence_init();
@@ -66,84 +107,49 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_stats(const __grid_constant__
     }
 
     const uint32_t hs_addr = smem_u32(hs);
-    const int w0 = P.w0, nw = P.nw;
+    const int j = lane & (G - 1), rr = lane / G;
     int s = 0;
     uint32_t parity = 0;
 
     for (int64_t tile = gw; tile < ntiles; tile += GW) {
         mbar_wait(&bars[s], parity);
-        const int64_t g = tile * R + lane;
-        const bool active = lane < R && g < P.n;
+        const int64_t g = tile * R + rr;
+        const bool active = rr < R && g < P.n;
         int L = 0;
         if (active) L = P.len ? __ldg(P.len + g) : P.uniform_len;
         const bool lenbad = active && (L <= 0 || L > S);
         if (lenbad) L = 0;
-        const uint8_t *srow = wbase + (size_t)s * stage_bytes + (size_t)(active ? lane : 0) * S;
+        const uint8_t *srow = wbase + (size_t)s * stage_bytes + (size_t)(active ? rr : 0) * S;
         const uint8_t *qrow = srow + slab_bytes;
-        const int nwf = L >> 2;                      // full words of this read
+        const int nwf = L >> 2;                                  // full words of this read
+        const int nk = nwf > j ? (nwf - j + G - 1) / G : 0;      // words of this lane: j, j+G, ...
         uint32_t bads = 0, badq = 0;
 
-        int wi = nwf > 0 ? lane % nwf : 0;           // skewed start
-        for (int t = 0; t < nwf; t++) {
-            const uint32_t sw = *reinterpret_cast<const uint32_t *>(srow + 4 * wi);
-            const uint32_t qw = *reinterpret_cast<const uint32_t *>(qrow + 4 * wi);
-            const uint32_t sel = base_selector(sw);
-            const uint32_t wbad_s = sw ^ __byte_perm(VLUT_LO, VLUT_HI, sel);
-            const uint32_t nuc4 = __byte_perm(NLUT_LO, NLUT_HI, sel);
-            const uint32_t wbad_q = qual_bad_bits(qw, qw | HI, qk) & HI;
-            bads |= wbad_s;
-            badq |= wbad_q;
-            const int rel = wi - w0;
-            if ((wbad_s | wbad_q) == 0 && rel >= 0 && rel < nw) {
-                const uint32_t qp4 = qw - qk.lo4;                     // q+15 per byte (legal bytes: no borrow)
-                if (((qp4 & 0xC0C0C0C0u) | (nuc4 & 0xFCFCFCFCu)) == 0) {
-                    const uint32_t qs4 = qp4 << 2;
-                    const uint32_t blk = hs_addr + (uint32_t)rel * ST_WBLK;
-                    // offset = q'*4 + nuc*256: byte0 <- qs4.k, byte1 <- nuc4.k, bytes 2,3 <- sign(nuc4.k) = 0
-                    const uint32_t o0 = prmt_raw(qs4, nuc4, 0xCC40u), o1 = prmt_raw(qs4, nuc4, 0xDD51u);
-                    const uint32_t o2 = prmt_raw(qs4, nuc4, 0xEE62u), o3 = prmt_raw(qs4, nuc4, 0xFF73u);
-                    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(blk + o0) : "memory");
-                    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(blk + o1 + ST_KBLK) : "memory");
-                    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(blk + o2 + 2 * ST_KBLK) : "memory");
-                    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(blk + o3 + 3 * ST_KBLK) : "memory");
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {                     // 'N' or q' >= 64: global histogram
-                        const int nuc = (nuc4 >> (8 * k)) & 0xFF, qp = (qp4 >> (8 * k)) & 0xFF;
-                        hist_global_add(P.hist, P.max_cycles, 4 * wi + k, nuc, qp, 1ull);
-                    }
-                }
-            }
-            if (++wi == nwf) wi = 0;
+        // skewed start so that the lanes of one instruction work on different cycles; next word prefetched
+        int k = nk > 0 ? rr % nk : 0;
+        uint32_t sw = 0, qw = 0;
+        if (nk > 0) {
+            sw = *reinterpret_cast<const uint32_t *>(srow + 4 * (G * k + j));
+            qw = *reinterpret_cast<const uint32_t *>(qrow + 4 * (G * k + j));
         }
-        // trailing 1..3 bases of the read (only in the pass that covers them)
+        for (int t = 0; t < nk; t++) {
+            const int wi = G * k + j;
+            if (++k == nk) k = 0;
+            const int wn = G * k + j;
+            const uint32_t sw_n = *reinterpret_cast<const uint32_t *>(srow + 4 * wn);
+            const uint32_t qw_n = *reinterpret_cast<const uint32_t *>(qrow + 4 * wn);
+            stats_word<false>(P, qk, sw, qw, wi, 0, hs_addr, bads, badq);
+            sw = sw_n; qw = qw_n;
+        }
+        // trailing 1..3 bases (owned by the lane whose turn it would be)
         const int remb = L & 3;
-        if (remb && nwf - w0 >= 0 && nwf - w0 < nw) {
-            const uint32_t m = head_mask(remb);
-            const uint32_t sw = *reinterpret_cast<const uint32_t *>(srow + 4 * nwf);
-            const uint32_t qw = *reinterpret_cast<const uint32_t *>(qrow + 4 * nwf);
-            const uint32_t sel = base_selector(sw);
-            const uint32_t wbad_s = (sw ^ __byte_perm(VLUT_LO, VLUT_HI, sel)) & m;
-            const uint32_t nuc4 = __byte_perm(NLUT_LO, NLUT_HI, sel);
-            const uint32_t wbad_q = qual_bad_bits(qw, qw | HI, qk) & HI & m;
-            bads |= wbad_s;
-            badq |= wbad_q;
-            if ((wbad_s | wbad_q) == 0) {
-                const uint32_t qp4 = qw - qk.lo4;
-                for (int k = 0; k < remb; k++) {
-                    const int nuc = (nuc4 >> (8 * k)) & 0xFF, qp = (qp4 >> (8 * k)) & 0xFF;
-                    if (nuc < 4 && qp < ST_QWIN)
-                        atomicAdd(reinterpret_cast<uint32_t *>(hs + (size_t)(nwf - w0) * ST_WBLK + k * ST_KBLK + nuc * 256 + qp * 4), 1u);
-                    else
-                        hist_global_add(P.hist, P.max_cycles, 4 * nwf + k, nuc, qp, 1ull);
-                }
-            }
-        } else if (remb && !(nwf - w0 >= 0 && nwf - w0 < nw)) {
-            // not this pass's cycles, but still validate the bytes once (pass 0 owns validation of the tail)
+        if (remb && (nwf & (G - 1)) == j) {
+            const uint32_t tsw = *reinterpret_cast<const uint32_t *>(srow + 4 * nwf);
+            const uint32_t tqw = *reinterpret_cast<const uint32_t *>(qrow + 4 * nwf);
+            stats_word<true>(P, qk, tsw, tqw, nwf, remb, hs_addr, bads, badq);
         }
-        if ((bads | badq) != 0 || lenbad) {
-            if (active) atomicMin(&P.counters[CNT_FIRST_BAD], (unsigned long long)(P.index_base + g));
-        }
+        if (((bads | badq) != 0 || lenbad) && active)
+            atomicMin(&P.counters[CNT_FIRST_BAD], (unsigned long long)(P.index_base + g));
 
         __syncwarp();
         if (lane == 0) {
@@ -155,11 +161,11 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_stats(const __grid_constant__
 
     // flush the CTA's shared histogram into the global u64 table
     __syncthreads();
-    const int bins = nw * 4 * 4 * ST_QWIN;
-    for (int i = tid; i < bins; i += ST_THREADS) {
+    const int bins = P.nw * 4 * 4 * ST_QWIN;
+    for (int i = tid; i < bins; i += NTHREADS) {
         const int qp = i & (ST_QWIN - 1), nuc = (i >> 6) & 3, k = (i >> 8) & 3, rel = i >> 10;
         const uint32_t v = *reinterpret_cast<const uint32_t *>(hs + (size_t)rel * ST_WBLK + k * ST_KBLK + nuc * 256 + qp * 4);
-        if (v) hist_global_add(P.hist, P.max_cycles, 4 * (w0 + rel) + k, nuc, qp, (unsigned long long)v);
+        if (v) hist_global_add(P.hist, P.max_cycles, 4 * (P.w0 + rel) + k, nuc, qp, (unsigned long long)v);
     }
 }
 
@@ -203,9 +209,12 @@ __global__ void __launch_bounds__(256) k_stats_simple(const StatsParams P)
     }
 }
 
-cudaError_t launch_stats(const StatsParams &p, int grid, uint32_t smem_bytes, cudaStream_t st)
+cudaError_t launch_stats(const StatsParams &p, int g, int grid, uint32_t smem_bytes, cudaStream_t st)
 {
-    k_stats<0><<<grid, ST_THREADS, smem_bytes, st>>>(p);
+    if (g == 1) k_stats<1><<<grid, ST_WARPS * 32, smem_bytes, st>>>(p);
+    else if (g == 2) k_stats<2><<<grid, ST_WARPS * 64, smem_bytes, st>>>(p);
+    else if (g == 4) k_stats<4><<<grid, ST_WARPS * 128, smem_bytes, st>>>(p);
+    else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
 
@@ -221,7 +230,10 @@ cudaError_t launch_stats_simple(const StatsParams &p, int sm_count, cudaStream_t
 
 cudaError_t stats_set_smem_attrs()
 {
-    return cudaFuncSetAttribute(k_stats<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(k_stats<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_stats<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_stats<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+    return e;
 }
 
 }  // namespace fxg

@@ -378,12 +378,38 @@ static int st_args(int oi, int optc, char *oa)
 
 /* Everything the tool prints is derived from one (cycle, nucleotide) histogram h[q+15]
  * (fastx_quality_stats.c:218-247 get_nth_value, :276-417 printers). */
-typedef struct { int count, min, max; long long sum; const uint64_t *h; int fasta; } nucstat;
+typedef struct { int count, min, max; long long sum; const uint64_t *h; int fasta; int cycle, nuc; } nucstat;
+
+/* FASTA input has no quality bins, so the reference's get_nth_value() walks past the end of its
+ * bases_values_count[] into the fields of the following table entries (min, max, count, padding, sum, bins ...).
+ * The result is garbage but deterministic; to stay byte-identical we replay the walk over the same memory
+ * image: struct nucleotide_data = { int min, max, count; (pad) ; unsigned long long sum; int bins[108]; } = 114
+ * ints, 6 per cycle (fastx_quality_stats.c:115-133).  fa_counts[cycle*6+nuc] are the only non-constant fields. */
+static const int *fa_counts = NULL;
+static int fa_cycles = 0;
+static int fa_int(long long idx)
+{
+    const long long e = idx / 114, f = idx % 114;
+    if (f == 0) return 100;                       /* min  */
+    if (f == 1) return -100;                      /* max  */
+    if (f == 2) return (e / 6 < fa_cycles) ? fa_counts[e] : 0;   /* count */
+    return 0;                                     /* padding, sum (never updated for FASTA), bins */
+}
 
 static int st_nth(const nucstat *s, int n)
 {
     if (n == 0) return s->min;
-    if (s->fasta) return 93;     /* no quality bins: the reference's walk stops on the next table's `min` sentinel */
+    if (s->fasta) {
+        const long long base = ((long long)s->cycle * 6 + s->nuc) * 114 + 6;
+        long long pos = 0;
+        while (n > 0) {
+            if (fa_int(base + pos) > n) break;
+            n -= fa_int(base + pos);
+            pos++;
+            while (fa_int(base + pos) == 0) pos++;
+        }
+        return (int)(pos - 15);
+    }
     int pos = 0;
     while (n > 0) {
         if ((long long)s->h[pos] > n) break;
@@ -394,9 +420,9 @@ static int st_nth(const nucstat *s, int n)
     return pos - 15;
 }
 
-static void st_fill(nucstat *s, const uint64_t *h, int fasta)
+static void st_fill(nucstat *s, const uint64_t *h, int fasta, int cycle, int nuc)
 {
-    s->h = h; s->fasta = fasta; s->count = 0; s->min = 100; s->max = -100; s->sum = 0;
+    s->h = h; s->fasta = fasta; s->count = 0; s->min = 100; s->max = -100; s->sum = 0; s->cycle = cycle; s->nuc = nuc;
     for (int b = 0; b < FXG_QBINS; b++) {
         if (!h[b]) continue;
         s->count += (int)h[b];
@@ -457,6 +483,17 @@ static int main_stats(int argc, char **argv)
     uint64_t all[FXG_QBINS];
     nucstat s[6];
     int max_count = 0;
+    if (!fastq) {   /* table of counts for the FASTA walk emulation */
+        int *fc = (int *)calloc((size_t)(maxlen + 1) * 6, sizeof(int));
+        if (!fc) err(1, "out of memory");
+        for (int c = 0; c < maxlen; c++)
+            for (int nuc = 0; nuc < 5; nuc++) {
+                const int v = (int)hist[(size_t)c * cyc_words + (size_t)nuc * FXG_QBINS + 15];
+                fc[c * 6 + 1 + nuc] = v;
+                fc[c * 6] += v;
+            }
+        fa_counts = fc; fa_cycles = maxlen;
+    }
     if (st_new_format) {
         fprintf(out, "cycle\tmax_count");
         for (int nuc = 0; nuc < 6; nuc++) for (int k = 0; k < 11; k++) fprintf(out, "\t%s_%s", names[nuc], cols[k]);
@@ -467,8 +504,8 @@ static int main_stats(int argc, char **argv)
     for (int c = 0; c < maxlen; c++) {
         const uint64_t *hc = hist + (size_t)c * cyc_words;
         for (int q = 0; q < FXG_QBINS; q++) all[q] = hc[q] + hc[FXG_QBINS + q] + hc[2 * FXG_QBINS + q] + hc[3 * FXG_QBINS + q] + hc[4 * FXG_QBINS + q];
-        st_fill(&s[0], all, !fastq);
-        for (int nuc = 0; nuc < 5; nuc++) st_fill(&s[1 + nuc], hc + (size_t)nuc * FXG_QBINS, !fastq);
+        st_fill(&s[0], all, !fastq, c, 0);
+        for (int nuc = 0; nuc < 5; nuc++) st_fill(&s[1 + nuc], hc + (size_t)nuc * FXG_QBINS, !fastq, c, 1 + nuc);
         if (s[0].count == 0) break;
         if (c == 0) max_count = s[0].count;
         if (st_new_format) {

@@ -39,7 +39,7 @@ def timeit(fn, reps=5):
     return e0.elapsed_time(e1) / reps
 
 
-configs = sys.argv[1:] or ["-1,0,0,0", "0,0,0,0", "1,1,1,4", "1,1,1,5", "1,1,2,2"]
+configs = sys.argv[1:] or ["-1,0,0,0"]
 for cfg in configs:
     os.environ["FXG_TUNE"] = cfg
     try:
@@ -55,7 +55,7 @@ for cfg in configs:
         print("FXG_TUNE=%s failed: %s" % (cfg, e), flush=True)
 os.environ.pop("FXG_TUNE", None)
 oseq, oqual = torch.empty_like(dseq), torch.empty_like(dqual)
-for cfg in ["0,0,0,0", "-1,0,0,0", "1,2,0,4", "1,2,0,5", "1,1,0,0", "1,4,0,5", "1,4,0,8"]:
+for cfg in ["0,0,0,0", "-1,0,0,0", "1,2,0,6"]:
     os.environ["FXG_TUNE"] = cfg
     try:
         ms = timeit(lambda: ctx.revcomp_dev(b, 33, oseq, oqual))
@@ -70,7 +70,7 @@ os.environ.pop("FXG_TUNE", None)
 hist = torch.zeros((L, 5, 109), dtype=torch.int64, device="cuda")
 ns = min(n, 20_000_000)
 bs = ctx.batch(dseq, dqual, ns, S, L)
-for cfg in ["1,0,1,0", "1,0,2,0", "0,0,0,0"]:
+for cfg in ["1,1,1,0", "1,2,1,0", "1,4,1,0", "1,2,2,0", "0,0,0,0"]:
     os.environ["FXG_TUNE"] = cfg
     ms = timeit(lambda: ctx.stats_accum_dev(bs, 33, hist, L), reps=3)
     print("FXG_TUNE=%-10s stats %.3f ms %7.1f GB/s (%.2f Gr/s, %.1f Gsamples/s)" % (cfg, ms, ns * 2 * L / ms / 1e6, ns / ms / 1e6, ns * L / ms / 1e6), flush=True)
@@ -79,10 +79,11 @@ nc = min(n, 4_000_000)
 aseq = torch.empty((nc, S), dtype=torch.uint8, device="cuda"); aqual = torch.empty((nc, S), dtype=torch.uint8, device="cuda")
 ctx.synth_dev(aseq, aqual, nc, L, S, 20260927, 2, 33)
 olen = torch.empty(nc, dtype=torch.int32, device="cuda")
-for ad in [b"AGATCGGAAGAGC", b"AGATCGGAAGAGCACACGTCTGAACTCC"]:
+for ad, payload in [(b"AGATCGGAAGAGC", "0"), (b"AGATCGGAAGAGC", "1"), (b"AGATCGGAAGAGCACACGTCTGAACTCC", "0"), (b"AGATCGGAAGAGCACACGTCTGAACTCC", "1")]:
+    os.environ["FXG_CLIP_PAYLOAD"] = payload
     o = F.ClipOpts(adapter=ad, min_length=20, keep_delta=0, discard_non_clipped=0, discard_clipped=0, discard_unknown=1, min_adapter_len=0)
     bc = ctx.batch(aseq, aqual, nc, S, L)
     ms = timeit(lambda: ctx.clip_dev(bc, None, 33, o, olen), reps=3)
-    print("clip H=%d: %.3f ms %.1f Mreads/s %.1f Gcells/s" % (len(ad), ms, nc / ms / 1e3, nc * L * len(ad) / ms / 1e6), flush=True)
+    print("clip H=%d %s: %.3f ms %.1f Mreads/s %.1f Gcells/s" % (len(ad), "forward-payload" if payload == "1" else "origin-bits+backtrace", ms, nc / ms / 1e3, nc * L * len(ad) / ms / 1e6), flush=True)
 rep = ctx.sync()
 print("first_bad", rep.first_bad_read, "clip kept", rep.n_out)
