@@ -468,7 +468,7 @@ static int stats_enqueue(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint64_
     int t_ring, t_g, t_stages, t_ctas;
     env_tune(&t_ring, &t_g, &t_stages, &t_ctas);
     const int stages = (t_stages > 0 && t_stages <= 2) ? t_stages : 1;
-    const int g = (t_g == 1 || t_g == 2 || t_g == 4) ? t_g : 2;     // lanes per read; 6*g warps per CTA
+    const int g = (t_g == 1 || t_g == 2 || t_g == 4) ? t_g : 4;     // lanes per read; 6*g warps per CTA (measured: g=4 best)
     const int warps = ST_WARPS * g;
     long rfit = ((long)MAX_DYN_SMEM - (long)hist_al) / warps / stages / (2L * b->stride);
     if (rfit > 32 / g) rfit = 32 / g;

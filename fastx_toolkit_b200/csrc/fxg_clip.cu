@@ -182,6 +182,9 @@ __global__ void __launch_bounds__(128) k_clip(const __grid_constant__ ClipParams
 // because a cell costs three fp32 adds, two compares and their selects, nothing else.
 // Used when the matrix width fits MAXW columns and the adapter fits one word per column.
 // ------------------------------------------------------------------------------------------------
+// HMAX is the adapter length rounded up to a multiple of 4; ALL HMAX rows are evaluated (rows >= H depend on
+// rows < H but never feed back, and are excluded from the arg-max), so the unrolled column has no early exits
+// and no predicated state merging.
 template <int HMAX, typename WordT, bool FIRST>
 __device__ __forceinline__ WordT clip_column_bits(const ClipParams &P, int H, int x, uint32_t qc, float (&ps)[HMAX],
                                                   float &best, int &bx, int &by)
@@ -192,7 +195,6 @@ __device__ __forceinline__ WordT clip_column_bits(const ClipParams &P, int H, in
     float diag_s = 0.0f;    // score (x-1, y-1)
 #pragma unroll
     for (int y = 0; y < HMAX; y++) {
-        if (y >= H) break;
         const uint32_t tc = P.adapter[y];
         const bool tn = tc == (uint32_t)'N';
         const float ms = (qn && tn) ? 0.0f : ((qn || tn) ? 0.1f : ((qc == tc) ? 1.0f : -1.0f));
@@ -208,7 +210,8 @@ __device__ __forceinline__ WordT clip_column_bits(const ClipParams &P, int H, in
         word |= o << (2 * y);
         ps[y] = sc;
         up_s = sc;
-        if (sc > best) { best = sc; bx = x; by = y; }
+        const bool live = (y < HMAX - 3) || (y < H);   // only the last 3 rows can lie beyond the adapter
+        if (live && sc > best) { best = sc; bx = x; by = y; }
     }
     return word;
 }
@@ -308,11 +311,23 @@ cudaError_t launch_clip(const ClipParams &p, int sm_count, int max_width, cudaSt
     if (blocks > cap) blocks = cap;
     const unsigned b = (unsigned)blocks;
     const char *force = getenv("FXG_CLIP_PAYLOAD");   // experimentation: force the forward-payload kernels
-    if (!(force && force[0] == '1')) {
-        if (p.alen <= 16 && max_width <= 256) { k_clip_bits<16, 256, uint32_t><<<b, 128, 0, st>>>(p); return cudaGetLastError(); }
-        if (p.alen <= 16 && max_width <= 1024) { k_clip_bits<16, 1024, uint32_t><<<b, 128, 0, st>>>(p); return cudaGetLastError(); }
-        if (p.alen <= 32 && max_width <= 256) { k_clip_bits<32, 256, unsigned long long><<<b, 128, 0, st>>>(p); return cudaGetLastError(); }
-        if (p.alen <= 32 && max_width <= 1024) { k_clip_bits<32, 1024, unsigned long long><<<b, 128, 0, st>>>(p); return cudaGetLastError(); }
+    if (!(force && force[0] == '1') && p.alen <= 32 && max_width <= 1024) {
+        const int hb = (p.alen + 3) / 4;      // adapter length bucket (multiple of 4 rows)
+#define FXG_CLIPB(HM, WT)                                                                          \
+        if (max_width <= 256) k_clip_bits<HM, 256, WT><<<b, 128, 0, st>>>(p);                      \
+        else k_clip_bits<HM, 1024, WT><<<b, 128, 0, st>>>(p);                                      \
+        return cudaGetLastError();
+        switch (hb) {
+        case 1: { FXG_CLIPB(4, uint32_t) }
+        case 2: { FXG_CLIPB(8, uint32_t) }
+        case 3: { FXG_CLIPB(12, uint32_t) }
+        case 4: { FXG_CLIPB(16, uint32_t) }
+        case 5: { FXG_CLIPB(20, unsigned long long) }
+        case 6: { FXG_CLIPB(24, unsigned long long) }
+        case 7: { FXG_CLIPB(28, unsigned long long) }
+        default: { FXG_CLIPB(32, unsigned long long) }
+        }
+#undef FXG_CLIPB
     }
     if (p.alen <= 16) k_clip<16><<<b, 128, 0, st>>>(p);
     else if (p.alen <= 32) k_clip<32><<<b, 128, 0, st>>>(p);

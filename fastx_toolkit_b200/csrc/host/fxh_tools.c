@@ -383,24 +383,24 @@ typedef struct { int count, min, max; long long sum; const uint64_t *h; int fast
 /* FASTA input has no quality bins, so the reference's get_nth_value() walks past the end of its
  * bases_values_count[] into the fields of the following table entries (min, max, count, padding, sum, bins ...).
  * The result is garbage but deterministic; to stay byte-identical we replay the walk over the same memory
- * image: struct nucleotide_data = { int min, max, count; (pad) ; unsigned long long sum; int bins[108]; } = 114
- * ints, 6 per cycle (fastx_quality_stats.c:115-133).  fa_counts[cycle*6+nuc] are the only non-constant fields. */
+ * image: struct nucleotide_data = { int min, max, count; unsigned long long sum; int bins[108]; } laid out under the
+ * `#pragma pack(1)` that fastx.h:60 leaves active = 113 ints (no padding), 6 per cycle (fastx_quality_stats.c:115-133).  fa_counts[cycle*6+nuc] are the only non-constant fields. */
 static const int *fa_counts = NULL;
 static int fa_cycles = 0;
 static int fa_int(long long idx)
 {
-    const long long e = idx / 114, f = idx % 114;
+    const long long e = idx / 113, f = idx % 113;
     if (f == 0) return 100;                       /* min  */
     if (f == 1) return -100;                      /* max  */
     if (f == 2) return (e / 6 < fa_cycles) ? fa_counts[e] : 0;   /* count */
-    return 0;                                     /* padding, sum (never updated for FASTA), bins */
+    return 0;                                     /* sum (never updated for FASTA), bins */
 }
 
 static int st_nth(const nucstat *s, int n)
 {
     if (n == 0) return s->min;
     if (s->fasta) {
-        const long long base = ((long long)s->cycle * 6 + s->nuc) * 114 + 6;
+        const long long base = ((long long)s->cycle * 6 + s->nuc) * 113 + 5;
         long long pos = 0;
         while (n > 0) {
             if (fa_int(base + pos) > n) break;
