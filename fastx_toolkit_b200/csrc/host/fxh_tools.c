@@ -401,12 +401,15 @@ static int st_nth(const nucstat *s, int n)
     if (n == 0) return s->min;
     if (s->fasta) {
         const long long base = ((long long)s->cycle * 6 + s->nuc) * 113 + 5;
+        /* Beyond the cycles that hold data every entry is {100,-100,0,...}: the reference keeps walking (its
+         * result then depends on whatever follows its static table); we stop at the end of the data. */
+        const long long end = (long long)fa_cycles * 6 * 113;
         long long pos = 0;
-        while (n > 0) {
+        while (n > 0 && base + pos < end) {
             if (fa_int(base + pos) > n) break;
             n -= fa_int(base + pos);
             pos++;
-            while (fa_int(base + pos) == 0) pos++;
+            while (base + pos < end && fa_int(base + pos) == 0) pos++;
         }
         return (int)(pos - 15);
     }

