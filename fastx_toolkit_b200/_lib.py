@@ -28,6 +28,12 @@ class ClipOpts(C.Structure):
                 ("min_adapter_len", C.c_int32)]
 
 
+class TextReport(C.Structure):
+    """struct fxg_text_report"""
+    _fields_ = [("n_records", C.c_int64), ("n_out_records", C.c_int64), ("consumed_bytes", C.c_int64), ("out_bytes", C.c_int64),
+                ("max_len", C.c_int32), ("anomaly", C.c_int32), ("anomaly_record", C.c_int64)]
+
+
 class Report(C.Structure):
     """struct fxg_report"""
     _fields_ = [("n_in", C.c_int64), ("n_out", C.c_int64), ("first_bad_read", C.c_int64), ("aux", C.c_int64 * 6)]
@@ -82,6 +88,11 @@ def lib():
         "fxg_clip_dev": (i32, [vp, BP, vp, i32, C.POINTER(ClipOpts), vp, vp, vp, i64]),
         "fxg_clip_host": (i32, [vp, BP, vp, i32, C.POINTER(ClipOpts), vp, vp, RP]),
         "fxg_hash_dev": (i32, [vp, BP, vp]),
+        "fxg_text_new": (i32, [vp, i32, sz, C.POINTER(vp)]),
+        "fxg_text_free": (None, [vp]),
+        "fxg_text_run_host": (i32, [vp, i32, vp, sz, i32, i32, i32, vp, C.POINTER(TextReport)]),
+        "fxg_text_error": (C.c_char_p, [vp]),
+        "fxg_text_launches": (i64, [vp]),
         "fxg_collapse_new": (i32, [i32, i64, C.c_int32, C.POINTER(vp)]),
         "fxg_collapse_free": (None, [vp]),
         "fxg_collapse_add": (i32, [vp, BP, vp, vp, i64]),
@@ -145,6 +156,36 @@ class Collapser:
     def close(self):
         if getattr(self, "h", None):
             self.L.fxg_collapse_free(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+class TextPipe:
+    """fxg_text: FASTQ text -> (K-LINES, K-RECS, K-PACK, op, K-EMIT) -> FASTQ text."""
+
+    def __init__(self, ctx, max_chunk_bytes):
+        self.L, self.cap = lib(), max_chunk_bytes
+        h = C.c_void_p()
+        rc = self.L.fxg_text_new(ctx.h, ctx.device, max_chunk_bytes, C.byref(h))
+        if rc != FXG_OK:
+            raise FxgError(rc, "fxg_text_new: " + self.L.fxg_strerror(rc).decode())
+        self.h = h
+
+    def run(self, op, text, q_offset, a0, a1):
+        """text: bytes / numpy uint8 array.  Returns (output bytes, TextReport)."""
+        import numpy as np
+        src = np.frombuffer(text, np.uint8) if isinstance(text, (bytes, bytearray)) else text
+        out = np.empty(self.cap + self.cap // 4 + 64, np.uint8)
+        rep = TextReport()
+        rc = self.L.fxg_text_run_host(self.h, op, src.ctypes.data, src.size, q_offset, a0, a1, out.ctypes.data, C.byref(rep))
+        if rc != FXG_OK:
+            raise FxgError(rc, self.L.fxg_text_error(self.h).decode())
+        return out[: rep.out_bytes].tobytes(), rep
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.fxg_text_free(self.h)
             self.h = None
 
     __del__ = close

@@ -543,6 +543,17 @@ extern "C" int fxg_clip_dev(fxg_ctx *ctx, const fxg_batch *b, const int32_t *wid
     return clip_enqueue(ctx, b, width, q_offset, o, out_len, out_class, out_cut, index_base, ctx->stream);
 }
 
+// internal hooks for fxg_text.cu (not part of the public header): run K-TRIM / K-FILTER on a caller-chosen stream
+extern "C" int fxg_internal_scan_on_stream(fxg_ctx *ctx, int mode, const fxg_batch *b, int q_offset, int thr_q, int min_len,
+                                           int min_percent, void *out, void *stream)
+{
+    int rc = check_batch(ctx, b, false, true, q_offset);
+    if (rc) return rc;
+    CK(ctx, cudaSetDevice(ctx->device));
+    return scan_enqueue(ctx, mode == 0 ? MODE_TRIM : MODE_FILTER, b, q_offset, thr_q, min_len, min_percent, out, 0, (cudaStream_t)stream);
+}
+extern "C" void *fxg_internal_counters(fxg_ctx *ctx) { return ctx ? (void *)ctx->d_counters : NULL; }
+
 // ---- K-HASH (std::hash<std::string> of every read; collapser routing key) ----------------------------------
 extern "C" int fxg_hash_dev(fxg_ctx *ctx, const fxg_batch *b, uint64_t *hash_dev)
 {

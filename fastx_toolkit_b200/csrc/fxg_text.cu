@@ -1,0 +1,391 @@
+// fxg_text.cu — the steps on either side of the per-read loop, moved to the GPU so the host does no per-byte work
+// (SURVEY.md §8f-1): raw FASTQ text in, FASTQ text out.
+//
+//   K-LINES  newline index of a text chunk                              (reader: fgets/chomp, fastx.c:324-378)
+//   K-RECS   4 lines -> record table + structural checks               (fastx.c:331-347,361-362,382-390)
+//   K-PACK   sequence / quality lines -> the SoA slabs the op kernels use
+//   <op>     K-TRIM / K-FILTER (fused validation) on the slabs — the kernels of fxg_kernels.cu, unchanged
+//   K-EMIT   surviving records -> output text "@name\nSEQ[:len]\n+name2\nQUAL[:len]\n"   (fastx.c:440-473)
+//
+// Anything the fast path does not handle bit-exactly by construction — a structural problem, a numeric or
+// mismatched quality line, an illegal base/quality, an over-long line — is reported as an *anomaly* with the index
+// of the first affected record; nothing is emitted for that chunk and the host re-reads it with the (slower)
+// host parser, which reproduces the reference's output prefix and error message exactly.
+// Scans are CUB (library primitive); everything else is hand-written.
+#include <cub/cub.cuh>
+#include <stdio.h>
+#include <string.h>
+
+#include "fxg.h"
+#include "fxg_kernels.cuh"
+
+namespace fxg {
+
+// ---- K-LINES ---------------------------------------------------------------------------------------------
+// each thread owns 64 bytes: count newlines, then (after a scan) write their positions
+__global__ void __launch_bounds__(256) k_nl_count(const uint8_t *text, uint64_t bytes, uint32_t *cnt, uint64_t nthreads_total)
+{
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nthreads_total; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t b0 = t * 64;
+        uint32_t c = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint64_t off = b0 + 16 * k;
+            if (off + 16 <= bytes) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(text + off));
+                const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t x = w[i] ^ 0x0A0A0A0Au;                         // zero byte <=> '\n'
+                    const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
+                    c += __popc(z);
+                }
+            } else {
+                for (uint64_t p = off; p < bytes && p < off + 16; p++) c += (text[p] == '\n');
+            }
+        }
+        cnt[t] = c;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_nl_scatter(const uint8_t *text, uint64_t bytes, const uint32_t *scan, uint32_t *line_end,
+                                                    uint64_t nthreads_total)
+{
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nthreads_total; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t b0 = t * 64;
+        uint32_t o = scan[t];
+        const uint64_t e = (b0 + 64 < bytes) ? b0 + 64 : bytes;
+        for (uint64_t p = b0; p < e; p += 4) {
+            if (p + 4 <= e) {
+                const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(text + p));
+                const uint32_t x = w ^ 0x0A0A0A0Au;
+                uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);   // bit7 of each '\n' byte
+                while (z) {
+                    const int b = (__ffs(z) - 1) >> 3;
+                    line_end[o++] = (uint32_t)(p + b);
+                    z &= z - 1;
+                }
+            } else {
+                for (uint64_t q = p; q < e; q++) if (text[q] == '\n') line_end[o++] = (uint32_t)q;
+            }
+        }
+    }
+}
+
+// ---- K-RECS ------------------------------------------------------------------------------------------------
+struct RecTable {
+    uint32_t *start;     // [n_rec*4] start offset of each line
+    uint32_t *llen;      // [n_rec*4] length of each line (CR removed)
+};
+
+enum { AN_NONE = 0, AN_PREFIX = 1, AN_EMPTY_SEQ = 2, AN_QUAL_LEN = 3, AN_LONG_LINE = 4, AN_BAD_RECORD = 5, AN_LINE_COUNT = 6 };
+
+__global__ void __launch_bounds__(256) k_recs(const uint8_t *text, const uint32_t *line_end, uint32_t n_rec, RecTable rt,
+                                              int32_t *seq_len, unsigned long long *anomaly /* [0]=min record, */, int *max_len)
+{
+    int local_max = 0;
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += gridDim.x * blockDim.x) {
+        uint32_t st[4], ln[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t li = 4 * r + k;
+            const uint32_t s = li == 0 ? 0u : line_end[li - 1] + 1u;
+            uint32_t e = line_end[li];
+            uint32_t l = e - s;
+            if (l > 0 && text[e - 1] == '\r') l--;            // chomp(): CRLF
+            st[k] = s; ln[k] = l;
+            rt.start[li] = s; rt.llen[li] = l;
+        }
+        int an = AN_NONE;
+        if (ln[0] == 0 || text[st[0]] != '@') an = AN_PREFIX;
+        else if (ln[1] == 0) an = AN_EMPTY_SEQ;
+        else if (ln[3] != ln[1]) an = AN_QUAL_LEN;               // numeric quality (or a broken record): host path
+        else if (ln[0] >= 24998u || ln[1] >= 24998u || ln[2] >= 24998u) an = AN_LONG_LINE;
+        if (an != AN_NONE) atomicMin(anomaly, ((unsigned long long)r << 8) | (unsigned long long)an);
+        seq_len[r] = (int32_t)ln[1];
+        if ((int)ln[1] > local_max && an == AN_NONE) local_max = (int)ln[1];
+    }
+    local_max = __reduce_max_sync(0xffffffffu, local_max);
+    if ((threadIdx.x & 31) == 0 && local_max > 0) atomicMax(max_len, local_max);
+}
+
+// ---- K-PACK: one thread per 16-byte destination chunk (both rows) ---------------------------------------------
+__device__ __forceinline__ uint4 load_unaligned16(const uint8_t *text, uint64_t src, int nbytes /* 1..16 valid */)
+{
+    // src is arbitrary: read the aligned words covering it and funnel-shift them into place
+    const uint64_t a = src & ~3ull;
+    const int sh = (int)(src & 3ull) * 8;
+    const uint32_t *p = reinterpret_cast<const uint32_t *>(text + a);
+    const int nwords = (nbytes + (int)(src & 3ull) + 3) >> 2;       // words touched (<= 5)
+    uint32_t w[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) w[i] = (i < nwords) ? __ldg(p + i) : 0u;
+    uint4 o;
+    o.x = __funnelshift_r(w[0], w[1], sh);
+    o.y = __funnelshift_r(w[1], w[2], sh);
+    o.z = __funnelshift_r(w[2], w[3], sh);
+    o.w = __funnelshift_r(w[3], w[4], sh);
+    return o;
+}
+
+__global__ void __launch_bounds__(256) k_pack(const uint8_t *text, RecTable rt, uint32_t n_rec, int stride, uint8_t *seq, uint8_t *qual)
+{
+    const int chunks = stride >> 4;
+    const uint64_t total = (uint64_t)n_rec * chunks;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t r = (uint32_t)(t / chunks);
+        const int c = (int)(t - (uint64_t)r * chunks);
+        const int L = (int)rt.llen[4 * r + 1];
+        const int nb = L - 16 * c;
+        uint4 s = make_uint4(0, 0, 0, 0), q = make_uint4(0, 0, 0, 0);
+        if (nb > 0) {
+            const int n = nb < 16 ? nb : 16;
+            s = load_unaligned16(text, (uint64_t)rt.start[4 * r + 1] + 16u * c, n);
+            q = load_unaligned16(text, (uint64_t)rt.start[4 * r + 3] + 16u * c, n);
+        }
+        const size_t off = (size_t)r * stride + (size_t)c * 16;
+        *reinterpret_cast<uint4 *>(seq + off) = s;
+        *reinterpret_cast<uint4 *>(qual + off) = q;
+    }
+}
+
+// ---- K-EMIT ----------------------------------------------------------------------------------------------------
+// out_len[r] < 0: record dropped.  keep_flags != NULL (filter): record kept iff flag, emitted at full length.
+__global__ void __launch_bounds__(256) k_emit_sizes(RecTable rt, uint32_t n_rec, const int32_t *out_len, const uint8_t *keep_flags,
+                                                    uint64_t *sizes)
+{
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += gridDim.x * blockDim.x) {
+        int ol = keep_flags ? (keep_flags[r] ? (int)rt.llen[4 * r + 1] : -1) : out_len[r];
+        sizes[r] = ol < 0 ? 0ull : (uint64_t)rt.llen[4 * r] + 1ull + (uint64_t)ol + 1ull + (uint64_t)(rt.llen[4 * r + 2] ? rt.llen[4 * r + 2] : 1u) + 1ull + (uint64_t)ol + 1ull;
+    }
+}
+
+__device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, int n, int lane)
+{
+    for (int i = lane; i < n; i += 32) dst[i] = src[i];
+}
+
+// one warp per record
+__global__ void __launch_bounds__(256) k_emit(const uint8_t *text, RecTable rt, uint32_t n_rec, const int32_t *out_len,
+                                              const uint8_t *keep_flags, const uint64_t *offs, uint8_t *out)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = warp; r < n_rec; r += nwarps) {
+        const int ol = keep_flags ? (keep_flags[r] ? (int)rt.llen[4 * r + 1] : -1) : out_len[r];
+        if (ol < 0) continue;
+        uint8_t *o = out + offs[r];
+        const int l0 = (int)rt.llen[4 * r], l2 = (int)rt.llen[4 * r + 2];
+        warp_copy(o, text + rt.start[4 * r], l0, lane);                 // "@name"
+        if (lane == 0) o[l0] = '\n';
+        o += l0 + 1;
+        warp_copy(o, text + rt.start[4 * r + 1], ol, lane);             // SEQ[:len]
+        if (lane == 0) o[ol] = '\n';
+        o += ol + 1;
+        if (l2 > 0) {                                                   // "+name2": first byte is always written as '+'
+            warp_copy(o, text + rt.start[4 * r + 2], l2, lane);
+            if (lane == 0) { o[0] = '+'; o[l2] = '\n'; }
+            o += l2 + 1;
+        } else {
+            if (lane == 0) { o[0] = '+'; o[1] = '\n'; }
+            o += 2;
+        }
+        warp_copy(o, text + rt.start[4 * r + 3], ol, lane);             // QUAL[:len]
+        if (lane == 0) o[ol] = '\n';
+    }
+}
+
+__global__ void k_count_kept(const int32_t *out_len, const uint8_t *keep_flags, uint32_t n_rec, unsigned long long *kept)
+{
+    unsigned c = 0;
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += gridDim.x * blockDim.x)
+        c += keep_flags ? (keep_flags[r] ? 1u : 0u) : (out_len[r] >= 0 ? 1u : 0u);
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(kept, (unsigned long long)c);
+}
+
+}  // namespace fxg
+
+using namespace fxg;
+
+// provided by fxg_api.cu
+extern "C" int fxg_internal_scan_on_stream(fxg_ctx *ctx, int mode, const fxg_batch *b, int q_offset, int thr_q, int min_len,
+                                           int min_percent, void *out, void *stream);
+extern "C" void *fxg_internal_counters(fxg_ctx *ctx);
+
+struct fxg_text {
+    fxg_ctx *ctx;
+    int device;
+    cudaStream_t st;
+    size_t cap_bytes;              // text capacity
+    uint8_t *d_text, *d_out;
+    uint32_t *d_cnt, *d_scan;      // per-64-byte newline counts
+    uint32_t *d_line_end;  size_t cap_lines;
+    uint32_t *d_start, *d_llen;    // record table (4 per record)
+    int32_t *d_seq_len, *d_out_len; uint8_t *d_keep;
+    uint64_t *d_sizes, *d_offs;
+    size_t cap_recs;
+    uint8_t *d_seq, *d_qual;  size_t cap_slab;
+    void *d_tmp; size_t tmp_bytes;
+    unsigned long long *d_scalars; // [0] anomaly(min), [1] kept, [2] max_len (int), [3] spare
+    unsigned long long *h_scalars; // pinned mirror
+    int64_t launches;
+    char err[256];
+};
+
+#define CKT(t, call)                                                                               \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            snprintf((t)->err, sizeof((t)->err), "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return FXG_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+static unsigned tgrid(uint64_t n, unsigned per_block = 256) { uint64_t b = (n + per_block - 1) / per_block; if (b > 148ull * 32) b = 148ull * 32; if (b < 1) b = 1; return (unsigned)b; }
+
+extern "C" const char *fxg_text_error(const fxg_text *t) { return t ? t->err : "no text context"; }
+extern "C" int64_t fxg_text_launches(const fxg_text *t) { return t ? t->launches : 0; }
+
+extern "C" void fxg_text_free(fxg_text *t)
+{
+    if (!t) return;
+    cudaSetDevice(t->device);
+    cudaFree(t->d_text); cudaFree(t->d_out); cudaFree(t->d_cnt); cudaFree(t->d_scan); cudaFree(t->d_line_end);
+    cudaFree(t->d_start); cudaFree(t->d_llen); cudaFree(t->d_seq_len); cudaFree(t->d_out_len); cudaFree(t->d_keep);
+    cudaFree(t->d_sizes); cudaFree(t->d_offs); cudaFree(t->d_seq); cudaFree(t->d_qual); cudaFree(t->d_tmp);
+    cudaFree(t->d_scalars); cudaFreeHost(t->h_scalars);
+    if (t->st) cudaStreamDestroy(t->st);
+    free(t);
+}
+
+extern "C" int fxg_text_new(fxg_ctx *ctx, int device, size_t max_chunk_bytes, fxg_text **out)
+{
+    if (!ctx || !out || max_chunk_bytes < 1024 || max_chunk_bytes >= 0xFFFFFF00ull) return FXG_ERR_ARG;
+    *out = NULL;
+    if (cudaSetDevice(device) != cudaSuccess) return FXG_ERR_CUDA;
+    fxg_text *t = (fxg_text *)calloc(1, sizeof(fxg_text));
+    if (!t) return FXG_ERR_NOMEM;
+    t->ctx = ctx; t->device = device; t->cap_bytes = max_chunk_bytes;
+    const size_t nthr = (max_chunk_bytes + 63) / 64;
+    bool ok = cudaStreamCreateWithFlags(&t->st, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaMalloc(&t->d_text, max_chunk_bytes + 64) == cudaSuccess && cudaMalloc(&t->d_out, max_chunk_bytes + max_chunk_bytes / 4 + 64) == cudaSuccess &&
+              cudaMalloc(&t->d_cnt, (nthr + 1) * 4) == cudaSuccess && cudaMalloc(&t->d_scan, (nthr + 1) * 4) == cudaSuccess &&
+              cudaMalloc(&t->d_scalars, 64) == cudaSuccess && cudaMallocHost(&t->h_scalars, 64) == cudaSuccess;
+    if (ok) {
+        size_t need = 0, best = 0;
+        cub::DeviceScan::ExclusiveSum(NULL, need, t->d_cnt, t->d_scan, (int)nthr + 1, t->st); best = need;
+        cub::DeviceScan::ExclusiveSum(NULL, need, (uint64_t *)NULL, (uint64_t *)NULL, (int)(max_chunk_bytes / 8 + 1), t->st); if (need > best) best = need;
+        t->tmp_bytes = best + 256;
+        ok = cudaMalloc(&t->d_tmp, t->tmp_bytes) == cudaSuccess;
+    }
+    if (!ok) { cudaGetLastError(); fxg_text_free(t); return FXG_ERR_NOMEM; }
+    *out = t;
+    return FXG_OK;
+}
+
+static int ensure(fxg_text *t, void **p, size_t *cap, size_t need_elems, size_t elem)
+{
+    if (*cap >= need_elems) return FXG_OK;
+    if (*p) cudaFree(*p);
+    *p = NULL; *cap = 0;
+    const size_t n = need_elems + need_elems / 8 + 1024;
+    CKT(t, cudaMalloc(p, n * elem));
+    *cap = n;
+    return FXG_OK;
+}
+
+// op: 0 = trim (a0 = threshold, a1 = min_len), 1 = filter (a0 = min_quality, a1 = min_percent)
+extern "C" int fxg_text_run_host(fxg_text *t, int op, const char *text_host, size_t bytes, int q_offset, int a0, int a1,
+                                 char *out_host, fxg_text_report *rep)
+{
+    if (!t || !text_host || !out_host || !rep || bytes > t->cap_bytes || (op != 0 && op != 1)) return FXG_ERR_ARG;
+    memset(rep, 0, sizeof(*rep));
+    rep->anomaly_record = -1;
+    if (bytes == 0) return FXG_OK;
+    CKT(t, cudaSetDevice(t->device));
+    cudaStream_t st = t->st;
+    const uint64_t nthr = (bytes + 63) / 64;
+    CKT(t, cudaMemcpyAsync(t->d_text, text_host, bytes, cudaMemcpyHostToDevice, st));
+    k_nl_count<<<tgrid(nthr), 256, 0, st>>>(t->d_text, bytes, t->d_cnt, nthr);
+    size_t need = t->tmp_bytes;
+    CKT(t, cub::DeviceScan::ExclusiveSum(t->d_tmp, need, t->d_cnt, t->d_scan, (int)nthr + 1, st));
+    uint32_t n_lines = 0;
+    CKT(t, cudaMemcpyAsync(&n_lines, t->d_scan + nthr, 4, cudaMemcpyDeviceToHost, st));
+    CKT(t, cudaStreamSynchronize(st));
+    t->launches += 3;
+    const uint32_t n_rec = n_lines / 4;
+    rep->n_records = n_rec;
+    if (n_rec == 0) return FXG_OK;
+    int rc;
+    { size_t cl = t->cap_lines; rc = ensure(t, (void **)&t->d_line_end, &cl, (size_t)n_lines + 4, 4); t->cap_lines = cl; if (rc) return rc; }
+    if (t->cap_recs < n_rec) {
+        size_t c;
+        c = 0; if ((rc = ensure(t, (void **)&t->d_start, &c, (size_t)n_rec * 4, 4))) return rc;
+        c = 0; if ((rc = ensure(t, (void **)&t->d_llen, &c, (size_t)n_rec * 4, 4))) return rc;
+        c = 0; if ((rc = ensure(t, (void **)&t->d_seq_len, &c, n_rec, 4))) return rc;
+        c = 0; if ((rc = ensure(t, (void **)&t->d_out_len, &c, n_rec, 4))) return rc;
+        c = 0; if ((rc = ensure(t, (void **)&t->d_keep, &c, n_rec, 1))) return rc;
+        c = 0; if ((rc = ensure(t, (void **)&t->d_sizes, &c, (size_t)n_rec + 1, 8))) return rc;
+        c = 0; if ((rc = ensure(t, (void **)&t->d_offs, &c, (size_t)n_rec + 1, 8))) return rc;
+        t->cap_recs = n_rec;
+    }
+    k_nl_scatter<<<tgrid(nthr), 256, 0, st>>>(t->d_text, bytes, t->d_scan, t->d_line_end, nthr);
+    t->h_scalars[0] = ~0ull; t->h_scalars[1] = 0; t->h_scalars[2] = 0; t->h_scalars[3] = 0;
+    CKT(t, cudaMemcpyAsync(t->d_scalars, t->h_scalars, 32, cudaMemcpyHostToDevice, st));
+    RecTable rt = { t->d_start, t->d_llen };
+    k_recs<<<tgrid(n_rec), 256, 0, st>>>(t->d_text, t->d_line_end, n_rec, rt, t->d_seq_len, t->d_scalars, (int *)(t->d_scalars + 2));
+    CKT(t, cudaMemcpyAsync(t->h_scalars, t->d_scalars, 32, cudaMemcpyDeviceToHost, st));
+    // bytes consumed = end of the last complete record
+    uint32_t last_end = 0;
+    CKT(t, cudaMemcpyAsync(&last_end, t->d_line_end + (size_t)4 * n_rec - 1, 4, cudaMemcpyDeviceToHost, st));
+    CKT(t, cudaStreamSynchronize(st));
+    t->launches += 2;
+    rep->consumed_bytes = (int64_t)last_end + 1;
+    if (t->h_scalars[0] != ~0ull) {
+        rep->anomaly = (int32_t)(t->h_scalars[0] & 0xFF);
+        rep->anomaly_record = (int64_t)(t->h_scalars[0] >> 8);
+        return FXG_OK;
+    }
+    const int max_len = (int)*(int *)(t->h_scalars + 2);
+    rep->max_len = max_len;
+    const int stride = (max_len + 15) & ~15;
+    { size_t need_slab = (size_t)n_rec * stride; if (t->cap_slab < need_slab) {
+        size_t c = 0; if ((rc = ensure(t, (void **)&t->d_seq, &c, need_slab, 1))) return rc;
+        c = 0; if ((rc = ensure(t, (void **)&t->d_qual, &c, need_slab, 1))) return rc;
+        t->cap_slab = need_slab; } }
+    k_pack<<<tgrid((uint64_t)n_rec * (stride >> 4)), 256, 0, st>>>(t->d_text, rt, n_rec, stride, t->d_seq, t->d_qual);
+    t->launches++;
+    // the op kernel of fxg_kernels.cu on the packed slabs (validation fused; first bad record -> context counters)
+    fxg_batch b = { t->d_seq, t->d_qual, t->d_seq_len, 0, stride, (int64_t)n_rec };
+    if ((rc = fxg_report_reset(t->ctx))) { snprintf(t->err, sizeof(t->err), "%s", fxg_last_error(t->ctx)); return rc; }
+    rc = fxg_internal_scan_on_stream(t->ctx, op, &b, q_offset, a0, op == 0 ? a1 : 0, op == 1 ? a1 : 0,
+                                     op == 0 ? (void *)t->d_out_len : (void *)t->d_keep, (void *)st);
+    if (rc) { snprintf(t->err, sizeof(t->err), "%s", fxg_last_error(t->ctx)); return rc; }
+    const int32_t *ol = op == 0 ? t->d_out_len : NULL;
+    const uint8_t *kf = op == 1 ? t->d_keep : NULL;
+    k_emit_sizes<<<tgrid(n_rec), 256, 0, st>>>(rt, n_rec, ol, kf, t->d_sizes);
+    CKT(t, cudaMemsetAsync(t->d_sizes + n_rec, 0, 8, st));
+    need = t->tmp_bytes;
+    CKT(t, cub::DeviceScan::ExclusiveSum(t->d_tmp, need, t->d_sizes, t->d_offs, (int)n_rec + 1, st));
+    k_emit<<<tgrid((uint64_t)n_rec * 32), 256, 0, st>>>(t->d_text, rt, n_rec, ol, kf, t->d_offs, t->d_out);
+    k_count_kept<<<tgrid(n_rec), 256, 0, st>>>(ol, kf, n_rec, t->d_scalars + 1);
+    uint64_t out_bytes = 0;
+    CKT(t, cudaMemcpyAsync(&out_bytes, t->d_offs + n_rec, 8, cudaMemcpyDeviceToHost, st));
+    CKT(t, cudaMemcpyAsync(t->h_scalars, t->d_scalars, 32, cudaMemcpyDeviceToHost, st));
+    CKT(t, cudaMemcpyAsync(t->h_scalars + 4, (unsigned long long *)fxg_internal_counters(t->ctx), 16, cudaMemcpyDeviceToHost, st));
+    CKT(t, cudaStreamSynchronize(st));
+    t->launches += 5;
+    if (t->h_scalars[5] != ~0ull) {          // the op kernel found an illegal base / quality: host path decides
+        rep->anomaly = AN_BAD_RECORD;
+        rep->anomaly_record = (int64_t)t->h_scalars[5];
+        return FXG_OK;
+    }
+    rep->n_out_records = (int64_t)t->h_scalars[1];
+    rep->out_bytes = (int64_t)out_bytes;
+    if (out_bytes) {
+        CKT(t, cudaMemcpyAsync(out_host, t->d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+        CKT(t, cudaStreamSynchronize(st));
+    }
+    return FXG_OK;
+}

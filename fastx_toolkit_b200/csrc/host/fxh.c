@@ -394,6 +394,31 @@ fxh_batch *fxh_reader_next(fxh_reader *r, int64_t max_reads)
     return b;
 }
 
+size_t fxh_reader_raw(fxh_reader *r, char **p)
+{
+    if (!r->eof && (r->len - r->pos) < (r->cap >> 1)) refill(r, r->pos);
+    *p = r->buf + r->pos;
+    return r->len - r->pos;
+}
+
+void fxh_reader_consume(fxh_reader *r, size_t bytes, int64_t records)
+{
+    r->pos += bytes;
+    r->line_no += 4ull * (uint64_t)records;
+    r->n_seq += (size_t)records;
+    r->n_reads += (size_t)records;
+    r->next_index += records;
+}
+
+void fxh_reader_pin(fxh_reader *r) { (void)fxg_host_register(r->buf, r->cap + 1); }
+int fxh_reader_at_eof(const fxh_reader *r) { return r->eof; }
+
+int fxh_text_path_enabled(void)
+{
+    const char *e = getenv("FASTX_TEXT_PATH");
+    return !(e && e[0] == '0');
+}
+
 fxg_batch fxh_as_fxg_batch(const fxh_batch *b, int with_qual)
 {
     fxg_batch g;
@@ -526,6 +551,19 @@ void fxh_write_record(fxh_writer *w, const fxh_batch *b, int64_t i, const uint8_
     w->len = (size_t)(p - w->buf);
     w->n_seq++;
     w->n_reads += (size_t)b->weight[i];
+}
+
+void fxh_write_raw(fxh_writer *w, const char *text, size_t bytes, int64_t records)
+{
+    writer_flush(w);
+    size_t off = 0;
+    while (off < bytes) {
+        ssize_t k = write(w->fd, text + off, bytes - off);
+        if (k < 0) { if (errno == EINTR) continue; err(1, "writing nucleotides failed"); }
+        off += (size_t)k;
+    }
+    w->n_seq += (size_t)records;
+    w->n_reads += (size_t)records;
 }
 
 void fxh_writer_close(fxh_writer *w)

@@ -66,12 +66,20 @@ size_t      fxh_num_input_reads(const fxh_reader *r);
 void        fxh_die_bad_record(const fxh_reader *r, const fxh_batch *b, int64_t idx);
 fxg_batch   fxh_as_fxg_batch(const fxh_batch *b, int with_qual);
 
+/* ---- raw access for the GPU text path (fxg_text_*): the unparsed bytes the reader currently holds ---- */
+size_t      fxh_reader_raw(fxh_reader *r, char **p);                       /* refills first; 0 = nothing left          */
+void        fxh_reader_consume(fxh_reader *r, size_t bytes, int64_t records);   /* 4-line FASTQ records             */
+void        fxh_reader_pin(fxh_reader *r);                                 /* page-lock the text buffer for DMA        */
+int         fxh_reader_at_eof(const fxh_reader *r);
+int         fxh_text_path_enabled(void);                                   /* FASTX_TEXT_PATH=0 disables it            */
+
 /* ---- writer ---- */
 typedef struct fxh_writer fxh_writer;
 fxh_writer *fxh_writer_open(const char *filename, int fastq, int compress);
 /* emit record i of b with the sequence (and quality) cut to out_len; seq/qual rows may come from another slab */
 void        fxh_write_record(fxh_writer *w, const fxh_batch *b, int64_t i, const uint8_t *seq_row, const uint8_t *qual_row,
                              int32_t out_len);
+void        fxh_write_raw(fxh_writer *w, const char *text, size_t bytes, int64_t records);   /* already formatted */
 void        fxh_writer_close(fxh_writer *w);
 size_t      fxh_num_output_sequences(const fxh_writer *w);
 size_t      fxh_num_output_reads(const fxh_writer *w);

@@ -37,6 +37,38 @@ static void *pbuf_get(pbuf *b, size_t bytes)
 
 static int batch_q(const fxh_batch *b) { return b->numeric_qual ? 33 : fxh_q_offset(); }
 
+/* GPU text path (fxg_text_*): whole chunks of raw FASTQ go to the GPU, which parses, packs, runs op and emits the
+ * output text; the host only moves blocks.  It stops at the first chunk holding anything it does not reproduce
+ * bit-exactly by construction (numeric qualities, broken structure, illegal bytes) and leaves the reader positioned
+ * at that chunk, so the record-by-record host path that follows produces the reference's output and message. */
+static void text_fast_path(fxg_ctx *ctx, fxh_reader *rd, fxh_writer *wr, int op, int a0, int a1)
+{
+    if (!fxh_text_path_enabled() || !fxh_reader_is_fastq(rd)) return;
+    char *p;
+    size_t len = fxh_reader_raw(rd, &p);
+    if (len == 0) return;
+    size_t cap = (size_t)256 << 20;
+    if (fxh_reader_at_eof(rd) && len + 4096 < cap) cap = len + 4096;
+    fxg_text *tx = NULL;
+    const int dev = getenv("FASTX_GPU") ? atoi(getenv("FASTX_GPU")) : 0;
+    if (fxg_text_new(ctx, dev, cap, &tx) != FXG_OK) return;            /* not enough memory: host path */
+    char *out = (char *)pinned(cap + cap / 4 + 64);
+    fxh_reader_pin(rd);
+    for (;;) {
+        len = fxh_reader_raw(rd, &p);
+        if (len == 0) break;
+        if (len > cap) len = cap;
+        fxg_text_report rep;
+        int rc = fxg_text_run_host(tx, op, p, len, fxh_q_offset(), a0, a1, out, &rep);
+        if (rc != FXG_OK) errx(1, "fxg_text_run_host failed: %s (%s)", fxg_strerror(rc), fxg_text_error(tx));
+        if (rep.anomaly != 0 || rep.n_records == 0) break;             /* let the host parser look at this chunk */
+        fxh_write_raw(wr, out, (size_t)rep.out_bytes, rep.n_out_records);
+        fxh_reader_consume(rd, (size_t)rep.consumed_bytes, rep.n_records);
+    }
+    fxg_free_pinned(out);
+    fxg_text_free(tx);
+}
+
 /* ================================================================================ fastq_quality_trimmer */
 static int tr_min_quality = 0, tr_min_length = 0;
 
@@ -67,6 +99,7 @@ static int main_trimmer(int argc, char **argv)
     fxg_ctx *ctx = fxh_gpu_open();
     pbuf out = { 0, 0 };
     fxh_batch *b;
+    text_fast_path(ctx, rd, wr, 0, tr_min_quality, tr_min_length);
     while ((b = fxh_reader_next(rd, fxh_batch_reads())) != NULL) {
         int32_t *out_len = (int32_t *)pbuf_get(&out, (size_t)b->n * sizeof(int32_t));
         fxg_batch gb = fxh_as_fxg_batch(b, 1);
@@ -122,6 +155,7 @@ static int main_filter(int argc, char **argv)
     fxg_ctx *ctx = fxh_gpu_open();
     pbuf out = { 0, 0 };
     fxh_batch *b;
+    text_fast_path(ctx, rd, wr, 1, fl_min_quality, fl_min_percent);
     while ((b = fxh_reader_next(rd, fxh_batch_reads())) != NULL) {
         uint8_t *keep = (uint8_t *)pbuf_get(&out, (size_t)b->n);
         fxg_batch gb = fxh_as_fxg_batch(b, 1);

@@ -176,6 +176,36 @@ int64_t     fxg_collapse_launches(const fxg_collapser *c);
 int         fxg_collapse_order_dev(int device, const uint64_t *hash_dev, const uint64_t *first_dev, const uint64_t *count_dev,
                                    int64_t n_unique, uint32_t *perm_dev);
 
+/* ---- next to the loop: FASTQ text in, FASTQ text out, parsed / packed / emitted on the GPU --------
+ * fxg_text_run_host(): `text_host` holds raw 4-line FASTQ (any number of bytes; an incomplete trailing record is left
+ * alone, see consumed_bytes).  The GPU indexes the lines (fastx.c:324-378 fgets/chomp), checks the record structure
+ * (fastx.c:331-347,361-362,382-390), packs the slabs, runs op 0 = fastq_quality_trimmer (a0 = -t, a1 = -l) or
+ * op 1 = fastq_quality_filter (a0 = -q, a1 = -p) with fused validation, and writes the surviving records as text
+ * (fastx.c:440-473) into out_host (capacity >= 1.25 x max_chunk_bytes).  Anything it cannot reproduce bit-exactly
+ * by construction (broken structure, numeric qualities, illegal bytes, over-long lines) is reported as
+ * anomaly != 0 with nothing emitted, so the caller can re-read that chunk with the host parser. */
+typedef struct {
+    int64_t n_records;        /* complete records found in the chunk                          */
+    int64_t n_out_records;    /* records emitted                                              */
+    int64_t consumed_bytes;   /* bytes of input covered by those records                      */
+    int64_t out_bytes;        /* bytes written to out_host                                    */
+    int32_t max_len;          /* longest read                                                 */
+    int32_t anomaly;          /* 0 = none, else FXG_TEXT_* class                              */
+    int64_t anomaly_record;   /* first record (0-based within the chunk) with the anomaly     */
+} fxg_text_report;
+#define FXG_TEXT_PREFIX     1
+#define FXG_TEXT_EMPTY_SEQ  2
+#define FXG_TEXT_QUAL_LEN   3
+#define FXG_TEXT_LONG_LINE  4
+#define FXG_TEXT_BAD_RECORD 5
+typedef struct fxg_text fxg_text;
+int         fxg_text_new(fxg_ctx *ctx, int device, size_t max_chunk_bytes, fxg_text **out);
+void        fxg_text_free(fxg_text *t);
+int         fxg_text_run_host(fxg_text *t, int op, const char *text_host, size_t bytes, int q_offset, int a0, int a1,
+                              char *out_host, fxg_text_report *rep);
+const char *fxg_text_error(const fxg_text *t);
+int64_t     fxg_text_launches(const fxg_text *t);
+
 #ifdef __cplusplus
 }
 #endif

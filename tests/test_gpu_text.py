@@ -1,0 +1,92 @@
+"""GPU parity (-m gpu): the text path (K-LINES / K-RECS / K-PACK / op / K-EMIT, fxg_text_run_host) — output text must be
+byte-identical to what the reference writer would emit for the oracle's decisions; anything unusual must be flagged."""
+import numpy as np
+import pytest
+
+import helpers as H
+from test_gpu_parity import ctx  # noqa: F401
+from test_oracle_golden import emit
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def fastq_bytes(seq, qual, lens, L, crlf=False, plus_names=False):
+    out = []
+    nl = b"\r\n" if crlf else b"\n"
+    for i in range(seq.shape[0]):
+        l = int(lens[i]) if lens is not None else L
+        name = b"r%d some comment" % i
+        out.append(b"@" + name + nl + seq[i, :l].tobytes() + nl + (b"+" + name if plus_names and i % 3 == 0 else b"+") + nl + qual[i, :l].tobytes() + nl)
+    return b"".join(out)
+
+
+def expected(text, q_offset, op, a0, a1):
+    import io, tempfile, os
+    p = tempfile.mktemp(suffix=".fq")
+    open(p, "wb").write(text)
+    recs = H.read_fastx(p)
+    os.unlink(p)
+    seq, qual, lens, stride, _ = H.slab_from_records(recs, q_offset)
+    if op == 0:
+        out, bad = H.o_trim(seq, qual, lens, 0, stride, q_offset, a0, a1)
+    else:
+        keep, bad = H.o_filter(seq, qual, lens, 0, stride, q_offset, a0, a1)
+        out = np.where(keep != 0, lens, -1)
+    return emit(recs, out, q_offset), int((out >= 0).sum()), len(recs)
+
+
+@pytest.mark.parametrize("L,ragged,crlf", [(150, False, False), (100, True, False), (50, False, True), (37, True, True)])
+def test_text_path_matches_reference_writer(ctx, L, ragged, crlf):
+    import fastx_toolkit_b200 as F
+    n = 20000
+    seq, qual = H.synth_slab(H.SEED_BASE + 13, n, L, H.WITH_N)
+    lens = H.ragged(seq, qual, np.random.default_rng(L), min_len=1) if ragged else None
+    text = fastq_bytes(seq, qual, lens, L, crlf, plus_names=True)
+    tp = F.TextPipe(ctx, len(text) + 4096)
+    for op, a0, a1 in ((0, 20, 20), (0, 35, 0), (1, 20, 90), (1, 30, 50)):
+        got, rep = tp.run(op, text, 33, a0, a1)
+        exp, kept, nrec = expected(text, 33, op, a0, a1)
+        assert rep.anomaly == 0 and rep.n_records == nrec == n and rep.consumed_bytes == len(text)
+        assert rep.n_out_records == kept and rep.out_bytes == len(exp)
+        assert got == exp
+    # a chunk that ends in the middle of a record: only the complete records are consumed
+    cut = len(text) - 57
+    got, rep = tp.run(0, text[:cut], 33, 20, 20)
+    assert rep.n_records == n - 1 and text[rep.consumed_bytes - 1:rep.consumed_bytes] == b"\n"
+    exp, kept, _ = expected(text[:rep.consumed_bytes], 33, 0, 20, 20)
+    assert got == exp and rep.n_out_records == kept
+    # last line without a trailing newline: that record is left to the caller
+    got, rep = tp.run(0, text.rstrip(b"\r\n"), 33, 20, 20)
+    assert rep.n_records == n - 1
+    assert tp.L.fxg_text_launches(tp.h) > 0
+    tp.close()
+
+
+def test_text_path_flags_anomalies(ctx):
+    import fastx_toolkit_b200 as F
+    n, L = 5000, 60
+    seq, qual = H.synth_slab(H.SEED_BASE + 13, n, L, H.PLAIN)
+    lines = fastq_bytes(seq, qual, None, L).split(b"\n")[:-1]
+    tp = F.TextPipe(ctx, 4 << 20)
+
+    def run(edit):
+        ls = list(lines)
+        edit(ls)
+        return tp.run(0, b"\n".join(ls) + b"\n", 33, 20, 20)[1]
+
+    rep = run(lambda ls: ls.__setitem__(4 * 1234 + 3, b"40 " * 59 + b"40"))        # numeric quality line
+    assert (rep.anomaly, rep.anomaly_record) == (3, 1234)
+    rep = run(lambda ls: ls.__setitem__(4 * 77, b"r77"))                             # no '@'
+    assert (rep.anomaly, rep.anomaly_record) == (1, 77)
+    rep = run(lambda ls: (ls.__setitem__(4 * 9 + 1, b""), ls.__setitem__(4 * 9 + 3, b"")))
+    assert (rep.anomaly, rep.anomaly_record) == (2, 9)
+    rep = run(lambda ls: ls.__setitem__(4 * 4000 + 1, b"ACGU" + b"A" * 56))          # illegal base -> op kernel
+    assert (rep.anomaly, rep.anomaly_record) == (5, 4000)
+    rep = run(lambda ls: ls.__setitem__(4 * 4001 + 3, b"I" * 59 + b"\x07"))          # illegal quality
+    assert (rep.anomaly, rep.anomaly_record) == (5, 4001)
+    rep = run(lambda ls: (ls.__setitem__(4 * 10 + 3, b"\x07" * 60), ls.__setitem__(4 * 5, b"x")))   # earliest wins per stage
+    assert (rep.anomaly, rep.anomaly_record) == (1, 5)
+    rep = run(lambda ls: None)
+    assert rep.anomaly == 0 and rep.n_records == n
+    tp.close()
