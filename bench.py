@@ -187,7 +187,7 @@ def main():
     ap.add_argument("--reads", type=int, default=100_000_000, help="reads per GPU (HBM-resident batch)")
     ap.add_argument("--e2e-reads", type=int, default=8_000_000, help="reads per GPU per e2e step (pinned host slabs)")
     ap.add_argument("--cpu-sample", type=int, default=3_000_000, help="reads in the single-core CPU baseline sample")
-    ap.add_argument("--ref-sample", type=int, default=500_000, help="reads per process per step for --impl reference")
+    ap.add_argument("--ref-sample", type=int, default=100_000, help="reads per process per step for --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -275,7 +275,7 @@ def main():
         torch.cuda.synchronize()
     clocks = sampler.stop()
 
-    # ---------------- end to end through the host C-ABI ----------------
+    # ---------------- end to end, slab level: pinned SoA slabs -> H2D -> K-TRIM -> D2H (fxg_trim_host) ----------------
     ne = min(args.e2e_reads, n)
     hseq = torch.empty((ne, STRIDE), dtype=torch.uint8).pin_memory()
     hqual = torch.empty((ne, STRIDE), dtype=torch.uint8).pin_memory()
@@ -286,15 +286,76 @@ def main():
     for _ in range(max(args.warmup, 3)):
         ctx.trim_host(hb, Q, T, MINLEN, hout)
     barrier()
-    launches_e0 = ctx.launches()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        r = ctx.trim_host(hb, Q, T, MINLEN, hout)
+        ctx.trim_host(hb, Q, T, MINLEN, hout)
     torch.cuda.synchronize()
     dt = max_over_ranks(time.perf_counter() - t0)
-    launches_e2e = ctx.launches() - launches_e0
     assert bool((hout == out[:ne].cpu()).all()), "e2e result differs from the HBM-resident result"
-    e2e_value = world * ne * args.steps / dt / 1e6
+    e2e_slab_value = world * ne * args.steps / dt / 1e6
+    del hseq, hqual
+
+    # ---------------- end to end, text level (the call a FASTQ user makes): FASTQ text in pinned host memory ->
+    # H2D -> K-LINES/K-RECS/K-PACK -> K-TRIM -> K-EMIT -> D2H -> trimmed FASTQ text in host memory (fxg_text_run_host),
+    # W worker threads per GPU, each with its own context so that copies and kernels of neighbouring chunks overlap
+    import ctypes as C
+    import threading
+    import numpy as np
+    chunk_reads = 250_000
+    exe = os.path.join(ROOT, "bin", "fxg_synth")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", ROOT, "tools"], stdout=subprocess.DEVNULL)
+    chunk = subprocess.run([exe, "-n", str(chunk_reads), "-l", str(L), "-s", str(SEED), "-f", str(rank * chunk_reads)],
+                           stdout=subprocess.PIPE, check=True).stdout
+    cb = len(chunk)
+    nchunks = max(1, args.e2e_reads // chunk_reads)
+    host_in = torch.empty(cb, dtype=torch.uint8).pin_memory()
+    host_in.numpy()[:] = np.frombuffer(chunk, np.uint8)
+    W = 3
+    workers = []
+    for _ in range(W):
+        wctx = F.Context(local_rank)
+        workers.append((wctx, F.TextPipe(wctx, cb + 4096), torch.empty(cb + cb // 4 + 64, dtype=torch.uint8).pin_memory()))
+    Lib = F.lib()
+    stat = {"out_bytes": 0, "launches": 0}
+
+    def text_worker(w, count):
+        wctx, tp, wout = workers[w]
+        rep = F.TextReport()
+        for _ in range(count):
+            rc = Lib.fxg_text_run_host(tp.h, 0, host_in.data_ptr(), cb, Q, T, MINLEN, wout.data_ptr(), C.byref(rep))
+            if rc != 0 or rep.anomaly != 0 or rep.n_records != chunk_reads:
+                raise RuntimeError("text path failed: rc=%d anomaly=%d" % (rc, rep.anomaly))
+        stat["out_bytes"] = int(rep.out_bytes)
+
+    def text_pass():
+        per = [nchunks // W + (1 if w < nchunks % W else 0) for w in range(W)]
+        th = [threading.Thread(target=text_worker, args=(w, per[w])) for w in range(W)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+
+    for _ in range(max(args.warmup, 3)):
+        text_pass()
+    # the emitted text must be what the reference writer produces for the kernel's own decisions
+    first = out[: chunk_reads].cpu().numpy() if rank == 0 else None
+    barrier()
+    l0 = sum(int(Lib.fxg_text_launches(w[1].h)) + w[0].launches() for w in workers)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        text_pass()
+    torch.cuda.synchronize()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    launches_e2e = sum(int(Lib.fxg_text_launches(w[1].h)) + w[0].launches() for w in workers) - l0
+    e2e_value = world * nchunks * chunk_reads * args.steps / dt / 1e6
+    if rank == 0:
+        got = workers[0][2].numpy()[: stat["out_bytes"]].tobytes().split(b"\n")
+        src = chunk.split(b"\n")
+        k = 0
+        for i in range(chunk_reads):
+            if first[i] >= 0:
+                assert got[4 * k] == src[4 * i] and got[4 * k + 1] == src[4 * i + 1][: first[i]] and got[4 * k + 3] == src[4 * i + 3][: first[i]], "text path output differs"
+                k += 1
+        assert len(got) == 4 * k + 1
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -312,10 +373,14 @@ def main():
                      "traffic": n * NCU_TRAFFIC_BYTES_PER_READ, "traffic_source": "ncu --set full capture of the same kernel (profiles/r01_ncu_trim_full.txt), bytes/read x reads per launch",
                      "kernel": "fxg::k_scan_w<G=1,TRIM,HAS_SEQ> (warp-private TMA ring, lane per read)", "algorithmic_bytes_per_read": ALGO_BYTES_PER_READ,
                      "kernel_ms": kernel_ms, "peak_source": peak_src},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * ne * 2 * STRIDE, "d2h_bytes_per_step": world * ne * 4,
-                "reads_per_step_per_gpu": ne, "api": "fxg_trim_host (pinned host slabs -> H2D -> K-TRIM -> D2H int32 per read)",
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * nchunks * cb, "d2h_bytes_per_step": world * nchunks * stat["out_bytes"],
+                "reads_per_step_per_gpu": nchunks * chunk_reads,
+                "api": "fxg_text_run_host: FASTQ text in pinned host memory -> H2D -> parse/pack/K-TRIM/emit on the GPU -> D2H -> trimmed FASTQ text "
+                       "in host memory; %d worker threads per GPU, chunks of %d reads" % (W, chunk_reads),
                 "timing": "host wall clock around the blocking C-ABI calls, synchronize both sides, max over ranks",
-                "gpu_launches": launches_e2e},
+                "gpu_launches": launches_e2e,
+                "slab_level": {"value": e2e_slab_value, "unit": UNIT, "api": "fxg_trim_host: pinned SoA slabs -> H2D -> K-TRIM -> D2H int32 per read",
+                               "h2d_bytes_per_step": world * ne * 2 * STRIDE, "d2h_bytes_per_step": world * ne * 4}},
         "gpu_launches": launches,
         "clocks": clocks,
     }

@@ -11,6 +11,7 @@
 #include <errno.h>
 #include <fcntl.h>
 #include <getopt.h>
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 #include <sys/stat.h>
@@ -458,6 +459,13 @@ struct fxh_writer {
     int fd;
     int closed;
     pid_t gzip_pid;
+    /* background write(2) of one already-formatted block at a time (the GPU text path alternates two blocks) */
+    pthread_t aw_thread;
+    pthread_mutex_t aw_mu;
+    pthread_cond_t aw_cv;
+    int aw_started, aw_busy, aw_quit;
+    const char *aw_buf;
+    size_t aw_bytes;
     int fastq;
     char *buf;
     size_t cap, len;
@@ -489,7 +497,6 @@ static int open_output_compressor(const char *filename, pid_t *pid)
 
 /* errx()/exit() must not lose buffered records: the reference's stdio buffers are flushed at exit too */
 static fxh_writer *g_open_writer = NULL;
-static void writer_flush(fxh_writer *w);
 static void flush_at_exit(void)
 {
     if (g_open_writer) fxh_writer_close(g_open_writer);
@@ -509,8 +516,10 @@ fxh_writer *fxh_writer_open(const char *filename, int fastq, int compress)
     return w;
 }
 
+static void aw_wait(fxh_writer *w);
 static void writer_flush(fxh_writer *w)
 {
+    aw_wait(w);          /* keep the byte order: a background block goes out before anything buffered later */
     size_t off = 0;
     while (off < w->len) {
         ssize_t k = write(w->fd, w->buf + off, w->len - off);
@@ -553,15 +562,60 @@ void fxh_write_record(fxh_writer *w, const fxh_batch *b, int64_t i, const uint8_
     w->n_reads += (size_t)b->weight[i];
 }
 
-void fxh_write_raw(fxh_writer *w, const char *text, size_t bytes, int64_t records)
+static void write_all(int fd, const char *text, size_t bytes)
 {
-    writer_flush(w);
     size_t off = 0;
     while (off < bytes) {
-        ssize_t k = write(w->fd, text + off, bytes - off);
+        ssize_t k = write(fd, text + off, bytes - off);
         if (k < 0) { if (errno == EINTR) continue; err(1, "writing nucleotides failed"); }
         off += (size_t)k;
     }
+}
+
+static void *aw_main(void *arg)
+{
+    fxh_writer *w = (fxh_writer *)arg;
+    pthread_mutex_lock(&w->aw_mu);
+    for (;;) {
+        while (!w->aw_busy && !w->aw_quit) pthread_cond_wait(&w->aw_cv, &w->aw_mu);
+        if (w->aw_busy) {
+            const char *b = w->aw_buf; size_t n = w->aw_bytes;
+            pthread_mutex_unlock(&w->aw_mu);
+            write_all(w->fd, b, n);
+            pthread_mutex_lock(&w->aw_mu);
+            w->aw_busy = 0;
+            pthread_cond_broadcast(&w->aw_cv);
+        } else if (w->aw_quit) break;
+    }
+    pthread_mutex_unlock(&w->aw_mu);
+    return NULL;
+}
+
+/* wait until the background block (if any) is on its way to the kernel */
+static void aw_wait(fxh_writer *w)
+{
+    if (!w->aw_started) return;
+    pthread_mutex_lock(&w->aw_mu);
+    while (w->aw_busy) pthread_cond_wait(&w->aw_cv, &w->aw_mu);
+    pthread_mutex_unlock(&w->aw_mu);
+}
+
+/* Formatted text produced elsewhere (the GPU): written by a background thread so that the next chunk's read + GPU
+ * work overlaps this write.  `text` must stay untouched until the NEXT fxh_write_raw() call returns. */
+void fxh_write_raw(fxh_writer *w, const char *text, size_t bytes, int64_t records)
+{
+    writer_flush(w);
+    if (!w->aw_started) {
+        pthread_mutex_init(&w->aw_mu, NULL);
+        pthread_cond_init(&w->aw_cv, NULL);
+        if (pthread_create(&w->aw_thread, NULL, aw_main, w) != 0) err(1, "pthread_create");
+        w->aw_started = 1;
+    }
+    aw_wait(w);
+    pthread_mutex_lock(&w->aw_mu);
+    w->aw_buf = text; w->aw_bytes = bytes; w->aw_busy = 1;
+    pthread_cond_broadcast(&w->aw_cv);
+    pthread_mutex_unlock(&w->aw_mu);
     w->n_seq += (size_t)records;
     w->n_reads += (size_t)records;
 }
@@ -572,6 +626,14 @@ void fxh_writer_close(fxh_writer *w)
     w->closed = 1;
     if (g_open_writer == w) g_open_writer = NULL;
     writer_flush(w);
+    if (w->aw_started) {
+        pthread_mutex_lock(&w->aw_mu);
+        w->aw_quit = 1;
+        pthread_cond_broadcast(&w->aw_cv);
+        pthread_mutex_unlock(&w->aw_mu);
+        pthread_join(w->aw_thread, NULL);
+        w->aw_started = 0;
+    }
     if (w->fd != STDOUT_FILENO) close(w->fd);
     if (w->gzip_pid > 0) { int st; waitpid(w->gzip_pid, &st, 0); }   /* let gzip finish before we exit */
 }

@@ -47,24 +47,29 @@ static void text_fast_path(fxg_ctx *ctx, fxh_reader *rd, fxh_writer *wr, int op,
     char *p;
     size_t len = fxh_reader_raw(rd, &p);
     if (len == 0) return;
-    size_t cap = (size_t)256 << 20;
+    size_t cap = (size_t)64 << 20;             /* chunk size: small enough to overlap, large enough for PCIe */
     if (fxh_reader_at_eof(rd) && len + 4096 < cap) cap = len + 4096;
     fxg_text *tx = NULL;
     const int dev = getenv("FASTX_GPU") ? atoi(getenv("FASTX_GPU")) : 0;
     if (fxg_text_new(ctx, dev, cap, &tx) != FXG_OK) return;            /* not enough memory: host path */
-    char *out = (char *)pinned(cap + cap / 4 + 64);
+    const size_t ocap = cap + cap / 4 + 64;
+    char *out = (char *)pinned(2 * ocap);       /* two output blocks: one is being written while the next is filled */
+    int which = 0;
     fxh_reader_pin(rd);
     for (;;) {
         len = fxh_reader_raw(rd, &p);
         if (len == 0) break;
         if (len > cap) len = cap;
         fxg_text_report rep;
-        int rc = fxg_text_run_host(tx, op, p, len, fxh_q_offset(), a0, a1, out, &rep);
+        char *o = out + (size_t)which * ocap;
+        int rc = fxg_text_run_host(tx, op, p, len, fxh_q_offset(), a0, a1, o, &rep);
         if (rc != FXG_OK) errx(1, "fxg_text_run_host failed: %s (%s)", fxg_strerror(rc), fxg_text_error(tx));
         if (rep.anomaly != 0 || rep.n_records == 0) break;             /* let the host parser look at this chunk */
-        fxh_write_raw(wr, out, (size_t)rep.out_bytes, rep.n_out_records);
+        fxh_write_raw(wr, o, (size_t)rep.out_bytes, rep.n_out_records);
         fxh_reader_consume(rd, (size_t)rep.consumed_bytes, rep.n_records);
+        which ^= 1;
     }
+    fxh_write_raw(wr, out, 0, 0);               /* drain the background write before the blocks are released */
     fxg_free_pinned(out);
     fxg_text_free(tx);
 }
