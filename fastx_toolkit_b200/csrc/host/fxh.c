@@ -17,6 +17,7 @@
 #include <sys/stat.h>
 #include <sys/types.h>
 #include <sys/wait.h>
+#include <time.h>
 #include <unistd.h>
 
 /* ------------------------------------------------------------------------------------------------
@@ -160,6 +161,11 @@ fxh_reader *fxh_reader_open(const char *filename, int allowed, int q_offset, int
     r->q_offset = q_offset;
     r->stale_rows = stale_rows;
     r->cap = (size_t)256 << 20;
+    {   /* a regular file smaller than the default window needs no more than its own size */
+        struct stat sb;
+        if (r->fd != STDIN_FILENO && fstat(r->fd, &sb) == 0 && S_ISREG(sb.st_mode) && (size_t)sb.st_size + (2u << 20) < r->cap)
+            r->cap = (size_t)sb.st_size + (2u << 20);
+    }
     r->buf = (char *)malloc(r->cap + 1);
     if (!r->buf) err(1, "out of memory (input buffer)");
     refill(r, 0);
@@ -411,7 +417,17 @@ void fxh_reader_consume(fxh_reader *r, size_t bytes, int64_t records)
     r->next_index += records;
 }
 
-void fxh_reader_pin(fxh_reader *r) { (void)fxg_host_register(r->buf, r->cap + 1); }
+void fxh_reader_pin(fxh_reader *r)
+{
+    if (r->cap >= ((size_t)32 << 20)) (void)fxg_host_register(r->buf, r->cap + 1);   /* small inputs: not worth page-locking */
+}
+
+double fxh_now(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
 int fxh_reader_at_eof(const fxh_reader *r) { return r->eof; }
 
 int fxh_text_path_enabled(void)

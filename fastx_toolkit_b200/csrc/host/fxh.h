@@ -88,5 +88,6 @@ size_t      fxh_num_output_reads(const fxh_writer *w);
 fxg_ctx    *fxh_gpu_open(void);                 /* FASTX_GPU=<index> (default 0); dies if no GPU: no CPU fallback */
 void        fxh_gpu_check(fxg_ctx *ctx, int rc, const char *what);
 int64_t     fxh_batch_reads(void);              /* FASTX_BATCH_READS (default 2 M) */
+double      fxh_now(void);                      /* monotonic seconds (FASTX_TIMING=1 phase report) */
 
 #endif

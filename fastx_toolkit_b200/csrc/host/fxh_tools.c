@@ -55,21 +55,32 @@ static void text_fast_path(fxg_ctx *ctx, fxh_reader *rd, fxh_writer *wr, int op,
     const size_t ocap = cap + cap / 4 + 64;
     char *out = (char *)pinned(2 * ocap);       /* two output blocks: one is being written while the next is filled */
     int which = 0;
+    const int timing = getenv("FASTX_TIMING") != NULL;
+    double t_read = 0, t_gpu = 0, t_write = 0, t0 = fxh_now(), ta, tb;
     fxh_reader_pin(rd);
+    const double t_pin = fxh_now() - t0;
     for (;;) {
+        ta = fxh_now();
         len = fxh_reader_raw(rd, &p);
+        tb = fxh_now(); t_read += tb - ta;
         if (len == 0) break;
         if (len > cap) len = cap;
         fxg_text_report rep;
         char *o = out + (size_t)which * ocap;
         int rc = fxg_text_run_host(tx, op, p, len, fxh_q_offset(), a0, a1, o, &rep);
+        ta = fxh_now(); t_gpu += ta - tb;
         if (rc != FXG_OK) errx(1, "fxg_text_run_host failed: %s (%s)", fxg_strerror(rc), fxg_text_error(tx));
         if (rep.anomaly != 0 || rep.n_records == 0) break;             /* let the host parser look at this chunk */
         fxh_write_raw(wr, o, (size_t)rep.out_bytes, rep.n_out_records);
         fxh_reader_consume(rd, (size_t)rep.consumed_bytes, rep.n_records);
+        t_write += fxh_now() - ta;
         which ^= 1;
     }
+    ta = fxh_now();
     fxh_write_raw(wr, out, 0, 0);               /* drain the background write before the blocks are released */
+    t_write += fxh_now() - ta;
+    if (timing) fprintf(stderr, "[timing] text path: pin %.3f s, read/refill %.3f s, H2D+GPU+D2H %.3f s, waiting for write(2) %.3f s, total %.3f s\n",
+                        t_pin, t_read, t_gpu, t_write, fxh_now() - t0);
     fxg_free_pinned(out);
     fxg_text_free(tx);
 }
@@ -99,9 +110,12 @@ static int main_trimmer(int argc, char **argv)
 {
     fxh_parse_cmdline(argc, argv, "t:l:", tr_args, fxh_usage_fastq_quality_trimmer);
     if (tr_min_quality == 0) errx(1, "Missing minimum quality threshold value (-t)");
+    const double t_start = fxh_now();
     fxh_reader *rd = fxh_reader_open(fxh_input_filename(), FXH_FASTQ_ONLY, fxh_q_offset(), 0);
     fxh_writer *wr = fxh_writer_open(fxh_output_filename(), 1, fxh_compress_output());
+    const double t_opened = fxh_now();
     fxg_ctx *ctx = fxh_gpu_open();
+    if (getenv("FASTX_TIMING")) fprintf(stderr, "[timing] open+first read %.3f s, GPU context %.3f s\n", t_opened - t_start, fxh_now() - t_opened);
     pbuf out = { 0, 0 };
     fxh_batch *b;
     text_fast_path(ctx, rd, wr, 0, tr_min_quality, tr_min_length);
@@ -117,6 +131,7 @@ static int main_trimmer(int argc, char **argv)
         if (rep.first_bad_read >= 0) { fxh_writer_close(wr); fxh_die_bad_record(rd, b, rep.first_bad_read); }
     }
     fxh_writer_close(wr);
+    if (getenv("FASTX_TIMING")) fprintf(stderr, "[timing] total %.3f s\n", fxh_now() - t_start);
     if (fxh_verbose()) {
         FILE *f = fxh_report_file();
         fprintf(f, "Minimum Quality Threshold: %d\n", tr_min_quality);
