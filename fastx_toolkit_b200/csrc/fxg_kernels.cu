@@ -627,12 +627,22 @@ __global__ void __launch_bounds__(256) k_synth(const SynthParams P)
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
+// Kernels that may need more than 48 KB of dynamic shared memory opt in right before the launch (a per-launch
+// cudaFuncSetAttribute costs microseconds; doing it for every instantiation at start-up made fxg_init() load
+// ~100 kernels eagerly).
+#define FXG_LAUNCH_DYN(KERNEL, GRID, BLOCK, SMEM, STREAM, PARAMS)                                   \
+    do {                                                                                           \
+        auto kf_ = KERNEL;                                                                         \
+        if ((SMEM) > 48u * 1024u) cudaFuncSetAttribute(kf_, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM); \
+        kf_<<<(GRID), (BLOCK), (SMEM), (STREAM)>>>(PARAMS);                                        \
+    } while (0)
+
 template <int MODE, bool HAS_SEQ>
 static cudaError_t launch_scan_g(const TilePlan &plan, const ScanParams &p, cudaStream_t st)
 {
 #define FXG_SCAN_CASE(GV)                                                                          \
     case GV:                                                                                       \
-        k_scan<GV, MODE, HAS_SEQ><<<plan.grid, THREADS, plan.smem_bytes, st>>>(p);                 \
+        FXG_LAUNCH_DYN((k_scan<GV, MODE, HAS_SEQ>), plan.grid, THREADS, plan.smem_bytes, st, p);       \
         break;
     switch (plan.g) {
         FXG_SCAN_CASE(1) FXG_SCAN_CASE(2) FXG_SCAN_CASE(4) FXG_SCAN_CASE(8) FXG_SCAN_CASE(16) FXG_SCAN_CASE(32)
@@ -647,7 +657,7 @@ static cudaError_t launch_scan_w(const TilePlan &plan, const ScanParams &p, cuda
 {
 #define FXG_SCANW_CASE(GV)                                                                         \
     case GV:                                                                                       \
-        k_scan_w<GV, MODE, HAS_SEQ><<<plan.grid, W_THREADS, plan.smem_bytes, st>>>(p);             \
+        FXG_LAUNCH_DYN((k_scan_w<GV, MODE, HAS_SEQ>), plan.grid, W_THREADS, plan.smem_bytes, st, p);   \
         break;
     switch (plan.g) {
         FXG_SCANW_CASE(1) FXG_SCANW_CASE(2) FXG_SCANW_CASE(4) FXG_SCANW_CASE(8)
@@ -672,7 +682,7 @@ static cudaError_t launch_revcomp_g(const TilePlan &plan, const RevcompParams &p
 {
 #define FXG_RC_CASE(GV)                                                                            \
     case GV:                                                                                       \
-        k_revcomp<GV, HAS_QUAL><<<plan.grid, THREADS, plan.smem_bytes, st>>>(p);                   \
+        FXG_LAUNCH_DYN((k_revcomp<GV, HAS_QUAL>), plan.grid, THREADS, plan.smem_bytes, st, p);         \
         break;
     switch (plan.g) {
         FXG_RC_CASE(1) FXG_RC_CASE(2) FXG_RC_CASE(4) FXG_RC_CASE(8) FXG_RC_CASE(16) FXG_RC_CASE(32)
@@ -687,7 +697,7 @@ static cudaError_t launch_revcomp_w(const TilePlan &plan, const RevcompParams &p
 {
 #define FXG_RCW_CASE(GV)                                                                           \
     case GV:                                                                                       \
-        k_revcomp_w<GV, HAS_QUAL><<<plan.grid, W_THREADS, plan.smem_bytes, st>>>(p);               \
+        FXG_LAUNCH_DYN((k_revcomp_w<GV, HAS_QUAL>), plan.grid, W_THREADS, plan.smem_bytes, st, p);     \
         break;
     switch (plan.g) {
         FXG_RCW_CASE(1) FXG_RCW_CASE(2) FXG_RCW_CASE(4) FXG_RCW_CASE(8)
@@ -713,36 +723,6 @@ cudaError_t launch_synth(const SynthParams &p, cudaStream_t st)
     return cudaGetLastError();
 }
 
-template <typename K> static cudaError_t set_max_smem(K kernel)
-{
-    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
-}
-
-cudaError_t kernels_set_smem_attrs()
-{
-    cudaError_t e = cudaSuccess;
-#define FXG_ATTR_G(GV)                                                                             \
-    if (e == cudaSuccess) e = set_max_smem(k_scan<GV, MODE_TRIM, true>);                           \
-    if (e == cudaSuccess) e = set_max_smem(k_scan<GV, MODE_TRIM, false>);                          \
-    if (e == cudaSuccess) e = set_max_smem(k_scan<GV, MODE_FILTER, true>);                         \
-    if (e == cudaSuccess) e = set_max_smem(k_scan<GV, MODE_FILTER, false>);                        \
-    if (e == cudaSuccess) e = set_max_smem(k_revcomp<GV, true>);                                   \
-    if (e == cudaSuccess) e = set_max_smem(k_revcomp<GV, false>);
-    FXG_ATTR_G(1) FXG_ATTR_G(2) FXG_ATTR_G(4) FXG_ATTR_G(8) FXG_ATTR_G(16) FXG_ATTR_G(32)
-#undef FXG_ATTR_G
-#define FXG_ATTR_W(GV)                                                                             \
-    if (e == cudaSuccess) e = set_max_smem(k_scan_w<GV, MODE_TRIM, true>);                         \
-    if (e == cudaSuccess) e = set_max_smem(k_scan_w<GV, MODE_TRIM, false>);                        \
-    if (e == cudaSuccess) e = set_max_smem(k_scan_w<GV, MODE_FILTER, true>);                       \
-    if (e == cudaSuccess) e = set_max_smem(k_scan_w<GV, MODE_FILTER, false>);
-    FXG_ATTR_W(1) FXG_ATTR_W(2) FXG_ATTR_W(4) FXG_ATTR_W(8)
-#undef FXG_ATTR_W
-#define FXG_ATTR_RW(GV)                                                                            \
-    if (e == cudaSuccess) e = set_max_smem(k_revcomp_w<GV, true>);                                 \
-    if (e == cudaSuccess) e = set_max_smem(k_revcomp_w<GV, false>);
-    FXG_ATTR_RW(1) FXG_ATTR_RW(2) FXG_ATTR_RW(4) FXG_ATTR_RW(8)
-#undef FXG_ATTR_RW
-    return e;
-}
+cudaError_t kernels_set_smem_attrs() { return cudaSuccess; }   // attributes are set per launch (FXG_LAUNCH_DYN)
 
 }  // namespace fxg

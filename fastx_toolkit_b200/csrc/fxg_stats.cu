@@ -211,10 +211,16 @@ __global__ void __launch_bounds__(256) k_stats_simple(const StatsParams P)
 
 cudaError_t launch_stats(const StatsParams &p, int g, int grid, uint32_t smem_bytes, cudaStream_t st)
 {
-    if (g == 1) k_stats<1><<<grid, ST_WARPS * 32, smem_bytes, st>>>(p);
-    else if (g == 2) k_stats<2><<<grid, ST_WARPS * 64, smem_bytes, st>>>(p);
-    else if (g == 4) k_stats<4><<<grid, ST_WARPS * 128, smem_bytes, st>>>(p);
+#define FXG_STATS_LAUNCH(GV)                                                                        \
+    do {                                                                                           \
+        cudaFuncSetAttribute(k_stats<GV>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM); \
+        k_stats<GV><<<grid, ST_WARPS * 32 * GV, smem_bytes, st>>>(p);                               \
+    } while (0)
+    if (g == 1) FXG_STATS_LAUNCH(1);
+    else if (g == 2) FXG_STATS_LAUNCH(2);
+    else if (g == 4) FXG_STATS_LAUNCH(4);
     else return cudaErrorInvalidValue;
+#undef FXG_STATS_LAUNCH
     return cudaGetLastError();
 }
 
@@ -228,12 +234,6 @@ cudaError_t launch_stats_simple(const StatsParams &p, int sm_count, cudaStream_t
     return cudaGetLastError();
 }
 
-cudaError_t stats_set_smem_attrs()
-{
-    cudaError_t e = cudaFuncSetAttribute(k_stats<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_stats<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_stats<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
-    return e;
-}
+cudaError_t stats_set_smem_attrs() { return cudaSuccess; }
 
 }  // namespace fxg
