@@ -91,6 +91,7 @@ def lib():
         "fxg_text_new": (i32, [vp, i32, sz, C.POINTER(vp)]),
         "fxg_text_free": (None, [vp]),
         "fxg_text_run_host": (i32, [vp, i32, vp, sz, i32, i32, i32, vp, C.POINTER(TextReport)]),
+        "fxg_text_stats_host": (i32, [vp, vp, sz, i32, vp, C.c_int32, C.POINTER(TextReport)]),
         "fxg_text_error": (C.c_char_p, [vp]),
         "fxg_text_launches": (i64, [vp]),
         "fxg_collapse_new": (i32, [i32, i64, C.c_int32, C.POINTER(vp)]),

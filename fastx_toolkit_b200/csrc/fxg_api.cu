@@ -553,6 +553,20 @@ extern "C" int fxg_internal_scan_on_stream(fxg_ctx *ctx, int mode, const fxg_bat
     return scan_enqueue(ctx, mode == 0 ? MODE_TRIM : MODE_FILTER, b, q_offset, thr_q, min_len, min_percent, out, 0, (cudaStream_t)stream);
 }
 extern "C" void *fxg_internal_counters(fxg_ctx *ctx) { return ctx ? (void *)ctx->d_counters : NULL; }
+extern "C" int fxg_internal_revcomp_on_stream(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint8_t *oseq, uint8_t *oqual, void *stream)
+{
+    int rc = check_batch(ctx, b, true, false, q_offset);
+    if (rc) return rc;
+    CK(ctx, cudaSetDevice(ctx->device));
+    return revcomp_enqueue(ctx, b, q_offset, oseq, oqual, 0, (cudaStream_t)stream);
+}
+extern "C" int fxg_internal_stats_on_stream(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint64_t *hist, int32_t max_cycles, void *stream)
+{
+    int rc = check_batch(ctx, b, true, false, q_offset);
+    if (rc) return rc;
+    CK(ctx, cudaSetDevice(ctx->device));
+    return stats_enqueue(ctx, b, q_offset, hist, max_cycles, NULL, 0, (cudaStream_t)stream);
+}
 
 // ---- K-HASH (std::hash<std::string> of every read; collapser routing key) ----------------------------------
 extern "C" int fxg_hash_dev(fxg_ctx *ctx, const fxg_batch *b, uint64_t *hash_dev)

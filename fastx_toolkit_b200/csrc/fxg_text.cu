@@ -167,7 +167,8 @@ __device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, int 
 
 // one warp per record
 __global__ void __launch_bounds__(256) k_emit(const uint8_t *text, RecTable rt, uint32_t n_rec, const int32_t *out_len,
-                                              const uint8_t *keep_flags, const uint64_t *offs, uint8_t *out)
+                                              const uint8_t *keep_flags, const uint64_t *offs, uint8_t *out,
+                                              const uint8_t *alt_seq, const uint8_t *alt_qual, int alt_stride)
 {
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(256) k_emit(const uint8_t *text, RecTable rt, 
         warp_copy(o, text + rt.start[4 * r], l0, lane);                 // "@name"
         if (lane == 0) o[l0] = '\n';
         o += l0 + 1;
-        warp_copy(o, text + rt.start[4 * r + 1], ol, lane);             // SEQ[:len]
+        warp_copy(o, alt_seq ? alt_seq + (size_t)r * alt_stride : text + rt.start[4 * r + 1], ol, lane);   // SEQ[:len]
         if (lane == 0) o[ol] = '\n';
         o += ol + 1;
         if (l2 > 0) {                                                   // "+name2": first byte is always written as '+'
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(256) k_emit(const uint8_t *text, RecTable rt, 
             if (lane == 0) { o[0] = '+'; o[1] = '\n'; }
             o += 2;
         }
-        warp_copy(o, text + rt.start[4 * r + 3], ol, lane);             // QUAL[:len]
+        warp_copy(o, alt_qual ? alt_qual + (size_t)r * alt_stride : text + rt.start[4 * r + 3], ol, lane);  // QUAL[:len]
         if (lane == 0) o[ol] = '\n';
     }
 }
@@ -212,6 +213,8 @@ using namespace fxg;
 extern "C" int fxg_internal_scan_on_stream(fxg_ctx *ctx, int mode, const fxg_batch *b, int q_offset, int thr_q, int min_len,
                                            int min_percent, void *out, void *stream);
 extern "C" void *fxg_internal_counters(fxg_ctx *ctx);
+extern "C" int fxg_internal_revcomp_on_stream(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint8_t *oseq, uint8_t *oqual, void *stream);
+extern "C" int fxg_internal_stats_on_stream(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint64_t *hist, int32_t max_cycles, void *stream);
 
 struct fxg_text {
     fxg_ctx *ctx;
@@ -226,6 +229,7 @@ struct fxg_text {
     uint64_t *d_sizes, *d_offs;
     size_t cap_recs;
     uint8_t *d_seq, *d_qual;  size_t cap_slab;
+    uint8_t *d_oseq, *d_oqual; size_t cap_oslab;   // revcomp output rows
     void *d_tmp; size_t tmp_bytes;
     unsigned long long *d_scalars; // [0] anomaly(min), [1] kept, [2] max_len (int), [3] spare
     unsigned long long *h_scalars; // pinned mirror
@@ -253,7 +257,7 @@ extern "C" void fxg_text_free(fxg_text *t)
     cudaSetDevice(t->device);
     cudaFree(t->d_text); cudaFree(t->d_out); cudaFree(t->d_cnt); cudaFree(t->d_scan); cudaFree(t->d_line_end);
     cudaFree(t->d_start); cudaFree(t->d_llen); cudaFree(t->d_seq_len); cudaFree(t->d_out_len); cudaFree(t->d_keep);
-    cudaFree(t->d_sizes); cudaFree(t->d_offs); cudaFree(t->d_seq); cudaFree(t->d_qual); cudaFree(t->d_tmp);
+    cudaFree(t->d_sizes); cudaFree(t->d_offs); cudaFree(t->d_seq); cudaFree(t->d_qual); cudaFree(t->d_oseq); cudaFree(t->d_oqual); cudaFree(t->d_tmp);
     cudaFree(t->d_scalars); cudaFreeHost(t->h_scalars);
     if (t->st) cudaStreamDestroy(t->st);
     free(t);
@@ -295,11 +299,12 @@ static int ensure(fxg_text *t, void **p, size_t *cap, size_t need_elems, size_t 
     return FXG_OK;
 }
 
-// op: 0 = trim (a0 = threshold, a1 = min_len), 1 = filter (a0 = min_quality, a1 = min_percent)
-extern "C" int fxg_text_run_host(fxg_text *t, int op, const char *text_host, size_t bytes, int q_offset, int a0, int a1,
-                                 char *out_host, fxg_text_report *rep)
+// op: 0 = trim (a0 = threshold, a1 = min_len), 1 = filter (a0 = min_quality, a1 = min_percent), 2 = reverse complement,
+//     3 = quality-stats accumulation into hist_dev (no text output)
+static int text_run(fxg_text *t, int op, const char *text_host, size_t bytes, int q_offset, int a0, int a1,
+                    char *out_host, uint64_t *hist_dev, int32_t max_cycles, fxg_text_report *rep)
 {
-    if (!t || !text_host || !out_host || !rep || bytes > t->cap_bytes || (op != 0 && op != 1)) return FXG_ERR_ARG;
+    if (!t || !text_host || !rep || bytes > t->cap_bytes || op < 0 || op > 3 || (op != 3 && !out_host) || (op == 3 && !hist_dev)) return FXG_ERR_ARG;
     memset(rep, 0, sizeof(*rep));
     rep->anomaly_record = -1;
     if (bytes == 0) return FXG_OK;
@@ -359,16 +364,39 @@ extern "C" int fxg_text_run_host(fxg_text *t, int op, const char *text_host, siz
     // the op kernel of fxg_kernels.cu on the packed slabs (validation fused; first bad record -> context counters)
     fxg_batch b = { t->d_seq, t->d_qual, t->d_seq_len, 0, stride, (int64_t)n_rec };
     if ((rc = fxg_report_reset(t->ctx))) { snprintf(t->err, sizeof(t->err), "%s", fxg_last_error(t->ctx)); return rc; }
-    rc = fxg_internal_scan_on_stream(t->ctx, op, &b, q_offset, a0, op == 0 ? a1 : 0, op == 1 ? a1 : 0,
-                                     op == 0 ? (void *)t->d_out_len : (void *)t->d_keep, (void *)st);
+    const uint8_t *alt_seq = NULL, *alt_qual = NULL;
+    if (op <= 1) {
+        rc = fxg_internal_scan_on_stream(t->ctx, op, &b, q_offset, a0, op == 0 ? a1 : 0, op == 1 ? a1 : 0,
+                                         op == 0 ? (void *)t->d_out_len : (void *)t->d_keep, (void *)st);
+    } else if (op == 2) {
+        const size_t need_slab = (size_t)n_rec * stride;
+        if (t->cap_oslab < need_slab) {
+            size_t c = 0; if ((rc = ensure(t, (void **)&t->d_oseq, &c, need_slab, 1))) return rc;
+            c = 0; if ((rc = ensure(t, (void **)&t->d_oqual, &c, need_slab, 1))) return rc;
+            t->cap_oslab = need_slab;
+        }
+        rc = fxg_internal_revcomp_on_stream(t->ctx, &b, q_offset, t->d_oseq, t->d_oqual, (void *)st);
+        alt_seq = t->d_oseq; alt_qual = t->d_oqual;
+    } else {
+        rc = fxg_internal_stats_on_stream(t->ctx, &b, q_offset, hist_dev, max_cycles, (void *)st);
+    }
     if (rc) { snprintf(t->err, sizeof(t->err), "%s", fxg_last_error(t->ctx)); return rc; }
-    const int32_t *ol = op == 0 ? t->d_out_len : NULL;
+    if (op == 3) {
+        // NB: an illegal record makes the whole chunk an anomaly, but its earlier reads are already in hist_dev;
+        // the caller must treat that as fatal (the reference prints nothing when quality_stats dies).
+        CKT(t, cudaMemcpyAsync(t->h_scalars + 4, (unsigned long long *)fxg_internal_counters(t->ctx), 16, cudaMemcpyDeviceToHost, st));
+        CKT(t, cudaStreamSynchronize(st));
+        t->launches += 1;
+        if (t->h_scalars[5] != ~0ull) { rep->anomaly = AN_BAD_RECORD; rep->anomaly_record = (int64_t)t->h_scalars[5]; }
+        return FXG_OK;
+    }
+    const int32_t *ol = op == 0 ? t->d_out_len : (op == 2 ? t->d_seq_len : NULL);     // revcomp keeps every read at full length
     const uint8_t *kf = op == 1 ? t->d_keep : NULL;
     k_emit_sizes<<<tgrid(n_rec), 256, 0, st>>>(rt, n_rec, ol, kf, t->d_sizes);
     CKT(t, cudaMemsetAsync(t->d_sizes + n_rec, 0, 8, st));
     need = t->tmp_bytes;
     CKT(t, cub::DeviceScan::ExclusiveSum(t->d_tmp, need, t->d_sizes, t->d_offs, (int)n_rec + 1, st));
-    k_emit<<<tgrid((uint64_t)n_rec * 32), 256, 0, st>>>(t->d_text, rt, n_rec, ol, kf, t->d_offs, t->d_out);
+    k_emit<<<tgrid((uint64_t)n_rec * 32), 256, 0, st>>>(t->d_text, rt, n_rec, ol, kf, t->d_offs, t->d_out, alt_seq, alt_qual, stride);
     k_count_kept<<<tgrid(n_rec), 256, 0, st>>>(ol, kf, n_rec, t->d_scalars + 1);
     uint64_t out_bytes = 0;
     CKT(t, cudaMemcpyAsync(&out_bytes, t->d_offs + n_rec, 8, cudaMemcpyDeviceToHost, st));
@@ -388,4 +416,17 @@ extern "C" int fxg_text_run_host(fxg_text *t, int op, const char *text_host, siz
         CKT(t, cudaStreamSynchronize(st));
     }
     return FXG_OK;
+}
+
+extern "C" int fxg_text_run_host(fxg_text *t, int op, const char *text_host, size_t bytes, int q_offset, int a0, int a1,
+                                 char *out_host, fxg_text_report *rep)
+{
+    if (op < 0 || op > 2) return FXG_ERR_ARG;
+    return text_run(t, op, text_host, bytes, q_offset, a0, a1, out_host, NULL, 0, rep);
+}
+
+extern "C" int fxg_text_stats_host(fxg_text *t, const char *text_host, size_t bytes, int q_offset, uint64_t *hist_dev,
+                                   int32_t max_cycles, fxg_text_report *rep)
+{
+    return text_run(t, 3, text_host, bytes, q_offset, 0, 0, NULL, hist_dev, max_cycles, rep);
 }

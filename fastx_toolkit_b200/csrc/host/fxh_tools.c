@@ -211,6 +211,7 @@ static int main_revcomp(int argc, char **argv)
     fxg_ctx *ctx = fxh_gpu_open();
     pbuf os = { 0, 0 }, oq = { 0, 0 };
     fxh_batch *b;
+    text_fast_path(ctx, rd, wr, 2, 0, 0);          /* FASTQ only; FASTA goes through the host parser */
     while ((b = fxh_reader_next(rd, fxh_batch_reads())) != NULL) {
         const size_t bytes = (size_t)b->n * b->stride;
         uint8_t *oseq = (uint8_t *)pbuf_get(&os, bytes), *oqual = fastq ? (uint8_t *)pbuf_get(&oq, bytes) : NULL;
@@ -523,6 +524,28 @@ static int main_stats(int argc, char **argv)
     fxh_gpu_check(ctx, fxg_sync(ctx), "fxg_sync");
     int maxlen = 0;
     fxh_batch *b;
+    if (fastq && fxh_text_path_enabled()) {        /* GPU text path: parse + pack + accumulate on the device */
+        char *p;
+        size_t len = fxh_reader_raw(rd, &p);
+        size_t cap = (size_t)64 << 20;
+        if (fxh_reader_at_eof(rd) && len + 4096 < cap) cap = len + 4096;
+        fxg_text *tx = NULL;
+        if (len > 0 && fxg_text_new(ctx, getenv("FASTX_GPU") ? atoi(getenv("FASTX_GPU")) : 0, cap, &tx) == FXG_OK) {
+            fxh_reader_pin(rd);
+            for (;;) {
+                len = fxh_reader_raw(rd, &p);
+                if (len == 0) break;
+                if (len > cap) len = cap;
+                fxg_text_report rep;
+                int rc = fxg_text_stats_host(tx, p, len, fxh_q_offset(), d_hist, max_cycles, &rep);
+                if (rc != FXG_OK) errx(1, "fxg_text_stats_host failed: %s (%s)", fxg_strerror(rc), fxg_text_error(tx));
+                if (rep.anomaly != 0 || rep.n_records == 0) break;   /* numeric qualities / broken input: host parser from here */
+                if (rep.max_len > maxlen) maxlen = rep.max_len;
+                fxh_reader_consume(rd, (size_t)rep.consumed_bytes, rep.n_records);
+            }
+            fxg_text_free(tx);
+        }
+    }
     while ((b = fxh_reader_next(rd, fxh_batch_reads())) != NULL) {
         fxg_batch gb = fxh_as_fxg_batch(b, fastq);
         fxg_report rep;

@@ -179,9 +179,11 @@ int         fxg_collapse_order_dev(int device, const uint64_t *hash_dev, const u
 /* ---- next to the loop: FASTQ text in, FASTQ text out, parsed / packed / emitted on the GPU --------
  * fxg_text_run_host(): `text_host` holds raw 4-line FASTQ (any number of bytes; an incomplete trailing record is left
  * alone, see consumed_bytes).  The GPU indexes the lines (fastx.c:324-378 fgets/chomp), checks the record structure
- * (fastx.c:331-347,361-362,382-390), packs the slabs, runs op 0 = fastq_quality_trimmer (a0 = -t, a1 = -l) or
- * op 1 = fastq_quality_filter (a0 = -q, a1 = -p) with fused validation, and writes the surviving records as text
- * (fastx.c:440-473) into out_host (capacity >= 1.25 x max_chunk_bytes).  Anything it cannot reproduce bit-exactly
+ * (fastx.c:331-347,361-362,382-390), packs the slabs, runs op 0 = fastq_quality_trimmer (a0 = -t, a1 = -l),
+ * op 1 = fastq_quality_filter (a0 = -q, a1 = -p) or op 2 = fastx_reverse_complement with fused validation, and writes
+ * the surviving records as text (fastx.c:440-473) into out_host (capacity >= 1.25 x max_chunk_bytes).
+ * fxg_text_stats_host() does the same up to the slabs and accumulates the quality-stats histogram (fxg_stats_accum_*)
+ * into hist_dev instead of emitting text.  Anything it cannot reproduce bit-exactly
  * by construction (broken structure, numeric qualities, illegal bytes, over-long lines) is reported as
  * anomaly != 0 with nothing emitted, so the caller can re-read that chunk with the host parser. */
 typedef struct {
@@ -203,6 +205,8 @@ int         fxg_text_new(fxg_ctx *ctx, int device, size_t max_chunk_bytes, fxg_t
 void        fxg_text_free(fxg_text *t);
 int         fxg_text_run_host(fxg_text *t, int op, const char *text_host, size_t bytes, int q_offset, int a0, int a1,
                               char *out_host, fxg_text_report *rep);
+int         fxg_text_stats_host(fxg_text *t, const char *text_host, size_t bytes, int q_offset, uint64_t *hist_dev,
+                                int32_t max_cycles, fxg_text_report *rep);
 const char *fxg_text_error(const fxg_text *t);
 int64_t     fxg_text_launches(const fxg_text *t);
 

@@ -63,6 +63,29 @@ def test_text_path_matches_reference_writer(ctx, L, ragged, crlf):
     tp.close()
 
 
+def test_text_path_revcomp_and_stats(ctx):
+    import ctypes as C
+    import fastx_toolkit_b200 as F
+    n, L = 15000, 75
+    seq, qual = H.synth_slab(H.SEED_BASE + 14, n, L, H.WITH_N)
+    lens = H.ragged(seq, qual, np.random.default_rng(4), min_len=1)
+    text = fastq_bytes(seq, qual, lens, L, crlf=False, plus_names=True)
+    tp = F.TextPipe(ctx, len(text) + 4096)
+    got, rep = tp.run(2, text, 33, 0, 0)
+    eseq, equal = H.o_revcomp(seq, qual, lens, 0, seq.shape[1])
+    exp = fastq_bytes(eseq, equal, lens, L, plus_names=True)
+    assert rep.anomaly == 0 and rep.n_out_records == n and got == exp
+    hist = torch.zeros((L, 5, 109), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    r2 = F.TextReport()
+    src = np.frombuffer(text, np.uint8)
+    rc = tp.L.fxg_text_stats_host(tp.h, src.ctypes.data, src.size, 33, hist.data_ptr(), L, C.byref(r2))
+    assert rc == 0 and r2.anomaly == 0 and r2.n_records == n and r2.max_len == int(lens.max())
+    eh, _ = H.o_stats_hist(seq, qual, lens, 0, seq.shape[1], 33, L)
+    assert np.array_equal(hist.cpu().numpy().astype(np.uint64), eh)
+    tp.close()
+
+
 def test_text_path_flags_anomalies(ctx):
     import fastx_toolkit_b200 as F
     n, L = 5000, 60
