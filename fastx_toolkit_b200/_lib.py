@@ -88,6 +88,12 @@ def lib():
         "fxg_clip_dev": (i32, [vp, BP, vp, i32, C.POINTER(ClipOpts), vp, vp, vp, i64]),
         "fxg_clip_host": (i32, [vp, BP, vp, i32, C.POINTER(ClipOpts), vp, vp, RP]),
         "fxg_hash_dev": (i32, [vp, BP, vp]),
+        "fxg_validate_dev": (i32, [vp, BP, i32, i64]),
+        "fxg_validate_host": (i32, [vp, BP, i32, RP]),
+        "fxg_mask_dev": (i32, [vp, BP, i32, i32, i32, vp, vp, i64]),
+        "fxg_mask_host": (i32, [vp, BP, i32, i32, i32, vp, vp, RP]),
+        "fxg_artifacts_dev": (i32, [vp, BP, i32, vp, i64]),
+        "fxg_artifacts_host": (i32, [vp, BP, i32, vp, RP]),
         "fxg_text_new": (i32, [vp, i32, sz, C.POINTER(vp)]),
         "fxg_text_free": (None, [vp]),
         "fxg_text_run_host": (i32, [vp, i32, vp, sz, i32, i32, i32, vp, C.POINTER(TextReport)]),
@@ -277,6 +283,30 @@ class Context:
     def clip_dev(self, b, widths, q_offset, opts, out_len, out_class=None, out_cut=None, index_base=0):
         self._ck(self.L.fxg_clip_dev(self.h, C.byref(b), _ptr(widths), q_offset, C.byref(opts), _ptr(out_len),
                                      _ptr(out_class), _ptr(out_cut), index_base))
+
+    def validate_dev(self, b, q_offset, index_base=0):
+        self._ck(self.L.fxg_validate_dev(self.h, C.byref(b), q_offset, index_base))
+
+    def mask_dev(self, b, q_offset, min_quality, mask_char, out_seq, masked_flag, index_base=0):
+        self._ck(self.L.fxg_mask_dev(self.h, C.byref(b), q_offset, min_quality, mask_char, _ptr(out_seq), _ptr(masked_flag), index_base))
+
+    def artifacts_dev(self, b, q_offset, keep, index_base=0):
+        self._ck(self.L.fxg_artifacts_dev(self.h, C.byref(b), q_offset, _ptr(keep), index_base))
+
+    def mask_host(self, b, q_offset, min_quality, mask_char, out_seq, masked_flag):
+        r = Report()
+        self._ck(self.L.fxg_mask_host(self.h, C.byref(b), q_offset, min_quality, mask_char, _ptr(out_seq), _ptr(masked_flag), C.byref(r)))
+        return r
+
+    def artifacts_host(self, b, q_offset, keep):
+        r = Report()
+        self._ck(self.L.fxg_artifacts_host(self.h, C.byref(b), q_offset, _ptr(keep), C.byref(r)))
+        return r
+
+    def validate_host(self, b, q_offset):
+        r = Report()
+        self._ck(self.L.fxg_validate_host(self.h, C.byref(b), q_offset, C.byref(r)))
+        return r
 
     def hash_dev(self, b, hash_out):
         self._ck(self.L.fxg_hash_dev(self.h, C.byref(b), _ptr(hash_out)))

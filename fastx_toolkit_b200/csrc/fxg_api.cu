@@ -581,6 +581,45 @@ extern "C" int fxg_hash_dev(fxg_ctx *ctx, const fxg_batch *b, uint64_t *hash_dev
     return FXG_OK;
 }
 
+// ---- (f-2) validate / fastq_masker / fastx_artifacts_filter ----------------------------------------------------
+static int extra_enqueue(fxg_ctx *ctx, int op, const fxg_batch *b, int q_offset, int thr_q, int mask_char, uint8_t *out_seq,
+                         uint8_t *flags, int64_t index_base, cudaStream_t st)
+{
+    if (b->n == 0) return FXG_OK;
+    CK(ctx, launch_extra(op, b->seq, b->qual, b->len, b->uniform_len, b->stride, b->n, q_offset, thr_q, mask_char, out_seq, flags,
+                         index_base, ctx->d_counters, ctx->sm_count, st));
+    ctx->launches += (op == 1) ? 2 : 1;
+    ctx->report.n_in += b->n;
+    return FXG_OK;
+}
+
+extern "C" int fxg_validate_dev(fxg_ctx *ctx, const fxg_batch *b, int q_offset, int64_t index_base)
+{
+    int rc = check_batch(ctx, b, true, false, q_offset);
+    if (rc) return rc;
+    CK(ctx, cudaSetDevice(ctx->device));
+    return extra_enqueue(ctx, 0, b, q_offset, 0, 0, NULL, NULL, index_base, ctx->stream);
+}
+
+extern "C" int fxg_mask_dev(fxg_ctx *ctx, const fxg_batch *b, int q_offset, int min_quality, int mask_char, uint8_t *out_seq,
+                            uint8_t *masked_flag, int64_t index_base)
+{
+    int rc = check_batch(ctx, b, true, true, q_offset);
+    if (rc) return rc;
+    if (!out_seq || !masked_flag || ((uintptr_t)out_seq & 15)) return arg_error(ctx, "out_seq / masked_flag");
+    CK(ctx, cudaSetDevice(ctx->device));
+    return extra_enqueue(ctx, 1, b, q_offset, min_quality, mask_char, out_seq, masked_flag, index_base, ctx->stream);
+}
+
+extern "C" int fxg_artifacts_dev(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint8_t *keep, int64_t index_base)
+{
+    int rc = check_batch(ctx, b, true, false, q_offset);
+    if (rc) return rc;
+    if (!keep) return arg_error(ctx, "keep is NULL");
+    CK(ctx, cudaSetDevice(ctx->device));
+    return extra_enqueue(ctx, 2, b, q_offset, 0, 0, NULL, keep, index_base, ctx->stream);
+}
+
 // ---- host-buffer pipelines ---------------------------------------------------------------------------
 // Chunks of the host slab travel H2D -> kernel -> D2H on PIPE_LANES side streams, so the copy of one
 // chunk overlaps the kernel and the result copy of its neighbours (both copy engines busy).
@@ -607,7 +646,7 @@ static int64_t chunk_reads(const fxg_batch *b)
     return cr;
 }
 
-enum { HOST_TRIM, HOST_FILTER, HOST_REVCOMP, HOST_STATS, HOST_CLIP };
+enum { HOST_TRIM, HOST_FILTER, HOST_REVCOMP, HOST_STATS, HOST_CLIP, HOST_VALIDATE, HOST_MASK, HOST_ARTIFACT };
 
 struct HostOp {
     int op;
@@ -635,6 +674,8 @@ static int host_pipeline(fxg_ctx *ctx, const fxg_batch *b, const HostOp &h, fxg_
         else if (h.op == HOST_FILTER) o0 = (size_t)cr;
         else if (h.op == HOST_REVCOMP) { o0 = (size_t)cr * S; o1 = has_qual ? (size_t)cr * S : 0; }
         else if (h.op == HOST_CLIP) { o0 = (size_t)cr * sizeof(int32_t); o1 = h.out1 ? (size_t)cr : 0; }
+        else if (h.op == HOST_MASK) { o0 = (size_t)cr * S; o1 = (size_t)cr; }
+        else if (h.op == HOST_ARTIFACT) o0 = (size_t)cr;
         if (has_seq && (rc = lane_reserve(ctx, lane, SLOT_SEQ, (size_t)cr * S))) return rc;
         if (has_qual && (rc = lane_reserve(ctx, lane, SLOT_QUAL, (size_t)cr * S))) return rc;
         if (b->len && (rc = lane_reserve(ctx, lane, SLOT_LEN, (size_t)cr * sizeof(int32_t)))) return rc;
@@ -676,6 +717,18 @@ static int host_pipeline(fxg_ctx *ctx, const fxg_batch *b, const HostOp &h, fxg_
                                    NULL, r0, st))) return rc;
             CK(ctx, cudaMemcpyAsync((int32_t *)h.out0 + r0, d0, (size_t)nr * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
             if (h.out1) CK(ctx, cudaMemcpyAsync((uint8_t *)h.out1 + r0, d1, (size_t)nr, cudaMemcpyDeviceToHost, st));
+            break;
+        case HOST_VALIDATE:
+            if ((rc = extra_enqueue(ctx, 0, &db, h.q_offset, 0, 0, NULL, NULL, r0, st))) return rc;
+            break;
+        case HOST_MASK:
+            if ((rc = extra_enqueue(ctx, 1, &db, h.q_offset, h.a0, h.a1, (uint8_t *)d0, (uint8_t *)d1, r0, st))) return rc;
+            CK(ctx, cudaMemcpyAsync((uint8_t *)h.out0 + (size_t)r0 * S, d0, (size_t)nr * S, cudaMemcpyDeviceToHost, st));
+            if (h.out1) CK(ctx, cudaMemcpyAsync((uint8_t *)h.out1 + r0, d1, (size_t)nr, cudaMemcpyDeviceToHost, st));
+            break;
+        case HOST_ARTIFACT:
+            if ((rc = extra_enqueue(ctx, 2, &db, h.q_offset, 0, 0, NULL, (uint8_t *)d0, r0, st))) return rc;
+            CK(ctx, cudaMemcpyAsync((uint8_t *)h.out0 + r0, d0, (size_t)nr, cudaMemcpyDeviceToHost, st));
             break;
         }
     }
@@ -740,5 +793,35 @@ extern "C" int fxg_clip_host(fxg_ctx *ctx, const fxg_batch *b, const int32_t *wi
     if (!out_len) return arg_error(ctx, "out_len is NULL");
     HostOp h = {};
     h.op = HOST_CLIP; h.q_offset = q_offset; h.clip = o; h.aux_host = width_host; h.out0 = out_len; h.out1 = out_class;
+    return host_pipeline(ctx, b, h, report);
+}
+
+extern "C" int fxg_validate_host(fxg_ctx *ctx, const fxg_batch *b, int q_offset, fxg_report *report)
+{
+    int rc = check_batch(ctx, b, true, false, q_offset);
+    if (rc) return rc;
+    HostOp h = {};
+    h.op = HOST_VALIDATE; h.q_offset = q_offset;
+    return host_pipeline(ctx, b, h, report);
+}
+
+extern "C" int fxg_mask_host(fxg_ctx *ctx, const fxg_batch *b, int q_offset, int min_quality, int mask_char, uint8_t *out_seq,
+                             uint8_t *masked_flag, fxg_report *report)
+{
+    int rc = check_batch(ctx, b, true, true, q_offset);
+    if (rc) return rc;
+    if (!out_seq) return arg_error(ctx, "out_seq is NULL");
+    HostOp h = {};
+    h.op = HOST_MASK; h.q_offset = q_offset; h.a0 = min_quality; h.a1 = mask_char; h.out0 = out_seq; h.out1 = masked_flag;
+    return host_pipeline(ctx, b, h, report);
+}
+
+extern "C" int fxg_artifacts_host(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint8_t *keep, fxg_report *report)
+{
+    int rc = check_batch(ctx, b, true, false, q_offset);
+    if (rc) return rc;
+    if (!keep) return arg_error(ctx, "keep is NULL");
+    HostOp h = {};
+    h.op = HOST_ARTIFACT; h.q_offset = q_offset; h.out0 = keep;
     return host_pipeline(ctx, b, h, report);
 }

@@ -1,7 +1,8 @@
 /*
- * fxh_tools.c — the six drop-in executables as one multi-call program (dispatch on basename(argv[0])):
+ * fxh_tools.c — the drop-in executables as one multi-call program (dispatch on basename(argv[0])):
  *   fastq_quality_trimmer  fastq_quality_filter  fastx_reverse_complement
  *   fastx_clipper          fastx_collapser       fastx_quality_stats
+ *   + the SURVEY §8(f-2) rows:  fastx_trimmer  fastq_masker  fastx_artifacts_filter
  * Same flags, streams, messages and exit status as FASTX-Toolkit 0.0.14; the per-read loop bodies run on the
  * GPU through include/fxg.h (no CPU fallback).  Reference mains:
  *   src/fastq_quality_trimmer/fastq_quality_trimmer.c:52-123   src/fastq_quality_filter/fastq_quality_filter.c:54-178
@@ -604,6 +605,191 @@ static int main_stats(int argc, char **argv)
     return 0;
 }
 
+/* ================================================================================ fastx_trimmer   */
+static int ft_first = 1, ft_last = 0, ft_by_position = 0, ft_from_end = 0;
+static unsigned int ft_trim_last = 0, ft_min_len = 0;
+
+static int ft_args(int oi, int optc, char *oa)
+{
+    (void)oi;
+    switch (optc) {
+    case 'f':
+        if (oa == NULL) errx(1, "[-f] parameter requires an argument value");
+        ft_first = (int)strtoul(oa, NULL, 10);
+        if (ft_first <= 0 || ft_first >= FXH_MAX_LINE) errx(1, "Invalid number bases to keep (-f %s)", oa);
+        ft_by_position = 1;
+        break;
+    case 'l':
+        if (oa == NULL) errx(1, "[-l] parameter requires an argument value");
+        ft_last = (int)strtoul(oa, NULL, 10);
+        if (ft_last <= 0 || ft_last >= FXH_MAX_LINE) errx(1, "Invalid number bases to keep (-l %s)", oa);
+        ft_by_position = 1;
+        break;
+    case 't':
+        if (oa == NULL) errx(1, "[-t] parameter requires an argument value");
+        ft_trim_last = (unsigned int)strtoul(oa, NULL, 10);
+        if (ft_trim_last <= 0 || ft_trim_last >= FXH_MAX_LINE) errx(1, "Invalid number bases to trim (-t %s)", oa);
+        ft_from_end = 1;
+        break;
+    case 'm':
+        if (oa == NULL) errx(1, "[-t] parameter requires an argument value");
+        ft_min_len = (unsigned int)strtoul(oa, NULL, 10);
+        if (ft_min_len <= 0 || ft_min_len >= FXH_MAX_LINE) errx(1, "Invalid minimum length value (-m %s)", oa);
+        break;
+    default: errx(1, "Unknown argument (%c)", optc);
+    }
+    return 1;
+}
+
+/* src/fastx_trimmer/fastx_trimmer.c:120-148: which slice of the read survives; -1 = the read is dropped */
+static int ft_slice(int len, int *start)
+{
+    size_t L = (size_t)len, s0 = 0;
+    if (ft_last != 0 && (size_t)ft_last < L) L = (size_t)ft_last;
+    if (ft_first != 1) {
+        if (L < (size_t)ft_first) return -1;
+        s0 = (size_t)ft_first - 1;
+        L = L - (size_t)ft_first + 1;
+    }
+    if (ft_trim_last > 0) {
+        if (L <= ft_trim_last) return -1;
+        const size_t i = L - ft_trim_last;
+        if (i < ft_min_len) return -1;
+        L = i;
+    }
+    *start = (int)s0;
+    return (int)L;
+}
+
+static int main_fastx_trimmer(int argc, char **argv)
+{
+    fxh_parse_cmdline(argc, argv, "l:f:t:m:", ft_args, fxh_usage_fastx_trimmer);
+    if (ft_by_position && ft_from_end) errx(1, "[-t], [-f] and [-l] options can not be used together. Use [-t] or [-l,-f]");
+    fxh_reader *rd = fxh_reader_open(fxh_input_filename(), FXH_FASTA_OR_FASTQ, fxh_q_offset(), 0);
+    const int fastq = fxh_reader_is_fastq(rd);
+    fxh_writer *wr = fxh_writer_open(fxh_output_filename(), fastq, fxh_compress_output());
+    fxg_ctx *ctx = fxh_gpu_open();
+    fxh_batch *b;
+    while ((b = fxh_reader_next(rd, fxh_batch_reads())) != NULL) {
+        fxg_batch gb = fxh_as_fxg_batch(b, fastq);
+        fxg_report rep;
+        fxh_gpu_check(ctx, fxg_validate_host(ctx, &gb, batch_q(b), &rep), "fxg_validate_host");   /* the reader's checks */
+        const int64_t lim = rep.first_bad_read >= 0 ? rep.first_bad_read : b->n;
+        for (int64_t i = 0; i < lim; i++) {
+            int st = 0;
+            const int nl = ft_slice(b->len[i], &st);
+            if (nl >= 0)
+                fxh_write_record(wr, b, i, b->seq + (size_t)i * b->stride + st, b->qual + (size_t)i * b->stride + st, nl);
+        }
+        if (rep.first_bad_read >= 0) { fxh_writer_close(wr); fxh_die_bad_record(rd, b, rep.first_bad_read); }
+    }
+    fxh_writer_close(wr);
+    if (fxh_verbose()) {
+        FILE *f = fxh_report_file();
+        if (ft_first != 1 || ft_last != 0) fprintf(f, "Trimming: base %d to %d\n", ft_first, ft_last);
+        if (ft_trim_last) {
+            fprintf(f, "Trimming %d bases from the end of the reads\n", ft_trim_last);
+            if (ft_min_len) fprintf(f, "Discarding reads shorter than %d bases\n", ft_min_len);
+        }
+        fprintf(f, "Input: %zu reads.\n", fxh_num_input_reads(rd));
+        fprintf(f, "Output: %zu reads.\n", fxh_num_output_reads(wr));
+    }
+    fxg_destroy(ctx);
+    return 0;
+}
+
+/* ================================================================================ fastq_masker   */
+static int mk_min_quality = 10;
+static char mk_char = 'N';
+
+static int mk_args(int oi, int optc, char *oa)
+{
+    (void)oi;
+    switch (optc) {
+    case 'q':
+        if (oa == NULL) errx(1, "[-q] parameter requires an argument value");
+        mk_min_quality = atoi(oa);
+        if (mk_min_quality < -40) errx(1, "Invalid minimum length value (-q %s)", oa);
+        break;
+    case 'r':
+        if (oa == NULL) errx(1, "[-r] parameter requires an argument value");
+        if (strlen(oa) != 1) errx(1, "[-r] parameter requires a single character as value");
+        mk_char = oa[0];
+        break;
+    default: errx(1, "Unknown argument (%c)", optc);
+    }
+    return 1;
+}
+
+static int main_masker(int argc, char **argv)
+{
+    fxh_parse_cmdline(argc, argv, "q:r:", mk_args, fxh_usage_fastq_masker);
+    fxh_reader *rd = fxh_reader_open(fxh_input_filename(), FXH_FASTQ_ONLY, fxh_q_offset(), 0);
+    fxh_writer *wr = fxh_writer_open(fxh_output_filename(), 1, fxh_compress_output());
+    fxg_ctx *ctx = fxh_gpu_open();
+    size_t masked_reads = 0, masked_nuc = 0;
+    pbuf os = { 0, 0 }, fl = { 0, 0 };
+    fxh_batch *b;
+    while ((b = fxh_reader_next(rd, fxh_batch_reads())) != NULL) {
+        uint8_t *oseq = (uint8_t *)pbuf_get(&os, (size_t)b->n * b->stride), *flag = (uint8_t *)pbuf_get(&fl, (size_t)b->n);
+        fxg_batch gb = fxh_as_fxg_batch(b, 1);
+        fxg_report rep;
+        fxh_gpu_check(ctx, fxg_mask_host(ctx, &gb, batch_q(b), mk_min_quality, (unsigned char)mk_char, oseq, flag, &rep), "fxg_mask_host");
+        const int64_t lim = rep.first_bad_read >= 0 ? rep.first_bad_read : b->n;
+        for (int64_t i = 0; i < lim; i++) {
+            if (flag[i]) masked_reads += (size_t)b->weight[i];
+            fxh_write_record(wr, b, i, oseq + (size_t)i * b->stride, b->qual + (size_t)i * b->stride, b->len[i]);
+        }
+        masked_nuc += (size_t)rep.aux[0];
+        if (rep.first_bad_read >= 0) { fxh_writer_close(wr); fxh_die_bad_record(rd, b, rep.first_bad_read); }
+    }
+    fxh_writer_close(wr);
+    if (fxh_verbose()) {
+        FILE *f = fxh_report_file();
+        fprintf(f, "Minimum Quality Threshold: %d\n", mk_min_quality);
+        fprintf(f, "Low-quality nucleotides replaced with '%c'\n", mk_char);
+        fprintf(f, "Input: %zu reads.\n", fxh_num_input_reads(rd));
+        fprintf(f, "Output: %zu reads.\n", fxh_num_output_reads(wr));
+        fprintf(f, "Masked reads: %zu\n", masked_reads);
+        fprintf(f, "Masked nucleotides: %zu\n", masked_nuc);
+    }
+    fxg_destroy(ctx);
+    return 0;
+}
+
+/* ================================================================================ fastx_artifacts_filter   */
+static int main_artifacts(int argc, char **argv)
+{
+    fxh_parse_cmdline(argc, argv, "", NULL, fxh_usage_fastx_artifacts_filter);
+    fxh_reader *rd = fxh_reader_open(fxh_input_filename(), FXH_FASTA_OR_FASTQ, fxh_q_offset(), 0);
+    const int fastq = fxh_reader_is_fastq(rd);
+    fxh_writer *wr = fxh_writer_open(fxh_output_filename(), fastq, fxh_compress_output());
+    fxg_ctx *ctx = fxh_gpu_open();
+    pbuf kp = { 0, 0 };
+    fxh_batch *b;
+    while ((b = fxh_reader_next(rd, fxh_batch_reads())) != NULL) {
+        uint8_t *keep = (uint8_t *)pbuf_get(&kp, (size_t)b->n);
+        fxg_batch gb = fxh_as_fxg_batch(b, fastq);
+        fxg_report rep;
+        fxh_gpu_check(ctx, fxg_artifacts_host(ctx, &gb, batch_q(b), keep, &rep), "fxg_artifacts_host");
+        const int64_t lim = rep.first_bad_read >= 0 ? rep.first_bad_read : b->n;
+        for (int64_t i = 0; i < lim; i++)
+            if (keep[i])
+                fxh_write_record(wr, b, i, b->seq + (size_t)i * b->stride, b->qual + (size_t)i * b->stride, b->len[i]);
+        if (rep.first_bad_read >= 0) { fxh_writer_close(wr); fxh_die_bad_record(rd, b, rep.first_bad_read); }
+    }
+    fxh_writer_close(wr);
+    if (fxh_verbose()) {
+        FILE *f = fxh_report_file();
+        fprintf(f, "Input: %zu reads.\n", fxh_num_input_reads(rd));
+        fprintf(f, "Output: %zu reads.\n", fxh_num_output_reads(wr));
+        size_t discarded = fxh_num_input_reads(rd) - fxh_num_output_reads(wr);
+        fprintf(f, "discarded %zu (%zu%%) artifact reads.\n", discarded, (discarded * 100) / fxh_num_input_reads(rd));
+    }
+    fxg_destroy(ctx);
+    return 0;
+}
+
 /* ================================================================================ dispatch */
 int main(int argc, char **argv)
 {
@@ -615,7 +801,10 @@ int main(int argc, char **argv)
     if (!strcmp(name, "fastx_clipper")) return main_clipper(argc, argv);
     if (!strcmp(name, "fastx_collapser")) return main_collapser(argc, argv);
     if (!strcmp(name, "fastx_quality_stats")) return main_stats(argc, argv);
+    if (!strcmp(name, "fastx_trimmer")) return main_fastx_trimmer(argc, argv);
+    if (!strcmp(name, "fastq_masker")) return main_masker(argc, argv);
+    if (!strcmp(name, "fastx_artifacts_filter")) return main_artifacts(argc, argv);
     fprintf(stderr, "%s: multi-call binary; invoke it as fastq_quality_trimmer, fastq_quality_filter, fastx_reverse_complement, "
-                    "fastx_clipper, fastx_collapser or fastx_quality_stats\n", name);
+                    "fastx_clipper, fastx_collapser, fastx_quality_stats, fastx_trimmer, fastq_masker or fastx_artifacts_filter\n", name);
     return 1;
 }

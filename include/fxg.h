@@ -176,6 +176,22 @@ int64_t     fxg_collapse_launches(const fxg_collapser *c);
 int         fxg_collapse_order_dev(int device, const uint64_t *hash_dev, const uint64_t *first_dev, const uint64_t *count_dev,
                                    int64_t n_unique, uint32_t *perm_dev);
 
+/* ---- (f-2) three more loop bodies on the same slabs ------------------------------------------------------------------
+ * fxg_validate_*: the reader's checks alone (fastx.c:45-54,118-135,361-362) — all fastx_trimmer needs, its body being
+ *                 pointer arithmetic (src/fastx_trimmer/fastx_trimmer.c:120-148).  Result: report.first_bad_read.
+ * fxg_mask_*:     fastq_masker body (src/fastq_masker/fastq_masker.c:92-107): bases with q < min_quality become
+ *                 mask_char; masked_flag[i] = 1 iff read i had one; report.n_out = masked reads, aux[0] = masked bases.
+ * fxg_artifacts_*: fastx_artifacts_filter decision (src/fastx_artifacts_filter/fastx_artifacts_filter.c:56-114):
+ *                 keep[i] = 0 iff one of A,C,G,T makes up at least len-3 bases; report.n_out = kept reads. */
+int fxg_validate_dev (fxg_ctx *ctx, const fxg_batch *b, int q_offset, int64_t index_base);
+int fxg_validate_host(fxg_ctx *ctx, const fxg_batch *b, int q_offset, fxg_report *report);
+int fxg_mask_dev (fxg_ctx *ctx, const fxg_batch *b, int q_offset, int min_quality, int mask_char, uint8_t *out_seq_dev,
+                  uint8_t *masked_flag_dev, int64_t index_base);
+int fxg_mask_host(fxg_ctx *ctx, const fxg_batch *b, int q_offset, int min_quality, int mask_char, uint8_t *out_seq_host,
+                  uint8_t *masked_flag_host, fxg_report *report);
+int fxg_artifacts_dev (fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint8_t *keep_dev, int64_t index_base);
+int fxg_artifacts_host(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint8_t *keep_host, fxg_report *report);
+
 /* ---- next to the loop: FASTQ text in, FASTQ text out, parsed / packed / emitted on the GPU --------
  * fxg_text_run_host(): `text_host` holds raw 4-line FASTQ (any number of bytes; an incomplete trailing record is left
  * alone, see consumed_bytes).  The GPU indexes the lines (fastx.c:324-378 fgets/chomp), checks the record structure

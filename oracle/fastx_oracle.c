@@ -664,3 +664,69 @@ int fxo_collapser_print_path(fxo_collapser *c, const char *path)
     fclose(f);
     return 0;
 }
+
+/* ------------------------------------------------------------------ (f-2) rows ---------------- */
+
+/* src/fastq_masker/fastq_masker.c:92-107 */
+void fxo_mask_batch(const uint8_t *seq, const uint8_t *qual, const int32_t *len, int uniform_len, int stride, int64_t n,
+                    int q_offset, int min_quality, int mask_char, uint8_t *out_seq, uint8_t *masked_flag,
+                    int64_t *masked_reads, int64_t *masked_bases)
+{
+    int64_t mr = 0, mb = 0;
+    for (int64_t i = 0; i < n; i++) {
+        const int L = rec_len(len, uniform_len, i);
+        const int64_t o = i * (int64_t)stride;
+        int masked = 0;
+        memset(out_seq + o, 0, (size_t)stride);
+        for (int k = 0; k < L; k++) {
+            const int q = (int)(signed char)qual[o + k] - q_offset;
+            if (q < min_quality) { out_seq[o + k] = (uint8_t)mask_char; masked = 1; mb++; }
+            else out_seq[o + k] = seq[o + k];
+        }
+        if (masked_flag) masked_flag[i] = (uint8_t)masked;
+        mr += masked;
+    }
+    if (masked_reads) *masked_reads = mr;
+    if (masked_bases) *masked_bases = mb;
+}
+
+/* src/fastx_artifacts_filter/fastx_artifacts_filter.c:56-114 */
+void fxo_artifacts_batch(const uint8_t *seq, const int32_t *len, int uniform_len, int stride, int64_t n, uint8_t *keep)
+{
+    for (int64_t i = 0; i < n; i++) {
+        const int L = rec_len(len, uniform_len, i);
+        int a = 0, c = 0, g = 0, t = 0, total = 0;
+        for (int k = 0; k < L; k++) {
+            total++;
+            switch (seq[i * (int64_t)stride + k]) {
+            case 'A': a++; break;
+            case 'C': c++; break;
+            case 'G': g++; break;
+            case 'T': t++; break;
+            default: break;   /* 'N' */
+            }
+        }
+        const int lim = total - 3;
+        keep[i] = (a >= lim || c >= lim || g >= lim || t >= lim) ? 0 : 1;
+    }
+}
+
+/* src/fastx_trimmer/fastx_trimmer.c:120-148 — pointer arithmetic only */
+int fxo_fastx_trimmer_record(int len, int first, int last, int trim_last, int min_len, int *start)
+{
+    int L = len, s0 = 0;
+    if (last != 0 && last < L) L = last;                 /* nucleotides[keep_last_base] = 0 */
+    if (first != 1) {
+        if (L < first) return -1;                        /* sequence too short - remove it */
+        s0 = first - 1;
+        L = L - first + 1;
+    }
+    if (trim_last > 0) {
+        if (L <= trim_last) return -1;
+        const int i = L - trim_last;
+        if (i < min_len) return -1;
+        L = i;
+    }
+    if (start) *start = s0;
+    return L;
+}

@@ -113,6 +113,15 @@ int64_t fxo_collapser_unique(const fxo_collapser *c);
 void fxo_collapser_order(fxo_collapser *c, int64_t *first_index, uint64_t *count);
 int fxo_collapser_print_path(fxo_collapser *c, const char *path);
 
+/* ---- (f-2) rows: fastq_masker (src/fastq_masker/fastq_masker.c:92-107), fastx_artifacts_filter
+ * (src/fastx_artifacts_filter/fastx_artifacts_filter.c:56-114), fastx_trimmer (src/fastx_trimmer/fastx_trimmer.c:120-148) */
+void fxo_mask_batch(const uint8_t *seq, const uint8_t *qual, const int32_t *len, int uniform_len, int stride, int64_t n,
+                    int q_offset, int min_quality, int mask_char, uint8_t *out_seq, uint8_t *masked_flag,
+                    int64_t *masked_reads, int64_t *masked_bases);
+void fxo_artifacts_batch(const uint8_t *seq, const int32_t *len, int uniform_len, int stride, int64_t n, uint8_t *keep);
+/* first/last: -f/-l (1-based, last 0 = none); trim_last/min_len: -t/-m.  Returns the new length (>=0) and *start, or -1 = discard */
+int fxo_fastx_trimmer_record(int len, int first, int last, int trim_last, int min_len, int *start);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,6 +65,9 @@ def oracle():
     L.fxo_adapter_cutoff_index.argtypes = [C.POINTER(FxoAlign), C.c_int, C.c_int]
     L.fxo_clip_record.argtypes = [u8p, C.c_int, C.c_int, u8p, C.c_int, C.POINTER(FxoClipOpts), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.fxo_clip_batch.argtypes = [u8p, i32p, i32p, C.c_int, C.c_int, C.c_int64, u8p, C.c_int, C.POINTER(FxoClipOpts), i32p, u8p, i32p]
+    L.fxo_mask_batch.argtypes = [u8p, u8p, i32p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, u8p, u8p, i64p, i64p]
+    L.fxo_artifacts_batch.argtypes = [u8p, i32p, C.c_int, C.c_int, C.c_int64, u8p]
+    L.fxo_fastx_trimmer_record.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
     L.fxo_hash_bytes.restype = C.c_uint64
     L.fxo_hash_bytes.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64]
     L.fxo_collapser_new.restype = C.c_void_p
@@ -126,6 +129,29 @@ def o_clip(seq, lens, widths, L, stride, adapter, opts):
     oracle().fxo_clip_batch(_p(seq, u8p), _p(lens, i32p), _p(widths, i32p), L, stride, n, _p(ad, u8p), len(adapter),
                             C.byref(opts), _p(out_len, i32p), _p(out_cls, u8p), _p(out_cut, i32p))
     return out_len, out_cls, out_cut
+
+
+def o_mask(seq, qual, lens, L, stride, Q, q, ch):
+    n = seq.shape[0]
+    out = np.zeros_like(seq)
+    flag = np.zeros(n, np.uint8)
+    mr, mb = C.c_int64(0), C.c_int64(0)
+    oracle().fxo_mask_batch(_p(seq, u8p), _p(qual, u8p), _p(lens, i32p), L, stride, n, Q, q, ch, _p(out, u8p), _p(flag, u8p),
+                            C.byref(mr), C.byref(mb))
+    return out, flag, mr.value, mb.value
+
+
+def o_artifacts(seq, lens, L, stride):
+    n = seq.shape[0]
+    keep = np.zeros(n, np.uint8)
+    oracle().fxo_artifacts_batch(_p(seq, u8p), _p(lens, i32p), L, stride, n, _p(keep, u8p))
+    return keep
+
+
+def o_fastx_trimmer(length, first, last, trim_last, min_len):
+    st = C.c_int(0)
+    nl = oracle().fxo_fastx_trimmer_record(length, first, last, trim_last, min_len, C.byref(st))
+    return nl, st.value
 
 
 def o_collapse(seq, lens, L, stride):
