@@ -92,6 +92,8 @@ __global__ void __launch_bounds__(256) k_artifact(const ExtraParams P)
         const uint8_t *srow = P.seq + (size_t)(active ? i : 0) * P.stride;
         const uint8_t *qrow = P.qual ? P.qual + (size_t)(active ? i : 0) * P.stride : NULL;
         uint32_t ca = 0, cc = 0, cg = 0, ct = 0, bad = 0;
+        uint32_t ba = 0, bc = 0, bg = 0, bt = 0;      // byte-lane partial counts (POPC is a quarter-rate pipe: avoid it)
+        int since = 0;
         for (int c = j; c * 16 < L; c += 4) {
             const int nb = L - 16 * c;
             const uint4 s4 = __ldg(reinterpret_cast<const uint4 *>(srow) + c);
@@ -107,12 +109,17 @@ __global__ void __launch_bounds__(256) k_artifact(const ExtraParams P)
                 if (qrow) bad |= qual_bad_bits(qw[w], qw[w] | HI, P.qk) & HI & m;
                 // for legal bases (all < 128): (x ^ pat) + 0x7F.. has bit7 set iff the byte differs from pat
                 const uint32_t mh = m & HI;
-                ca += __popc(~((x ^ 0x41414141u) + 0x7F7F7F7Fu) & mh);
-                cc += __popc(~((x ^ 0x43434343u) + 0x7F7F7F7Fu) & mh);
-                cg += __popc(~((x ^ 0x47474747u) + 0x7F7F7F7Fu) & mh);
-                ct += __popc(~((x ^ 0x54545454u) + 0x7F7F7F7Fu) & mh);
+                ba += (~((x ^ 0x41414141u) + 0x7F7F7F7Fu) & mh) >> 7;
+                bc += (~((x ^ 0x43434343u) + 0x7F7F7F7Fu) & mh) >> 7;
+                bg += (~((x ^ 0x47474747u) + 0x7F7F7F7Fu) & mh) >> 7;
+                bt += (~((x ^ 0x54545454u) + 0x7F7F7F7Fu) & mh) >> 7;
+            }
+            if (++since == 48) {                       // 4 words x 48 chunks = 192 < 256 per byte lane
+                ca += __dp4a(ba, ONES, 0u); cc += __dp4a(bc, ONES, 0u); cg += __dp4a(bg, ONES, 0u); ct += __dp4a(bt, ONES, 0u);
+                ba = bc = bg = bt = 0; since = 0;
             }
         }
+        ca += __dp4a(ba, ONES, 0u); cc += __dp4a(bc, ONES, 0u); cg += __dp4a(bg, ONES, 0u); ct += __dp4a(bt, ONES, 0u);
 #pragma unroll
         for (int o = 2; o > 0; o >>= 1) {
             ca += __shfl_xor_sync(0xffffffffu, ca, o); cc += __shfl_xor_sync(0xffffffffu, cc, o);

@@ -55,6 +55,14 @@ elif op == "clip":
     o = F.ClipOpts(adapter=b"AGATCGGAAGAGC", min_length=20, keep_delta=0, discard_non_clipped=0, discard_clipped=0, discard_unknown=1, min_adapter_len=0)
     ms = timed(lambda: ctx.clip_dev(b, None, 33, o, out)); bytes_ = n * (L + 4)
     print("clip: %.1f Gcells/s" % (n * L * 13 / ms / 1e6))
+elif op == "mask":
+    os_ = torch.empty_like(dseq); fl = torch.empty(n, dtype=torch.uint8, device="cuda")
+    ms = timed(lambda: ctx.mask_dev(b, 33, 20, ord("N"), os_, fl)); bytes_ = n * 3 * L
+elif op == "artifacts":
+    fl = torch.empty(n, dtype=torch.uint8, device="cuda")
+    ms = timed(lambda: ctx.artifacts_dev(b, 33, fl)); bytes_ = n * (2 * L + 1)
+elif op == "validate":
+    ms = timed(lambda: ctx.validate_dev(b, 33)); bytes_ = n * 2 * L
 elif op == "collapse":
     torch.cuda.synchronize()
     t0 = time.perf_counter()
