@@ -88,6 +88,10 @@ def lib():
         "fxg_clip_dev": (i32, [vp, BP, vp, i32, C.POINTER(ClipOpts), vp, vp, vp, i64]),
         "fxg_clip_host": (i32, [vp, BP, vp, i32, C.POINTER(ClipOpts), vp, vp, RP]),
         "fxg_hash_dev": (i32, [vp, BP, vp]),
+        "fxg_comm_init_all": (i32, [i32, C.POINTER(i32), C.POINTER(vp)]),
+        "fxg_comm_allreduce_u64": (i32, [vp, C.POINTER(vp), sz]),
+        "fxg_comm_free": (None, [vp]),
+        "fxg_comm_error": (C.c_char_p, [vp]),
         "fxg_validate_dev": (i32, [vp, BP, i32, i64]),
         "fxg_validate_host": (i32, [vp, BP, i32, RP]),
         "fxg_mask_dev": (i32, [vp, BP, i32, i32, i32, vp, vp, i64]),

@@ -76,6 +76,21 @@ int fxh_parse_cmdline(int argc, char *argv[], const char *program_options, fxh_p
 /* ------------------------------------------------------------------------------------------------
  * GPU helpers
  * ---------------------------------------------------------------------------------------------- */
+int fxh_gpu_count(void)
+{
+    const char *e = getenv("FASTX_GPUS");
+    int n = e ? atoi(e) : 1;
+    return n > 0 ? (n > 64 ? 64 : n) : 1;
+}
+
+fxg_ctx *fxh_gpu_open_dev(int dev)
+{
+    fxg_ctx *ctx = NULL;
+    int rc = fxg_init(dev, &ctx);
+    if (rc != FXG_OK) errx(1, "GPU %d unavailable: %s (%s). This build has no CPU fallback.", dev, fxg_strerror(rc), fxg_last_error(NULL));
+    return ctx;
+}
+
 fxg_ctx *fxh_gpu_open(void)
 {
     const char *e = getenv("FASTX_GPU");

@@ -516,43 +516,66 @@ static int main_stats(int argc, char **argv)
         out = fopen(fxh_output_filename(), "w+");
         if (out == NULL) err(1, "Failed to create output file (%s)", fxh_output_filename());
     }
-    fxg_ctx *ctx = fxh_gpu_open();
+    /* FASTX_GPUS=N: chunks go to the GPUs round-robin, each GPU keeps a partial histogram, and one NCCL all-reduce
+     * (fxg_comm_allreduce_u64) merges them before printing — the only collective this tool needs. */
+    const int ngpu = fxh_gpu_count();
+    const int dev0 = getenv("FASTX_GPU") ? atoi(getenv("FASTX_GPU")) : 0;
+    fxg_ctx *ctxs[64]; uint64_t *hists[64]; fxg_text *txs[64]; int devs[64];
     const int max_cycles = FXH_MAX_LINE;
     const size_t hist_bytes = (size_t)max_cycles * 5 * FXG_QBINS * sizeof(uint64_t);
-    uint64_t *d_hist = (uint64_t *)fxg_alloc_device(ctx, hist_bytes);
-    if (!d_hist) errx(1, "cannot allocate the histogram on the GPU: %s", fxg_last_error(ctx));
-    fxh_gpu_check(ctx, fxg_memset_dev(ctx, d_hist, 0, hist_bytes), "fxg_memset_dev");
-    fxh_gpu_check(ctx, fxg_sync(ctx), "fxg_sync");
-    int maxlen = 0;
+    for (int g = 0; g < ngpu; g++) {
+        devs[g] = dev0 + g;
+        ctxs[g] = fxh_gpu_open_dev(devs[g]);
+        hists[g] = (uint64_t *)fxg_alloc_device(ctxs[g], hist_bytes);
+        if (!hists[g]) errx(1, "cannot allocate the histogram on GPU %d: %s", devs[g], fxg_last_error(ctxs[g]));
+        fxh_gpu_check(ctxs[g], fxg_memset_dev(ctxs[g], hists[g], 0, hist_bytes), "fxg_memset_dev");
+        fxh_gpu_check(ctxs[g], fxg_sync(ctxs[g]), "fxg_sync");
+        txs[g] = NULL;
+    }
+    fxg_ctx *ctx = ctxs[0];
+    uint64_t *d_hist = hists[0];
+    int maxlen = 0, turn = 0;
     fxh_batch *b;
     if (fastq && fxh_text_path_enabled()) {        /* GPU text path: parse + pack + accumulate on the device */
         char *p;
         size_t len = fxh_reader_raw(rd, &p);
         size_t cap = (size_t)64 << 20;
         if (fxh_reader_at_eof(rd) && len + 4096 < cap) cap = len + 4096;
-        fxg_text *tx = NULL;
-        if (len > 0 && fxg_text_new(ctx, getenv("FASTX_GPU") ? atoi(getenv("FASTX_GPU")) : 0, cap, &tx) == FXG_OK) {
+        int ok = len > 0;
+        for (int g = 0; ok && g < ngpu; g++) ok = fxg_text_new(ctxs[g], devs[g], cap, &txs[g]) == FXG_OK;
+        if (ok) {
             fxh_reader_pin(rd);
             for (;;) {
                 len = fxh_reader_raw(rd, &p);
                 if (len == 0) break;
                 if (len > cap) len = cap;
                 fxg_text_report rep;
-                int rc = fxg_text_stats_host(tx, p, len, fxh_q_offset(), d_hist, max_cycles, &rep);
-                if (rc != FXG_OK) errx(1, "fxg_text_stats_host failed: %s (%s)", fxg_strerror(rc), fxg_text_error(tx));
+                const int g = turn % ngpu;
+                int rc = fxg_text_stats_host(txs[g], p, len, fxh_q_offset(), hists[g], max_cycles, &rep);
+                if (rc != FXG_OK) errx(1, "fxg_text_stats_host failed: %s (%s)", fxg_strerror(rc), fxg_text_error(txs[g]));
                 if (rep.anomaly != 0 || rep.n_records == 0) break;   /* numeric qualities / broken input: host parser from here */
                 if (rep.max_len > maxlen) maxlen = rep.max_len;
                 fxh_reader_consume(rd, (size_t)rep.consumed_bytes, rep.n_records);
+                turn++;
             }
-            fxg_text_free(tx);
         }
+        for (int g = 0; g < ngpu; g++) if (txs[g]) fxg_text_free(txs[g]);
     }
     while ((b = fxh_reader_next(rd, fxh_batch_reads())) != NULL) {
         fxg_batch gb = fxh_as_fxg_batch(b, fastq);
         fxg_report rep;
-        fxh_gpu_check(ctx, fxg_stats_accum_host(ctx, &gb, batch_q(b), d_hist, max_cycles, fastq ? NULL : b->weight, &rep), "fxg_stats_accum_host");
+        const int g = turn++ % ngpu;
+        fxh_gpu_check(ctxs[g], fxg_stats_accum_host(ctxs[g], &gb, batch_q(b), hists[g], max_cycles, fastq ? NULL : b->weight, &rep), "fxg_stats_accum_host");
         if (rep.first_bad_read >= 0) fxh_die_bad_record(rd, b, rep.first_bad_read);
         for (int64_t i = 0; i < b->n; i++) if (b->len[i] > maxlen) maxlen = b->len[i];
+    }
+    if (ngpu > 1 && maxlen > 0) {
+        fxg_comm *comm = NULL;
+        int rc = fxg_comm_init_all(ngpu, devs, &comm);
+        if (rc != FXG_OK) errx(1, "fxg_comm_init_all failed: %s (%s)", fxg_strerror(rc), fxg_comm_error(NULL));
+        rc = fxg_comm_allreduce_u64(comm, hists, (size_t)maxlen * 5 * FXG_QBINS);
+        if (rc != FXG_OK) errx(1, "fxg_comm_allreduce_u64 failed: %s (%s)", fxg_strerror(rc), fxg_comm_error(comm));
+        fxg_comm_free(comm);
     }
     const size_t cyc_words = (size_t)5 * FXG_QBINS;
     uint64_t *hist = (uint64_t *)calloc((size_t)(maxlen + 1) * cyc_words, sizeof(uint64_t));
@@ -600,8 +623,7 @@ static int main_stats(int argc, char **argv)
         }
     }
     if (out != stdout) fclose(out); else fflush(out);
-    fxg_free_device(ctx, d_hist);
-    fxg_destroy(ctx);
+    for (int g = 0; g < ngpu; g++) { fxg_free_device(ctxs[g], hists[g]); fxg_destroy(ctxs[g]); }
     return 0;
 }
 

@@ -176,6 +176,16 @@ int64_t     fxg_collapse_launches(const fxg_collapser *c);
 int         fxg_collapse_order_dev(int device, const uint64_t *hash_dev, const uint64_t *first_dev, const uint64_t *count_dev,
                                    int64_t n_unique, uint32_t *perm_dev);
 
+/* ---- the one native collective: all-reduce of the quality-stats histograms ------------------------
+ * One process driving several GPUs (the drop-in tools with FASTX_GPUS=N): ncclCommInitAll over `devices`, then an
+ * in-place ncclSum/ncclUint64 all-reduce of one buffer per device.  NCCL is dlopen()ed at the first call.
+ * (Multi-process jobs — torchrun — all-reduce the same buffers with their own communicator.) */
+typedef struct fxg_comm fxg_comm;
+int         fxg_comm_init_all(int ndev, const int *devices, fxg_comm **out);
+int         fxg_comm_allreduce_u64(fxg_comm *c, uint64_t *const *bufs_dev, size_t count);
+void        fxg_comm_free(fxg_comm *c);
+const char *fxg_comm_error(const fxg_comm *c);
+
 /* ---- (f-2) three more loop bodies on the same slabs ------------------------------------------------------------------
  * fxg_validate_*: the reader's checks alone (fastx.c:45-54,118-135,361-362) — all fastx_trimmer needs, its body being
  *                 pointer arithmetic (src/fastx_trimmer/fastx_trimmer.c:120-148).  Result: report.first_bad_read.

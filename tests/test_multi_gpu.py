@@ -20,3 +20,40 @@ def test_two_rank_nccl_stats_allreduce_and_collapser_exchange():
                        env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
     assert r.returncode == 0, r.stdout.decode()[-2000:]
     assert b"collapser U=" in r.stdout and b"MISMATCH" not in r.stdout
+
+
+def test_native_nccl_allreduce_and_multi_gpu_stats_tool(tmp_path):
+    """fxg_comm_allreduce_u64 (NCCL from C, one process driving 2 GPUs) and fastx_quality_stats with FASTX_GPUS=2."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import ctypes as C
+    import numpy as np
+    import fastx_toolkit_b200 as F
+    L = F.lib()
+    devs = (C.c_int * 2)(0, 1)
+    comm = C.c_void_p()
+    assert L.fxg_comm_init_all(2, devs, C.byref(comm)) == 0, L.fxg_comm_error(None)
+    a = torch.arange(0, 1000, dtype=torch.int64, device="cuda:0")
+    b = torch.arange(0, 1000, dtype=torch.int64, device="cuda:1") * 3
+    bufs = (C.c_void_p * 2)(a.data_ptr(), b.data_ptr())
+    torch.cuda.synchronize(0); torch.cuda.synchronize(1)
+    assert L.fxg_comm_allreduce_u64(comm, bufs, 1000) == 0, L.fxg_comm_error(comm)
+    exp = np.arange(1000, dtype=np.int64) * 4
+    assert np.array_equal(a.cpu().numpy(), exp) and np.array_equal(b.cpu().numpy(), exp)
+    L.fxg_comm_free(comm)
+
+    if H.ref_tool("fastx_quality_stats") is None:
+        pytest.skip("oracle/_ref not built")
+    from test_tools_cli import BIN, run_tool
+    fq = str(tmp_path / "in.fq")
+    seq, qual = H.synth_slab(H.SEED_BASE + 17, 600000, 150, H.WITH_N)       # > 64 MB of text: several chunks
+    H.write_fastq(fq, seq, qual, None, 150)
+    ref = run_tool(H.ref_tool("fastx_quality_stats"), ["-N", "-i", fq])
+    env = dict(os.environ, FASTX_GPUS="2")
+    r = subprocess.run([os.path.join(BIN, "fastx_quality_stats"), "-N", "-i", fq], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert (r.returncode, r.stdout) == (ref[0], ref[1]), r.stderr.decode()[-500:]
+    env["FASTX_TEXT_PATH"] = "0"
+    env["FASTX_BATCH_READS"] = "100000"
+    r = subprocess.run([os.path.join(BIN, "fastx_quality_stats"), "-i", fq], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    ref = run_tool(H.ref_tool("fastx_quality_stats"), ["-i", fq])
+    assert (r.returncode, r.stdout) == (ref[0], ref[1]), r.stderr.decode()[-500:]
