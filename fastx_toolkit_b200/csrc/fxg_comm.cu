@@ -51,6 +51,8 @@ extern "C" int fxg_comm_init_all(int ndev, const int *devices, fxg_comm **out)
     c->comms = (ncclComm_t *)calloc(ndev, sizeof(ncclComm_t));
     c->streams = (cudaStream_t *)calloc(ndev, sizeof(cudaStream_t));
     memcpy(c->devices, devices, sizeof(int) * ndev);
+    // the drop-in tools write their DATA to stdout: NCCL's version banner / debug log must never land there
+    setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
     c->lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
     if (!c->lib) { snprintf(g_comm_err, sizeof g_comm_err, "dlopen(libnccl.so.2): %s", dlerror()); fxg_comm_free(c); return FXG_ERR_NCCL; }
     *(void **)&c->CommInitAll = dlsym(c->lib, "ncclCommInitAll");
