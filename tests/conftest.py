@@ -11,3 +11,12 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+def pytest_sessionstart(session):
+    """Build what the tests load (libfxg.so, bin/ tools, the oracle) when a fresh checkout has not been built yet."""
+    import subprocess
+    need = [os.path.join(ROOT, "fastx_toolkit_b200", "libfxg.so"), os.path.join(ROOT, "bin", "fastx_b200"),
+            os.path.join(ROOT, "oracle", "libfastx_oracle.so")]
+    if not all(os.path.exists(p) for p in need):
+        subprocess.check_call(["make", "-C", ROOT, "lib", "tools", "oracle"], stdout=subprocess.DEVNULL)
