@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include "fxg.h"
 
@@ -66,7 +67,14 @@ extern "C" int fxg_comm_init_all(int ndev, const int *devices, fxg_comm **out)
         fxg_comm_free(c);
         return FXG_ERR_NCCL;
     }
+    // NCCL prints its version banner with printf() when NCCL_DEBUG=VERSION/WARN (this image exports NCCL_DEBUG=VERSION):
+    // point fd 1 at stderr while the communicators are created, then restore it.
+    fflush(stdout);
+    const int saved_stdout = dup(STDOUT_FILENO);
+    if (saved_stdout >= 0) dup2(STDERR_FILENO, STDOUT_FILENO);
     ncclResult_t r = c->CommInitAll(c->comms, ndev, devices);
+    fflush(stdout);
+    if (saved_stdout >= 0) { dup2(saved_stdout, STDOUT_FILENO); close(saved_stdout); }
     if (r != ncclSuccess) {
         snprintf(g_comm_err, sizeof g_comm_err, "ncclCommInitAll: %s", c->GetErrorString ? c->GetErrorString(r) : "error");
         fxg_comm_free(c);
