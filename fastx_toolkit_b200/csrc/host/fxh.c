@@ -148,7 +148,7 @@ static void refill(fxh_reader *r, size_t keep_from)
     /* move the unparsed tail to the front, then read more */
     size_t tail = r->len - keep_from;
     if (keep_from > 0) { memmove(r->buf, r->buf + keep_from, tail); r->len = tail; r->pos -= keep_from; }
-    if (r->len + (1u << 20) > r->cap) {
+    if (r->len + 4096 > r->cap) {               /* one record larger than the window: grow it */
         size_t ncap = r->cap * 2;
         char *nb = (char *)realloc(r->buf, ncap + 1);
         if (!nb) err(1, "out of memory (input buffer)");
@@ -176,6 +176,10 @@ fxh_reader *fxh_reader_open(const char *filename, int allowed, int q_offset, int
     r->q_offset = q_offset;
     r->stale_rows = stale_rows;
     r->cap = (size_t)256 << 20;
+    if (getenv("FASTX_WINDOW_BYTES")) {         /* testing knob: small windows exercise the refill / carry-over logic */
+        long long v = atoll(getenv("FASTX_WINDOW_BYTES"));
+        if (v >= 65536) r->cap = (size_t)v;
+    }
     {   /* a regular file smaller than the default window needs no more than its own size */
         struct stat sb;
         if (r->fd != STDIN_FILENO && fstat(r->fd, &sb) == 0 && S_ISREG(sb.st_mode) && (size_t)sb.st_size + (2u << 20) < r->cap)
@@ -444,6 +448,13 @@ double fxh_now(void)
     return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 int fxh_reader_at_eof(const fxh_reader *r) { return r->eof; }
+
+size_t fxh_text_chunk_bytes(void)
+{
+    const char *e = getenv("FASTX_CHUNK_BYTES");       /* testing knob; default 64 MB per GPU text chunk */
+    long long v = e ? atoll(e) : 0;
+    return v >= 16384 ? (size_t)v : ((size_t)64 << 20);
+}
 
 int fxh_text_path_enabled(void)
 {

@@ -72,6 +72,7 @@ void        fxh_reader_consume(fxh_reader *r, size_t bytes, int64_t records);   
 void        fxh_reader_pin(fxh_reader *r);                                 /* page-lock the text buffer for DMA        */
 int         fxh_reader_at_eof(const fxh_reader *r);
 int         fxh_text_path_enabled(void);                                   /* FASTX_TEXT_PATH=0 disables it            */
+size_t      fxh_text_chunk_bytes(void);                                    /* FASTX_CHUNK_BYTES (default 64 MB)        */
 
 /* ---- writer ---- */
 typedef struct fxh_writer fxh_writer;

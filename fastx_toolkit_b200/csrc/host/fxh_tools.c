@@ -48,7 +48,7 @@ static void text_fast_path(fxg_ctx *ctx, fxh_reader *rd, fxh_writer *wr, int op,
     char *p;
     size_t len = fxh_reader_raw(rd, &p);
     if (len == 0) return;
-    size_t cap = (size_t)64 << 20;             /* chunk size: small enough to overlap, large enough for PCIe */
+    size_t cap = fxh_text_chunk_bytes();       /* chunk size: small enough to overlap, large enough for PCIe */
     if (fxh_reader_at_eof(rd) && len + 4096 < cap) cap = len + 4096;
     fxg_text *tx = NULL;
     const int dev = getenv("FASTX_GPU") ? atoi(getenv("FASTX_GPU")) : 0;
@@ -539,7 +539,7 @@ static int main_stats(int argc, char **argv)
     if (fastq && fxh_text_path_enabled()) {        /* GPU text path: parse + pack + accumulate on the device */
         char *p;
         size_t len = fxh_reader_raw(rd, &p);
-        size_t cap = (size_t)64 << 20;
+        size_t cap = fxh_text_chunk_bytes();
         if (fxh_reader_at_eof(rd) && len + 4096 < cap) cap = len + 4096;
         int ok = len > 0;
         for (int g = 0; ok && g < ngpu; g++) ok = fxg_text_new(ctxs[g], devs[g], cap, &txs[g]) == FXG_OK;

@@ -127,6 +127,33 @@ def test_trim_filter_revcomp_stats_binaries(tmp_path, L, kind, ragged, crlf):
 
 @gpu
 @needs_ref
+def test_small_windows_and_chunks(tmp_path):
+    """tiny reader window + tiny GPU text chunks: records straddle every boundary; output must not change"""
+    fq = str(tmp_path / "in.fq")
+    synth_fastq(fq, 40000, 100, H.WITH_N, np.random.default_rng(5))
+    fa = str(tmp_path / "in.fa")
+    seq, _ = H.synth_slab(H.SEED_BASE + 4, 40000, 60, H.DUPS)
+    H.write_fasta(fa, seq, None, 60)
+    env_sets = [dict(FASTX_WINDOW_BYTES="70000", FASTX_CHUNK_BYTES="20000"), dict(FASTX_WINDOW_BYTES="300000", FASTX_CHUNK_BYTES="100000"),
+                dict(FASTX_WINDOW_BYTES="70000", FASTX_TEXT_PATH="0", FASTX_BATCH_READS="777")]
+    for env in env_sets:
+        os.environ.update(env)
+        try:
+            assert_same("fastq_quality_trimmer", ["-t", "25", "-l", "30", "-v", "-i", fq])
+            assert_same("fastq_quality_filter", ["-q", "20", "-p", "80", "-v", "-i", fq])
+            assert_same("fastx_reverse_complement", ["-i", fq])
+            assert_same("fastx_quality_stats", ["-i", fq])
+            assert_same("fastx_clipper", ["-a", "AGATCGGAAGAGC", "-l", "10", "-n", "-v", "-i", fq])
+            assert_same("fastx_collapser", ["-v", "-i", fa])
+            assert_same("fastx_reverse_complement", ["-i", fa])
+            assert_same("fastq_quality_trimmer", ["-t", "25"], stdin=open(fq, "rb").read())
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+
+
+@gpu
+@needs_ref
 def test_output_file_report_stream_and_gzip(tmp_path):
     fq = str(tmp_path / "in.fq")
     synth_fastq(fq, 5000, 100, H.PLAIN)
