@@ -31,7 +31,8 @@ class ClipOpts(C.Structure):
 class TextReport(C.Structure):
     """struct fxg_text_report"""
     _fields_ = [("n_records", C.c_int64), ("n_out_records", C.c_int64), ("consumed_bytes", C.c_int64), ("out_bytes", C.c_int64),
-                ("max_len", C.c_int32), ("anomaly", C.c_int32), ("anomaly_record", C.c_int64)]
+                ("max_len", C.c_int32), ("anomaly", C.c_int32), ("anomaly_record", C.c_int64),
+                ("min_len", C.c_int32), ("reserved", C.c_int32), ("clip_class", C.c_int64 * 6)]
 
 
 class Report(C.Structure):
@@ -101,6 +102,7 @@ def lib():
         "fxg_text_new": (i32, [vp, i32, sz, C.POINTER(vp)]),
         "fxg_text_free": (None, [vp]),
         "fxg_text_run_host": (i32, [vp, i32, vp, sz, i32, i32, i32, vp, C.POINTER(TextReport)]),
+        "fxg_text_clip_host": (i32, [vp, vp, sz, i32, C.POINTER(ClipOpts), i32, i32, vp, C.POINTER(TextReport)]),
         "fxg_text_stats_host": (i32, [vp, vp, sz, i32, vp, C.c_int32, C.POINTER(TextReport)]),
         "fxg_text_error": (C.c_char_p, [vp]),
         "fxg_text_launches": (i64, [vp]),
@@ -190,6 +192,18 @@ class TextPipe:
         out = np.empty(self.cap + self.cap // 4 + 64, np.uint8)
         rep = TextReport()
         rc = self.L.fxg_text_run_host(self.h, op, src.ctypes.data, src.size, q_offset, a0, a1, out.ctypes.data, C.byref(rep))
+        if rc != FXG_OK:
+            raise FxgError(rc, self.L.fxg_text_error(self.h).decode())
+        return out[: rep.out_bytes].tobytes(), rep
+
+    def clip(self, text, q_offset, opts, show_adapter_only=0, expect_len=0):
+        """fxg_text_clip_host: fastx_clipper on a chunk of equal-length reads.  Returns (output bytes, TextReport)."""
+        import numpy as np
+        src = np.frombuffer(text, np.uint8) if isinstance(text, (bytes, bytearray)) else text
+        out = np.empty(self.cap + self.cap // 4 + 64, np.uint8)
+        rep = TextReport()
+        rc = self.L.fxg_text_clip_host(self.h, src.ctypes.data, src.size, q_offset, C.byref(opts), show_adapter_only, expect_len,
+                                       out.ctypes.data, C.byref(rep))
         if rc != FXG_OK:
             raise FxgError(rc, self.L.fxg_text_error(self.h).decode())
         return out[: rep.out_bytes].tobytes(), rep

@@ -560,6 +560,15 @@ extern "C" int fxg_internal_revcomp_on_stream(fxg_ctx *ctx, const fxg_batch *b, 
     CK(ctx, cudaSetDevice(ctx->device));
     return revcomp_enqueue(ctx, b, q_offset, oseq, oqual, 0, (cudaStream_t)stream);
 }
+extern "C" int fxg_internal_clip_on_stream(fxg_ctx *ctx, const fxg_batch *b, int q_offset, const fxg_clip_opts *o, int32_t *out_len,
+                                           uint8_t *out_class, void *stream)
+{
+    int rc = check_batch(ctx, b, true, false, q_offset);
+    if (rc) return rc;
+    if ((rc = check_clip_opts(ctx, o))) return rc;
+    CK(ctx, cudaSetDevice(ctx->device));
+    return clip_enqueue(ctx, b, NULL, q_offset, o, out_len, out_class, NULL, 0, (cudaStream_t)stream);
+}
 extern "C" int fxg_internal_stats_on_stream(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint64_t *hist, int32_t max_cycles, void *stream)
 {
     int rc = check_batch(ctx, b, true, false, q_offset);

@@ -81,9 +81,9 @@ struct RecTable {
 enum { AN_NONE = 0, AN_PREFIX = 1, AN_EMPTY_SEQ = 2, AN_QUAL_LEN = 3, AN_LONG_LINE = 4, AN_BAD_RECORD = 5, AN_LINE_COUNT = 6 };
 
 __global__ void __launch_bounds__(256) k_recs(const uint8_t *text, const uint32_t *line_end, uint32_t n_rec, RecTable rt,
-                                              int32_t *seq_len, unsigned long long *anomaly /* [0]=min record, */, int *max_len)
+                                              int32_t *seq_len, unsigned long long *anomaly /* [0]=min record, */, int *max_len, int *min_len)
 {
-    int local_max = 0;
+    int local_max = 0, local_min = 0x7FFFFFFF;
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += gridDim.x * blockDim.x) {
         uint32_t st[4], ln[4];
 #pragma unroll
@@ -104,9 +104,12 @@ __global__ void __launch_bounds__(256) k_recs(const uint8_t *text, const uint32_
         if (an != AN_NONE) atomicMin(anomaly, ((unsigned long long)r << 8) | (unsigned long long)an);
         seq_len[r] = (int32_t)ln[1];
         if ((int)ln[1] > local_max && an == AN_NONE) local_max = (int)ln[1];
+        if ((int)ln[1] < local_min && an == AN_NONE) local_min = (int)ln[1];
     }
     local_max = __reduce_max_sync(0xffffffffu, local_max);
     if ((threadIdx.x & 31) == 0 && local_max > 0) atomicMax(max_len, local_max);
+    local_min = __reduce_min_sync(0xffffffffu, local_min);
+    if ((threadIdx.x & 31) == 0 && local_min != 0x7FFFFFFF) atomicMin(min_len, local_min);
 }
 
 // ---- K-PACK: one thread per 16-byte destination chunk (both rows) ---------------------------------------------
@@ -196,6 +199,19 @@ __global__ void __launch_bounds__(256) k_emit(const uint8_t *text, RecTable rt, 
     }
 }
 
+// clipper: what the tool emits per record (fastx_clipper.cpp:280-319): normally the WRITE class at its clipped length;
+// with -k only the adapter-only reads, untruncated
+__global__ void k_clip_emit_len(const int32_t *clip_len, const uint8_t *cls, const int32_t *seq_len, uint32_t n_rec, int show_adapter_only,
+                                int32_t *emit_len)
+{
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += gridDim.x * blockDim.x) {
+        int e = -1;
+        if (show_adapter_only) { if (cls[r] == FXG_CLIP_ADAPTER_ONLY) e = seq_len[r]; }
+        else if (cls[r] == FXG_CLIP_WRITE) e = clip_len[r];
+        emit_len[r] = e;
+    }
+}
+
 __global__ void k_count_kept(const int32_t *out_len, const uint8_t *keep_flags, uint32_t n_rec, unsigned long long *kept)
 {
     unsigned c = 0;
@@ -214,6 +230,8 @@ extern "C" int fxg_internal_scan_on_stream(fxg_ctx *ctx, int mode, const fxg_bat
                                            int min_percent, void *out, void *stream);
 extern "C" void *fxg_internal_counters(fxg_ctx *ctx);
 extern "C" int fxg_internal_revcomp_on_stream(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint8_t *oseq, uint8_t *oqual, void *stream);
+extern "C" int fxg_internal_clip_on_stream(fxg_ctx *ctx, const fxg_batch *b, int q_offset, const fxg_clip_opts *o, int32_t *out_len,
+                                           uint8_t *out_class, void *stream);
 extern "C" int fxg_internal_stats_on_stream(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint64_t *hist, int32_t max_cycles, void *stream);
 
 struct fxg_text {
@@ -275,7 +293,7 @@ extern "C" int fxg_text_new(fxg_ctx *ctx, int device, size_t max_chunk_bytes, fx
     bool ok = cudaStreamCreateWithFlags(&t->st, cudaStreamNonBlocking) == cudaSuccess &&
               cudaMalloc(&t->d_text, max_chunk_bytes + 64) == cudaSuccess && cudaMalloc(&t->d_out, max_chunk_bytes + max_chunk_bytes / 4 + 64) == cudaSuccess &&
               cudaMalloc(&t->d_cnt, (nthr + 1) * 4) == cudaSuccess && cudaMalloc(&t->d_scan, (nthr + 1) * 4) == cudaSuccess &&
-              cudaMalloc(&t->d_scalars, 64) == cudaSuccess && cudaMallocHost(&t->h_scalars, 64) == cudaSuccess;
+              cudaMalloc(&t->d_scalars, 64) == cudaSuccess && cudaMallocHost(&t->h_scalars, 128) == cudaSuccess;
     if (ok) {
         size_t need = 0, best = 0;
         cub::DeviceScan::ExclusiveSum(NULL, need, t->d_cnt, t->d_scan, (int)nthr + 1, t->st); best = need;
@@ -301,10 +319,13 @@ static int ensure(fxg_text *t, void **p, size_t *cap, size_t need_elems, size_t 
 
 // op: 0 = trim (a0 = threshold, a1 = min_len), 1 = filter (a0 = min_quality, a1 = min_percent), 2 = reverse complement,
 //     3 = quality-stats accumulation into hist_dev (no text output)
+//     4 = fastx_clipper on a chunk whose reads all have the same length (clip != NULL; a0 = -k flag, a1 = the running
+//         maximum read length seen by the caller so far, 0 = none yet)
 static int text_run(fxg_text *t, int op, const char *text_host, size_t bytes, int q_offset, int a0, int a1,
-                    char *out_host, uint64_t *hist_dev, int32_t max_cycles, fxg_text_report *rep)
+                    char *out_host, uint64_t *hist_dev, int32_t max_cycles, const fxg_clip_opts *clip, fxg_text_report *rep)
 {
-    if (!t || !text_host || !rep || bytes > t->cap_bytes || op < 0 || op > 3 || (op != 3 && !out_host) || (op == 3 && !hist_dev)) return FXG_ERR_ARG;
+    if (!t || !text_host || !rep || bytes > t->cap_bytes || op < 0 || op > 4 || (op != 3 && !out_host) || (op == 3 && !hist_dev) ||
+        (op == 4 && !clip)) return FXG_ERR_ARG;
     memset(rep, 0, sizeof(*rep));
     rep->anomaly_record = -1;
     if (bytes == 0) return FXG_OK;
@@ -336,10 +357,10 @@ static int text_run(fxg_text *t, int op, const char *text_host, size_t bytes, in
         t->cap_recs = n_rec;
     }
     k_nl_scatter<<<tgrid(nthr), 256, 0, st>>>(t->d_text, bytes, t->d_scan, t->d_line_end, nthr);
-    t->h_scalars[0] = ~0ull; t->h_scalars[1] = 0; t->h_scalars[2] = 0; t->h_scalars[3] = 0;
+    t->h_scalars[0] = ~0ull; t->h_scalars[1] = 0; t->h_scalars[2] = 0; t->h_scalars[3] = 0x7FFFFFFFull;
     CKT(t, cudaMemcpyAsync(t->d_scalars, t->h_scalars, 32, cudaMemcpyHostToDevice, st));
     RecTable rt = { t->d_start, t->d_llen };
-    k_recs<<<tgrid(n_rec), 256, 0, st>>>(t->d_text, t->d_line_end, n_rec, rt, t->d_seq_len, t->d_scalars, (int *)(t->d_scalars + 2));
+    k_recs<<<tgrid(n_rec), 256, 0, st>>>(t->d_text, t->d_line_end, n_rec, rt, t->d_seq_len, t->d_scalars, (int *)(t->d_scalars + 2), (int *)(t->d_scalars + 3));
     CKT(t, cudaMemcpyAsync(t->h_scalars, t->d_scalars, 32, cudaMemcpyDeviceToHost, st));
     // bytes consumed = end of the last complete record
     uint32_t last_end = 0;
@@ -354,6 +375,14 @@ static int text_run(fxg_text *t, int op, const char *text_host, size_t bytes, in
     }
     const int max_len = (int)*(int *)(t->h_scalars + 2);
     rep->max_len = max_len;
+    rep->min_len = (int)*(int *)(t->h_scalars + 3);
+    if (op == 4 && (rep->min_len != max_len || (a1 > 0 && max_len != a1))) {
+        // mixed read lengths: the reference's aligner then reads stale bytes of earlier reads —
+        // only the host packer reproduces that; hand the chunk back
+        rep->anomaly = AN_LINE_COUNT + 1;     /* FXG_TEXT_MIXED_LEN */
+        rep->anomaly_record = 0;
+        return FXG_OK;
+    }
     const int stride = (max_len + 15) & ~15;
     { size_t need_slab = (size_t)n_rec * stride; if (t->cap_slab < need_slab) {
         size_t c = 0; if ((rc = ensure(t, (void **)&t->d_seq, &c, need_slab, 1))) return rc;
@@ -377,6 +406,15 @@ static int text_run(fxg_text *t, int op, const char *text_host, size_t bytes, in
         }
         rc = fxg_internal_revcomp_on_stream(t->ctx, &b, q_offset, t->d_oseq, t->d_oqual, (void *)st);
         alt_seq = t->d_oseq; alt_qual = t->d_oqual;
+    } else if (op == 4) {
+        // K-CLIP writes its lengths into the sizes scratch (int32 view) and classes into d_keep; emit lengths -> d_out_len
+        int32_t *clip_len = reinterpret_cast<int32_t *>(t->d_sizes);
+        b.len = NULL; b.uniform_len = max_len;      // equal lengths: the narrow (uniform) K-CLIP instantiation
+        rc = fxg_internal_clip_on_stream(t->ctx, &b, q_offset, clip, clip_len, t->d_keep, (void *)st);
+        if (!rc) {
+            k_clip_emit_len<<<tgrid(n_rec), 256, 0, st>>>(clip_len, t->d_keep, t->d_seq_len, n_rec, a0, t->d_out_len);
+            t->launches++;
+        }
     } else {
         rc = fxg_internal_stats_on_stream(t->ctx, &b, q_offset, hist_dev, max_cycles, (void *)st);
     }
@@ -390,7 +428,7 @@ static int text_run(fxg_text *t, int op, const char *text_host, size_t bytes, in
         if (t->h_scalars[5] != ~0ull) { rep->anomaly = AN_BAD_RECORD; rep->anomaly_record = (int64_t)t->h_scalars[5]; }
         return FXG_OK;
     }
-    const int32_t *ol = op == 0 ? t->d_out_len : (op == 2 ? t->d_seq_len : NULL);     // revcomp keeps every read at full length
+    const int32_t *ol = (op == 0 || op == 4) ? t->d_out_len : (op == 2 ? t->d_seq_len : NULL);   // revcomp keeps every read at full length
     const uint8_t *kf = op == 1 ? t->d_keep : NULL;
     k_emit_sizes<<<tgrid(n_rec), 256, 0, st>>>(rt, n_rec, ol, kf, t->d_sizes);
     CKT(t, cudaMemsetAsync(t->d_sizes + n_rec, 0, 8, st));
@@ -401,9 +439,10 @@ static int text_run(fxg_text *t, int op, const char *text_host, size_t bytes, in
     uint64_t out_bytes = 0;
     CKT(t, cudaMemcpyAsync(&out_bytes, t->d_offs + n_rec, 8, cudaMemcpyDeviceToHost, st));
     CKT(t, cudaMemcpyAsync(t->h_scalars, t->d_scalars, 32, cudaMemcpyDeviceToHost, st));
-    CKT(t, cudaMemcpyAsync(t->h_scalars + 4, (unsigned long long *)fxg_internal_counters(t->ctx), 16, cudaMemcpyDeviceToHost, st));
+    CKT(t, cudaMemcpyAsync(t->h_scalars + 4, (unsigned long long *)fxg_internal_counters(t->ctx), 64, cudaMemcpyDeviceToHost, st));
     CKT(t, cudaStreamSynchronize(st));
     t->launches += 5;
+    if (op == 4) for (int k = 0; k < 6; k++) rep->clip_class[k] = (int64_t)t->h_scalars[4 + (k == 0 ? 0 : 2 + k)];   // CNT_OUT, CNT_AUX0+k
     if (t->h_scalars[5] != ~0ull) {          // the op kernel found an illegal base / quality: host path decides
         rep->anomaly = AN_BAD_RECORD;
         rep->anomaly_record = (int64_t)t->h_scalars[5];
@@ -422,11 +461,17 @@ extern "C" int fxg_text_run_host(fxg_text *t, int op, const char *text_host, siz
                                  char *out_host, fxg_text_report *rep)
 {
     if (op < 0 || op > 2) return FXG_ERR_ARG;
-    return text_run(t, op, text_host, bytes, q_offset, a0, a1, out_host, NULL, 0, rep);
+    return text_run(t, op, text_host, bytes, q_offset, a0, a1, out_host, NULL, 0, NULL, rep);
+}
+
+extern "C" int fxg_text_clip_host(fxg_text *t, const char *text_host, size_t bytes, int q_offset, const fxg_clip_opts *o,
+                                  int show_adapter_only, int expect_len, char *out_host, fxg_text_report *rep)
+{
+    return text_run(t, 4, text_host, bytes, q_offset, show_adapter_only, expect_len, out_host, NULL, 0, o, rep);
 }
 
 extern "C" int fxg_text_stats_host(fxg_text *t, const char *text_host, size_t bytes, int q_offset, uint64_t *hist_dev,
                                    int32_t max_cycles, fxg_text_report *rep)
 {
-    return text_run(t, 3, text_host, bytes, q_offset, 0, 0, NULL, hist_dev, max_cycles, rep);
+    return text_run(t, 3, text_host, bytes, q_offset, 0, 0, NULL, hist_dev, max_cycles, NULL, rep);
 }

@@ -447,6 +447,15 @@ double fxh_now(void)
     clock_gettime(CLOCK_MONOTONIC, &ts);
     return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
+void fxh_reader_seed_shadow(fxh_reader *r, const char *last_seq, int len)
+{
+    if (!r->stale_rows || len <= 0 || len > FXH_MAX_LINE) return;
+    if (!r->shadow) { r->shadow = (uint8_t *)calloc(1, FXH_MAX_LINE + 16); if (!r->shadow) err(1, "out of memory"); }
+    memcpy(r->shadow, last_seq, (size_t)len);
+    r->shadow[len] = 0;
+    if (len > r->wmax) r->wmax = len;
+}
+
 int fxh_reader_at_eof(const fxh_reader *r) { return r->eof; }
 
 size_t fxh_text_chunk_bytes(void)

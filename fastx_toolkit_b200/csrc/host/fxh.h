@@ -71,6 +71,9 @@ size_t      fxh_reader_raw(fxh_reader *r, char **p);                       /* re
 void        fxh_reader_consume(fxh_reader *r, size_t bytes, int64_t records);   /* 4-line FASTQ records             */
 void        fxh_reader_pin(fxh_reader *r);                                 /* page-lock the text buffer for DMA        */
 int         fxh_reader_at_eof(const fxh_reader *r);
+/* clipper: tell the packer what the aligner's query buffer holds after records the text path consumed
+ * (the last read, all earlier reads having had the same length) */
+void        fxh_reader_seed_shadow(fxh_reader *r, const char *last_seq, int len);
 int         fxh_text_path_enabled(void);                                   /* FASTX_TEXT_PATH=0 disables it            */
 size_t      fxh_text_chunk_bytes(void);                                    /* FASTX_CHUNK_BYTES (default 64 MB)        */
 

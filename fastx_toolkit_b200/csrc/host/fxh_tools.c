@@ -271,6 +271,53 @@ static int cl_args(int oi, int optc, char *oa)
     return 1;
 }
 
+/* GPU text path for the clipper: chunks whose reads all have one length (the usual sequencer output).  The first
+ * chunk with another length, a malformed record or an illegal byte goes — with everything after it — to the record
+ * path below, whose packer is told what the aligner's query buffer would hold at that point. */
+static void clip_text_path(fxg_ctx *ctx, fxh_reader *rd, fxh_writer *wr, const fxg_clip_opts *o, unsigned int *count_input, unsigned int *cnt)
+{
+    if (!fxh_text_path_enabled() || !fxh_reader_is_fastq(rd)) return;
+    char *p;
+    size_t len = fxh_reader_raw(rd, &p);
+    if (len == 0) return;
+    size_t cap = fxh_text_chunk_bytes();
+    if (fxh_reader_at_eof(rd) && len + 4096 < cap) cap = len + 4096;
+    fxg_text *tx = NULL;
+    const int dev = getenv("FASTX_GPU") ? atoi(getenv("FASTX_GPU")) : 0;
+    if (fxg_text_new(ctx, dev, cap, &tx) != FXG_OK) return;
+    const size_t ocap = cap + cap / 4 + 64;
+    char *out = (char *)pinned(2 * ocap);
+    int which = 0, expect_len = 0;
+    fxh_reader_pin(rd);
+    for (;;) {
+        len = fxh_reader_raw(rd, &p);
+        if (len == 0) break;
+        if (len > cap) len = cap;
+        fxg_text_report rep;
+        char *ob = out + (size_t)which * ocap;
+        int rc = fxg_text_clip_host(tx, p, len, fxh_q_offset(), o, cl_show_adapter_only, expect_len, ob, &rep);
+        if (rc != FXG_OK) errx(1, "fxg_text_clip_host failed: %s (%s)", fxg_strerror(rc), fxg_text_error(tx));
+        if (rep.anomaly != 0 || rep.n_records == 0) break;
+        expect_len = rep.max_len;
+        fxh_write_raw(wr, ob, (size_t)rep.out_bytes, rep.n_out_records);
+        *count_input += (unsigned int)rep.n_records;
+        for (int k = 0; k < 6; k++) cnt[k] += (unsigned int)rep.clip_class[k];
+        {   /* sequence line of the last consumed record: 3 newlines back from the end of the record */
+            size_t e = (size_t)rep.consumed_bytes - 1;          /* the record's final newline */
+            int nl = 0;
+            while (e > 0 && nl < 3) { e--; if (p[e] == '\n') nl++; }     /* e = newline ending line 2 */
+            size_t s2 = e;
+            while (s2 > 0 && p[s2 - 1] != '\n') s2--;
+            fxh_reader_seed_shadow(rd, p + s2, rep.max_len);
+        }
+        fxh_reader_consume(rd, (size_t)rep.consumed_bytes, rep.n_records);
+        which ^= 1;
+    }
+    fxh_write_raw(wr, out, 0, 0);
+    fxg_free_pinned(out);
+    fxg_text_free(tx);
+}
+
 static int main_clipper(int argc, char **argv)
 {
     fxh_parse_cmdline(argc, argv, "M:kDCcd:a:s:l:n", cl_args, fxh_usage_fastx_clipper);
@@ -287,6 +334,7 @@ static int main_clipper(int argc, char **argv)
     unsigned int count_input = 0, cnt[6] = { 0, 0, 0, 0, 0, 0 };
     pbuf ol = { 0, 0 }, oc = { 0, 0 };
     fxh_batch *b;
+    clip_text_path(ctx, rd, wr, &o, &count_input, cnt);
     while ((b = fxh_reader_next(rd, fxh_batch_reads())) != NULL) {
         int32_t *out_len = (int32_t *)pbuf_get(&ol, (size_t)b->n * sizeof(int32_t));
         uint8_t *out_cls = (uint8_t *)pbuf_get(&oc, (size_t)b->n);

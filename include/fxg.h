@@ -220,17 +220,25 @@ typedef struct {
     int32_t max_len;          /* longest read                                                 */
     int32_t anomaly;          /* 0 = none, else FXG_TEXT_* class                              */
     int64_t anomaly_record;   /* first record (0-based within the chunk) with the anomaly     */
+    int32_t min_len;          /* shortest read                                                */
+    int32_t reserved;
+    int64_t clip_class[6];    /* fxg_text_clip_host: reads per FXG_CLIP_* class               */
 } fxg_text_report;
 #define FXG_TEXT_PREFIX     1
 #define FXG_TEXT_EMPTY_SEQ  2
 #define FXG_TEXT_QUAL_LEN   3
 #define FXG_TEXT_LONG_LINE  4
 #define FXG_TEXT_BAD_RECORD 5
+#define FXG_TEXT_MIXED_LEN  7   /* clipper: read lengths differ (the reference then reads stale bytes: host path) */
 typedef struct fxg_text fxg_text;
 int         fxg_text_new(fxg_ctx *ctx, int device, size_t max_chunk_bytes, fxg_text **out);
 void        fxg_text_free(fxg_text *t);
 int         fxg_text_run_host(fxg_text *t, int op, const char *text_host, size_t bytes, int q_offset, int a0, int a1,
                               char *out_host, fxg_text_report *rep);
+/* fastx_clipper on a chunk of equal-length reads (expect_len = the length of every earlier read, 0 = none yet); other
+ * chunks come back as FXG_TEXT_MIXED_LEN because the reference's aligner then depends on earlier reads' bytes. */
+int         fxg_text_clip_host(fxg_text *t, const char *text_host, size_t bytes, int q_offset, const fxg_clip_opts *o,
+                               int show_adapter_only, int expect_len, char *out_host, fxg_text_report *rep);
 int         fxg_text_stats_host(fxg_text *t, const char *text_host, size_t bytes, int q_offset, uint64_t *hist_dev,
                                 int32_t max_cycles, fxg_text_report *rep);
 const char *fxg_text_error(const fxg_text *t);

@@ -113,3 +113,46 @@ def test_text_path_flags_anomalies(ctx):
     rep = run(lambda ls: None)
     assert rep.anomaly == 0 and rep.n_records == n
     tp.close()
+
+
+def test_text_path_clipper(ctx):
+    """fxg_text_clip_host (fastx_clipper.cpp:257-320 on whole text chunks): equal-length chunks are clipped and emitted on
+    the GPU, anything else is handed back as FXG_TEXT_MIXED_LEN"""
+    import tempfile, os
+    import fastx_toolkit_b200 as F
+    n, L = 20000, 100
+    adapter = b"AGATCGGAAGAGC"
+    seq, qual = H.synth_slab(H.SEED_BASE + 2, n, L, H.ADAPTER)
+    text = fastq_bytes(seq, qual, None, L, plus_names=True)
+    p = tempfile.mktemp(suffix=".fq")
+    open(p, "wb").write(text)
+    recs = H.read_fastx(p)
+    os.unlink(p)
+    tp = F.TextPipe(ctx, len(text) + 4096)
+    for kw, k in ((dict(min_length=20), 0), (dict(min_length=5, discard_non_clipped=1, discard_unknown=0), 0),
+                  (dict(min_length=5, discard_clipped=1), 0), (dict(min_length=10, keep_delta=16, min_adapter_len=6), 0),
+                  (dict(min_length=5), 1)):
+        full = dict(min_length=5, keep_delta=0, discard_non_clipped=0, discard_clipped=0, discard_unknown=1, min_adapter_len=0)
+        full.update(kw)
+        e_len, e_cls, _ = H.o_clip(seq, None, None, L, seq.shape[1], adapter, H.FxoClipOpts(**full))
+        if k:
+            out = np.where(e_cls == 1, L, -1)
+        else:
+            out = np.where(e_cls == 0, e_len, -1)
+        exp = emit(recs, out, 33)
+        got, rep = tp.clip(text, 33, F.ClipOpts(adapter=adapter, **full), k, 0)
+        assert rep.anomaly == 0 and rep.n_records == n and rep.min_len == rep.max_len == L
+        assert [rep.clip_class[c] for c in range(6)] == [int((e_cls == c).sum()) for c in range(6)]
+        assert rep.n_out_records == int((out >= 0).sum()) and got == exp
+    o = F.ClipOpts(adapter=adapter, min_length=5, keep_delta=0, discard_non_clipped=0, discard_clipped=0, discard_unknown=1, min_adapter_len=0)
+    # earlier reads were longer / shorter than this chunk's: host path
+    assert tp.clip(text, 33, o, 0, L + 1)[1].anomaly == 7
+    assert tp.clip(text, 33, o, 0, L)[1].anomaly == 0
+    # one short read inside the chunk
+    lens = np.full(n, L, np.int32); lens[n // 2] = L - 3
+    assert tp.clip(fastq_bytes(seq, qual, lens, L), 33, o, 0, 0)[1].anomaly == 7
+    # illegal base is still reported by the op kernel
+    s2 = seq.copy(); s2[321, 5] = ord("x")
+    rep = tp.clip(fastq_bytes(s2, qual, None, L), 33, o, 0, 0)[1]
+    assert (rep.anomaly, rep.anomaly_record) == (5, 321)
+    tp.close()

@@ -154,6 +154,38 @@ def test_small_windows_and_chunks(tmp_path):
 
 @gpu
 @needs_ref
+def test_clipper_text_path_and_fallback_transition(tmp_path):
+    """fastx_clipper on the GPU text path (equal-length reads), then a file whose read lengths change part-way: the
+    record path that takes over must see the aligner's stale query buffer exactly as the reference leaves it"""
+    fq = str(tmp_path / "uni.fq")
+    synth_fastq(fq, 30000, 100, H.ADAPTER, np.random.default_rng(11))
+    rng = np.random.default_rng(12)
+    mixed = str(tmp_path / "mixed.fq")
+    with open(fq, "rb") as f:
+        lines = f.read().split(b"\n")[:-1]
+    recs = [lines[i:i + 4] for i in range(0, len(lines), 4)]
+    with open(mixed, "wb") as f:
+        for k, r in enumerate(recs):
+            if k >= 12000 and rng.random() < 0.5:                      # shorter reads after a long uniform prefix
+                L = int(rng.integers(5, 100))
+                r = [r[0], r[1][:L], r[2], r[3][:L]]
+            f.write(b"\n".join(r) + b"\n")
+    opts = [["-a", "AGATCGGAAGAGC", "-l", "10", "-v"], ["-a", "AGATCGGAAGAGC", "-n", "-c", "-v"], ["-a", "AGATCGGAAGAGC", "-C", "-v"],
+            ["-a", "AGATCGGAAGAGC", "-k", "-v"], ["-a", "AGATCGGAAGAGCACACGTCTGAACTCCAGTCAC", "-d", "3", "-M", "4", "-n", "-v"]]
+    for env in [dict(), dict(FASTX_WINDOW_BYTES="400000", FASTX_CHUNK_BYTES="150000"), dict(FASTX_TEXT_PATH="0")]:
+        os.environ.update(env)
+        try:
+            for o in opts:
+                assert_same("fastx_clipper", o + ["-i", fq])
+                assert_same("fastx_clipper", o + ["-i", mixed])
+            assert_same("fastx_clipper", ["-a", "AGATCGGAAGAGC", "-v"], stdin=open(mixed, "rb").read())
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+
+
+@gpu
+@needs_ref
 def test_output_file_report_stream_and_gzip(tmp_path):
     fq = str(tmp_path / "in.fq")
     synth_fastq(fq, 5000, 100, H.PLAIN)
