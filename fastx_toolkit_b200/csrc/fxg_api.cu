@@ -434,7 +434,14 @@ static int revcomp_enqueue(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint8
     p.tile_reads = plan.tile_reads; p.stages = plan.stages;
     p.qk = make_qualk(q_offset, 0);
     p.out_seq = out_seq; p.out_qual = out_qual; p.index_base = index_base; p.counters = ctx->d_counters;
-    CK(ctx, launch_revcomp(has_qual, plan, p, st));
+    {
+        cudaError_t e = launch_revcomp(has_qual, plan, p, st);
+        if (e != cudaSuccess) {
+            snprintf(ctx->err, sizeof(ctx->err), "launch_revcomp: %s (n %lld stride %d ring %d g %d tile %d grid %d smem %u)", cudaGetErrorString(e),
+                     (long long)b->n, b->stride, plan.warp_ring, plan.g, plan.tile_reads, plan.grid, plan.smem_bytes);
+            return FXG_ERR_CUDA;
+        }
+    }
     ctx->launches++;
     ctx->report.n_in += b->n;
     return FXG_OK;

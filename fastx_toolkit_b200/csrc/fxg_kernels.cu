@@ -633,7 +633,7 @@ __global__ void __launch_bounds__(256) k_synth(const SynthParams P)
 #define FXG_LAUNCH_DYN(KERNEL, GRID, BLOCK, SMEM, STREAM, PARAMS)                                   \
     do {                                                                                           \
         auto kf_ = KERNEL;                                                                         \
-        if ((SMEM) > 48u * 1024u) cudaFuncSetAttribute(kf_, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM); \
+        if ((SMEM) > 40u * 1024u   /* static mbarrier words count against the 48 KB default too */) cudaFuncSetAttribute(kf_, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM); \
         kf_<<<(GRID), (BLOCK), (SMEM), (STREAM)>>>(PARAMS);                                        \
     } while (0)
 

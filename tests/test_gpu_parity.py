@@ -113,6 +113,31 @@ def test_revcomp_uniform(ctx, L, n):
     assert np.array_equal(back, seq) and np.array_equal(backq, qual)
 
 
+def test_every_stride_bucket(ctx):
+    """every 16-byte stride from 16 to 512 (plus a few longer): each picks its own tile / shared-memory plan, several of
+    which sit exactly on the 48 KB opt-in boundary (stride 96 with qualities needs 48 KB + the barrier words)"""
+    strides = list(range(16, 513, 16)) + [640, 768, 1024, 1536, 2048]
+    rng = np.random.default_rng(3)
+    for S in strides:
+        L = S - int(rng.integers(0, 16))
+        n = 1500 + int(rng.integers(0, 200))
+        seq, qual = H.synth_slab(H.SEED_BASE + S, n, L, H.WITH_N)
+        assert seq.shape[1] == S
+        for pass_ in range(2):
+            ln, LL = (None, L) if pass_ == 0 else (H.ragged(seq, qual, np.random.default_rng(S), min_len=1), 0)
+            exp, _ = H.o_trim(seq, qual, ln, LL, S, 33, 22, 10)
+            got, rep = run_trim(ctx, seq, qual, ln, LL, 33, 22, 10)
+            assert np.array_equal(got, exp), ("trim", S, ln is None)
+            exp, _ = H.o_filter(seq, qual, ln, LL, S, 33, 22, 70)
+            got, rep = run_filter(ctx, seq, qual, ln, LL, 33, 22, 70)
+            assert np.array_equal(got, exp), ("filter", S, ln is None)
+            eseq, equal = H.o_revcomp(seq, qual, ln, LL, S)
+            gseq, gqual, rep = run_revcomp(ctx, seq, qual, ln, LL)
+            assert np.array_equal(gseq, eseq) and np.array_equal(gqual, equal), ("revcomp", S, ln is None)
+            gseq, _, rep = run_revcomp(ctx, seq, None, ln, LL)
+            assert np.array_equal(gseq, eseq), ("revcomp fasta", S, ln is None)
+
+
 def test_decide_only_variant(ctx):
     seq, qual = H.synth_slab(H.SEED_BASE, 12345, 150)
     exp, _ = H.o_trim(None, qual, None, 150, 160, 33, 20, 20)
