@@ -80,6 +80,10 @@ constexpr int ST_QWIN = 64;                       // q' = q+15 in [0,64) lives i
 constexpr int ST_KBLK = 4 * ST_QWIN * 4;          // bytes per (word, byte k): 4 nucs x 64 x u32 = 1024
 constexpr int ST_WBLK = 4 * ST_KBLK + 36;         // bytes per word block
 constexpr int ST_MAXW = 40;                       // words (4 cycles each) per pass: 160 cycles
+// second-generation layout (k_stats2): [bin = nuc*64 + q'][column 40k + w] u32 — bank = (8k + w) mod 32
+constexpr int S2_PITCH = 4 * ST_MAXW * 4;         // bytes per bin: 160 columns x u32 = 640
+constexpr int S2_HIST_BYTES = 4 * ST_QWIN * S2_PITCH;   // 256 bins: 163 840 bytes
+constexpr int S2_TILE_READS = 8;                  // reads per warp tile (4 lanes per read)
 
 struct StatsParams {
     const uint8_t *seq;
@@ -121,6 +125,7 @@ struct ClipParams {
 };
 
 cudaError_t launch_stats(const StatsParams &p, int g, int grid, uint32_t smem_bytes, cudaStream_t st);
+cudaError_t launch_stats2(const StatsParams &p, int warps, int grid, uint32_t smem_bytes, cudaStream_t st);
 cudaError_t launch_stats_simple(const StatsParams &p, int sm_count, cudaStream_t st);
 cudaError_t launch_clip(const ClipParams &p, int sm_count, int max_width, cudaStream_t st);
 cudaError_t stats_set_smem_attrs();

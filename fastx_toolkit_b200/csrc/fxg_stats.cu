@@ -169,6 +169,256 @@ __global__ void __launch_bounds__(ST_WARPS * G * 32, 1) k_stats(const __grid_con
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// K-STATS, second generation: bank-conflict-free shared histogram.
+//
+// Layout: hist[bin = nuc*64 + q'][pc] u32, 160 physical columns per bin (pitch 640 B), where the column of
+// cycle 4w+k (w = 4-byte word of the read, k = byte in the word) is pc = 40k + w.  The bank of a counter is
+// therefore (8k + w) mod 32 — a function of the CYCLE only, never of the data — so an ATOMS whose 32 lanes
+// sit on 32 columns with distinct (8k + w) mod 32 is one wavefront whatever the qualities are.
+// A warp owns a tile of 8 reads, 4 lanes per read (lane = 4*rr + j):
+//   * A scheme, 32-word superblocks: at step t lane (rr,j) takes word 4*((t+rr)&7) + j — the 32 lanes cover
+//     32 different words, k is the same for all lanes of one ATOMS (static, address immediate);
+//   * B scheme, 8-word blocks (the words past the last full superblock): at step s lane (rr,j) takes word
+//     (2j+s+g(rr))&7 of the block and issues its four bytes in the rotated order k = (j+i)&3, so the four lanes
+//     that share a word use four different k.
+// Per word: 3 ops for the PRMT selector, 2 PRMT (legal-character table with 'N' poisoned, nuc<<6 table), one
+// IADD3 (nuc<<6 | q'), 2 LOP3 for "all four samples are plain A/C/G/T with 0 <= q' < 64" (this subsumes the
+// quality range check when Q-15 <= 64); per sample: byte extract, IMAD (bin*640 + column), ATOMS.
+// Words with 'N', q' >= 64 or illegal bytes take a per-byte path; the 1..3 bytes past the last full word are
+// done once per tile with one lane per byte.
+// ---------------------------------------------------------------------------------------------------
+constexpr uint32_t V2LUT_HI = 0x47FFFF54u;      // VLUT_HI with 'N' (code 6) poisoned: N goes to the per-byte path
+constexpr uint32_t N6_LO = 0x40000000u;         // nuc<<6 by code: 1:A->00, 3:C->40
+constexpr uint32_t N6_HI = 0x800000C0u;         //                 4:T->C0, 7:G->80
+
+__device__ __forceinline__ uint32_t lds32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void reds_inc(uint32_t addr)
+{
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+}
+
+// one base (exact path): validation as the reader does it, 'N' and q' >= 64 go to the global table.
+// Returns 1 when the base or its quality is illegal.
+__device__ __forceinline__ uint32_t stats2_byte(const StatsParams &P, uint32_t c, uint32_t q, int wrel, int k, uint32_t hs_addr)
+{
+    const uint32_t lo = P.qk.lo4 & 0xFFu, hmax = 127u - (P.qk.hik4 & 0xFFu) - lo;
+    const uint32_t code = c & 7u;
+    const uint32_t legal = __byte_perm(VLUT_LO, VLUT_HI, code) & 0xFFu;
+    const uint32_t nuc = __byte_perm(NLUT_LO, NLUT_HI, code) & 0xFFu;
+    const uint32_t qp = q - lo;
+    if (legal != c || qp > hmax) return 1u;
+    if (nuc < 4u && qp < (uint32_t)ST_QWIN)
+        reds_inc(hs_addr + (nuc * 64u + qp) * S2_PITCH + (uint32_t)k * (4u * ST_MAXW) + 4u * (uint32_t)wrel);
+    else
+        hist_global_add(P.hist, P.max_cycles, 4 * (P.w0 + wrel) + k, (int)nuc, (int)qp, 1ull);
+    return 0u;
+}
+// per-byte path of one full word (rare: 'N', q' >= 64 or an illegal byte somewhere in the word)
+__device__ __noinline__ uint32_t stats2_slow_word(const StatsParams &P, uint32_t sw, uint32_t qw, int wrel, uint32_t hs_addr)
+{
+    uint32_t bad = 0;
+    for (int k = 0; k < 4; k++) bad |= stats2_byte(P, (sw >> (8 * k)) & 0xFFu, (qw >> (8 * k)) & 0xFFu, wrel, k, hs_addr);
+    return bad;
+}
+
+// loop-invariant operands kept in registers (opaque to the compiler, which would otherwise rebuild the
+// 32-bit immediates in front of every PRMT)
+struct Stats2K {
+    uint32_t vlut_lo, n6_lo, neg_lo4;
+};
+
+// decode one full word: comb = (nuc<<6 | q') per byte, valid when the returned test word is 0 (four plain
+// A/C/G/T bases with 0 <= q' < 64)
+__device__ __forceinline__ uint32_t stats2_decode(const Stats2K &K, uint32_t sw, uint32_t qw, uint32_t &comb)
+{
+    const uint32_t y = sw & 0x07070707u;
+    const uint32_t sel = prmt_raw(y | (y >> 4), 0u, 0x4420u);
+    const uint32_t e = prmt_raw(K.vlut_lo, V2LUT_HI, sel);
+    const uint32_t n6 = prmt_raw(K.n6_lo, N6_HI, sel);
+    comb = n6 + qw + K.neg_lo4;
+    return (sw ^ e) | ((comb ^ n6) & 0xC0C0C0C0u);
+}
+// four counter increments of one decoded word at byte offset o = 4*wrel of the pass window
+template <bool DYNK>
+__device__ __forceinline__ void stats2_emit(uint32_t comb, uint32_t o, uint32_t hs_addr, const uint32_t (&ksel)[4], const uint32_t (&koff)[4])
+{
+    if (!DYNK) {
+        const uint32_t b0 = comb & 0xFFu, b1 = prmt_raw(comb, 0u, 0x4441u), b2 = prmt_raw(comb, 0u, 0x4442u), b3 = comb >> 24;
+        const uint32_t col = hs_addr + o;
+        reds_inc(b0 * S2_PITCH + col);
+        reds_inc(b1 * S2_PITCH + col + 1u * (4u * ST_MAXW));
+        reds_inc(b2 * S2_PITCH + col + 2u * (4u * ST_MAXW));
+        reds_inc(b3 * S2_PITCH + col + 3u * (4u * ST_MAXW));
+    } else {
+        const uint32_t col = hs_addr + o;
+#pragma unroll
+        for (int i = 0; i < 4; i++) reds_inc(prmt_raw(comb, 0u, ksel[i]) * S2_PITCH + (col + koff[i]));
+    }
+}
+template <bool DYNK>
+__device__ __forceinline__ void stats2_word(const StatsParams &P, const Stats2K &K, uint32_t sw, uint32_t qw, uint32_t o, uint32_t hs_addr,
+                                            const uint32_t (&ksel)[4], const uint32_t (&koff)[4], uint32_t &bad)
+{
+    uint32_t comb;
+    if (stats2_decode(K, sw, qw, comb) == 0u) stats2_emit<DYNK>(comb, o, hs_addr, ksel, koff);
+    else bad |= stats2_slow_word(P, sw, qw, (int)(o >> 2), hs_addr);
+}
+// two full words with one branch between them
+template <bool DYNK>
+__device__ __forceinline__ void stats2_pair(const StatsParams &P, const Stats2K &K, uint32_t sw0, uint32_t qw0, uint32_t o0, uint32_t sw1,
+                                            uint32_t qw1, uint32_t o1, uint32_t hs_addr, const uint32_t (&ksel)[4],
+                                            const uint32_t (&koff)[4], uint32_t &bad)
+{
+    uint32_t c0, c1;
+    const uint32_t t0 = stats2_decode(K, sw0, qw0, c0), t1 = stats2_decode(K, sw1, qw1, c1);
+    if ((t0 | t1) == 0u) {
+        stats2_emit<DYNK>(c0, o0, hs_addr, ksel, koff);
+        stats2_emit<DYNK>(c1, o1, hs_addr, ksel, koff);
+    } else {
+        if (t0 == 0u) stats2_emit<DYNK>(c0, o0, hs_addr, ksel, koff);
+        else bad |= stats2_slow_word(P, sw0, qw0, (int)(o0 >> 2), hs_addr);
+        if (t1 == 0u) stats2_emit<DYNK>(c1, o1, hs_addr, ksel, koff);
+        else bad |= stats2_slow_word(P, sw1, qw1, (int)(o1 >> 2), hs_addr);
+    }
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_stats2(const __grid_constant__ StatsParams P)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int NTHREADS = WARPS * 32;
+    __shared__ __align__(8) uint64_t full_bar[WARPS];
+
+    // one stage per warp: a warp's wait for HBM is covered by the other warps of the SM
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int S = P.stride, R = P.tile_reads;                          // R <= 8
+    const uint32_t slab_bytes = (uint32_t)R * (uint32_t)S;
+    uint8_t *wbase = smem + S2_HIST_BYTES + (size_t)w * (2u * slab_bytes);
+    uint64_t *bar = &full_bar[w];
+    const uint32_t ntiles = (uint32_t)((P.n + R - 1) / R);            // host guarantees n / R < 2^31
+    const uint32_t gw = blockIdx.x * WARPS + w, GW = gridDim.x * WARPS;
+
+    for (uint32_t i = tid * 16; i < (uint32_t)S2_HIST_BYTES; i += NTHREADS * 16) *reinterpret_cast<uint4 *>(smem + i) = make_uint4(0, 0, 0, 0);
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](uint32_t tile) {
+        const int64_t r0 = (int64_t)tile * R;
+        const int64_t left = P.n - r0;
+        const uint32_t bytes = (uint32_t)(left < R ? left : R) * (uint32_t)S;
+        mbar_arrive_expect_tx(bar, bytes * 2u);
+        bulk_g2s(wbase, P.seq + r0 * S, bytes, bar);
+        bulk_g2s(wbase + slab_bytes, P.qual + r0 * S, bytes, bar);
+    };
+    if (lane == 0 && gw < ntiles) issue(gw);
+
+    const uint32_t hs_addr = smem_u32(smem);
+    const int j = lane & 3, rr = lane >> 2;
+    Stats2K K;
+    const uint32_t zero = (uint32_t)((unsigned long long)P.n >> 62);       // 0, but only known at run time
+    K.vlut_lo = VLUT_LO + zero; K.n6_lo = N6_LO + zero; K.neg_lo4 = zero - P.qk.lo4;
+    const int passoff = 4 * P.w0, ncols = 4 * P.nw;
+    const int nsb = P.nw >> 5;                                   // full 32-word superblocks (A scheme)
+    const int nb8 = (P.nw + 7) >> 3;                             // 8-word blocks in all
+    uint32_t ksel[4], koff[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t k = (uint32_t)((j + i) & 3);
+        ksel[i] = 0x4440u + k;
+        koff[i] = k * (4u * ST_MAXW);
+    }
+    const uint32_t uoj0 = (uint32_t)(16 * rr + 4 * j);           // A scheme, t = 0: word 4*rr + j
+    const int grr = ((rr & 3) << 1) | (rr >> 2);                 // B scheme skew: a bijection of 0..7 with g(rr+4) - g(rr) odd,
+                                                                 // so rows rr and rr+4 (same bank octet at S = 160) never collide
+    const uint32_t srow = smem_u32(wbase) + (uint32_t)(rr < R ? rr : 0) * (uint32_t)S + (uint32_t)passoff;
+    const uint32_t qrow = srow + slab_bytes;
+    const bool lane_on = rr < R;
+    const int ulen = P.uniform_len;
+    const bool ragged = P.len != nullptr;
+    uint32_t parity = 0;
+
+    for (uint32_t tile = gw; tile < ntiles; tile += GW) {
+        const int64_t g = (int64_t)tile * R + rr;
+        const bool active = lane_on && g < P.n;
+        int L = 0;
+        if (active) L = ragged ? __ldg(P.len + g) : ulen;
+        const bool lenbad = active && (L <= 0 || L > S);
+        if (lenbad) L = 0;
+        int Lp = L - passoff;                                    // bases of this read inside the pass window
+        if (Lp > ncols) Lp = ncols;
+        const int lim = Lp - 4;                                  // a word at byte offset o is full iff o <= lim
+        uint32_t bad = 0;
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+
+        if (nsb) {                                               // nw <= ST_MAXW = 40: at most one superblock
+            constexpr int sb = 0;
+            if (__all_sync(0xFFFFFFFFu, lim >= 128 * sb + 124)) {   // every read of the tile fills the superblock
+#pragma unroll
+                for (int t = 0; t < 8; t += 2) {
+                    const uint32_t o0 = 128u * (uint32_t)sb + ((uoj0 + 16u * t) & 0x7Fu);
+                    const uint32_t o1 = 128u * (uint32_t)sb + ((uoj0 + 16u * t + 16u) & 0x7Fu);
+                    stats2_pair<false>(P, K, lds32(srow + o0), lds32(qrow + o0), o0, lds32(srow + o1), lds32(qrow + o1), o1, hs_addr, ksel,
+                                       koff, bad);
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    const uint32_t o = 128u * (uint32_t)sb + ((uoj0 + 16u * t) & 0x7Fu);
+                    if ((int)o <= lim) stats2_word<false>(P, K, lds32(srow + o), lds32(qrow + o), o, hs_addr, ksel, koff, bad);
+                }
+            }
+        }
+        for (int b8 = nsb * 4; b8 < nb8; b8++) {
+            const uint32_t o0 = 32u * (uint32_t)b8 + 4u * (uint32_t)((2 * j + grr) & 7);
+            const uint32_t o1 = 32u * (uint32_t)b8 + 4u * (uint32_t)((2 * j + 1 + grr) & 7);
+            const bool v0 = (int)o0 <= lim, v1 = (int)o1 <= lim;
+            if (v0 && v1)
+                stats2_pair<true>(P, K, lds32(srow + o0), lds32(qrow + o0), o0, lds32(srow + o1), lds32(qrow + o1), o1, hs_addr, ksel, koff, bad);
+            else if (v0)
+                stats2_word<true>(P, K, lds32(srow + o0), lds32(qrow + o0), o0, hs_addr, ksel, koff, bad);
+            else if (v1)
+                stats2_word<true>(P, K, lds32(srow + o1), lds32(qrow + o1), o1, hs_addr, ksel, koff, bad);
+        }
+        // the 1..3 bases after the last full word: lane j of the read takes byte j
+        if (Lp > 0 && j < (Lp & 3)) {
+            const uint32_t o = (uint32_t)(Lp & ~3);
+            bad |= stats2_byte(P, lds8(srow + o + j), lds8(qrow + o + j), (int)(o >> 2), j, hs_addr);
+        }
+        if ((bad != 0 || lenbad) && active)
+            atomicMin(&P.counters[CNT_FIRST_BAD], (unsigned long long)(P.index_base + g));
+
+        __syncwarp();
+        if (lane == 0 && tile + GW < ntiles) issue(tile + GW);
+    }
+
+    // flush the CTA's shared histogram into the global u64 table
+    __syncthreads();
+    for (int i = tid; i < S2_HIST_BYTES / 4; i += NTHREADS) {
+        const uint32_t v = *reinterpret_cast<const uint32_t *>(smem + 4 * (size_t)i);
+        if (v) {
+            const int bin = i / (4 * ST_MAXW), pc = i - bin * (4 * ST_MAXW);
+            const int k = pc / ST_MAXW, wr = pc - k * ST_MAXW;
+            hist_global_add(P.hist, P.max_cycles, 4 * (P.w0 + wr) + k, bin >> 6, bin & 63, (unsigned long long)v);
+        }
+    }
+}
+
 // General fallback (any stride, FASTA input, per-read weights): one thread per 16-byte chunk, global atomics.
 __global__ void __launch_bounds__(256) k_stats_simple(const StatsParams P)
 {
@@ -221,6 +471,21 @@ cudaError_t launch_stats(const StatsParams &p, int g, int grid, uint32_t smem_by
     else if (g == 4) FXG_STATS_LAUNCH(4);
     else return cudaErrorInvalidValue;
 #undef FXG_STATS_LAUNCH
+    return cudaGetLastError();
+}
+
+cudaError_t launch_stats2(const StatsParams &p, int warps, int grid, uint32_t smem_bytes, cudaStream_t st)
+{
+#define FXG_STATS2_LAUNCH(WV)                                                                        \
+    do {                                                                                            \
+        cudaFuncSetAttribute(k_stats2<WV>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM); \
+        k_stats2<WV><<<grid, WV * 32, smem_bytes, st>>>(p);                                          \
+    } while (0)
+    if (warps == 24) FXG_STATS2_LAUNCH(24);
+    else if (warps == 16) FXG_STATS2_LAUNCH(16);
+    else if (warps == 12) FXG_STATS2_LAUNCH(12);
+    else return cudaErrorInvalidValue;
+#undef FXG_STATS2_LAUNCH
     return cudaGetLastError();
 }
 
