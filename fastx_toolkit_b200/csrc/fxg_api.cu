@@ -104,6 +104,14 @@ extern "C" int fxg_init(int device, fxg_ctx **out)
     for (int l = 0; l < PIPE_LANES; l++)
         if ((e = cudaStreamCreateWithFlags(&ctx->lane_stream[l], cudaStreamNonBlocking)) != cudaSuccess) { free(ctx); INIT_FAIL("cudaStreamCreate", e); }
     if ((e = cudaMalloc(&ctx->d_counters, CNT_WORDS * sizeof(unsigned long long))) != cudaSuccess) { free(ctx); INIT_FAIL("cudaMalloc", e); }
+    {   // stream-ordered scratch (clipper work list): keep freed blocks in the pool instead of returning them at every sync
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     if ((e = cudaMallocHost(&ctx->h_counters, CNT_WORDS * sizeof(unsigned long long))) != cudaSuccess) { free(ctx); INIT_FAIL("cudaMallocHost", e); }
     if ((e = kernels_set_smem_attrs()) != cudaSuccess || (e = stats_set_smem_attrs()) != cudaSuccess) { free(ctx); INIT_FAIL("cudaFuncSetAttribute(max dynamic smem)", e); }
     *out = ctx;
@@ -544,8 +552,32 @@ static int clip_enqueue(fxg_ctx *ctx, const fxg_batch *b, const int32_t *width, 
     p.min_length = o->min_length; p.keep_delta = o->keep_delta; p.discard_non_clipped = o->discard_non_clipped;
     p.discard_clipped = o->discard_clipped; p.discard_unknown = o->discard_unknown; p.min_adapter_len = o->min_adapter_len;
     p.out_len = out_len; p.out_class = out_class; p.out_cut = out_cut; p.index_base = index_base; p.counters = ctx->d_counters;
-    CK(ctx, launch_clip(p, ctx->sm_count, (width || b->len) ? b->stride : b->uniform_len, st));
-    ctx->launches++;
+    // Integer fast path (k_clip_dpx, two reads per thread in packed s16x2): batches of one length, adapters of
+    // A/C/G/T only, up to 16 characters.  Reads with an 'N' go on a list and through the fp32 kernel in a second
+    // launch.  FXG_CLIP_V=1 selects the fp32 kernel for everything.
+    const char *cv = getenv("FXG_CLIP_V");
+    bool dpx = !(cv && cv[0] == '1') && !width && !b->len && p.alen >= 1 && p.alen <= 16 && b->uniform_len <= 256 &&
+               b->n < (1ll << 31);
+    for (int i = 0; i < p.alen && dpx; i++) {
+        const char c = o->adapter[i];
+        if (!(c == 'A' || c == 'C' || c == 'G' || c == 'T')) dpx = false;
+    }
+    if (dpx) {
+        void *scratch = NULL;
+        CK(ctx, cudaMallocAsync(&scratch, 16 + (size_t)b->n * sizeof(int32_t), st));
+        CK(ctx, cudaMemsetAsync(scratch, 0, 16, st));
+        p.list_count = (unsigned long long *)scratch;
+        p.list = (int32_t *)((char *)scratch + 16);
+        p.list_pass = 0;
+        CK(ctx, launch_clip(p, ctx->sm_count, b->uniform_len, st));
+        p.list_pass = 1;
+        CK(ctx, launch_clip(p, ctx->sm_count, b->uniform_len, st));
+        CK(ctx, cudaFreeAsync(scratch, st));
+        ctx->launches += 2;
+    } else {
+        CK(ctx, launch_clip(p, ctx->sm_count, (width || b->len) ? b->stride : b->uniform_len, st));
+        ctx->launches++;
+    }
     ctx->report.n_in += b->n;
     return FXG_OK;
 }

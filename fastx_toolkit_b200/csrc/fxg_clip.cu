@@ -16,6 +16,7 @@
 #include <stdlib.h>
 
 #include "fxg_kernels.cuh"
+#include "fxg_clip_dpx.cuh"
 
 namespace fxg {
 
@@ -103,6 +104,38 @@ __device__ __forceinline__ int cutoff_index(uint32_t lo, uint32_t hi, int qend, 
 }
 
 enum { CLS_WRITE = 0, CLS_ADAPTER_ONLY = 1, CLS_TOO_SHORT = 2, CLS_NON_CLIPPED = 3, CLS_CLIPPED = 4, CLS_HAS_N = 5 };
+
+// cut-off + discard cascade (fastx_clipper.cpp:280-319) of one read; writes its outputs, returns its class
+__device__ __forceinline__ int clip_epilogue(const ClipParams &P, int64_t g, int L, bool bad, uint32_t lo, uint32_t hi, int bx, int firstN)
+{
+    const int cut = bad ? -1 : cutoff_index(lo, hi, bx, L, P.min_adapter_len);
+    int newL = L, cls;
+    if (cut > 0) { const int at = cut + P.keep_delta; if (at < newL) newL = at; }
+    if (cut == 0) cls = CLS_ADAPTER_ONLY;
+    else if ((unsigned)newL < (unsigned)P.min_length) cls = CLS_TOO_SHORT;
+    else if (cut == -1 && P.discard_non_clipped) cls = CLS_NON_CLIPPED;
+    else if (cut > 0 && P.discard_clipped) cls = CLS_CLIPPED;
+    else if (P.discard_unknown && firstN < newL) cls = CLS_HAS_N;
+    else cls = CLS_WRITE;
+    P.out_len[g] = (cls == CLS_WRITE) ? newL : -1;
+    if (P.out_class) P.out_class[g] = (uint8_t)cls;
+    if (P.out_cut) P.out_cut[g] = cut;
+    return cls;
+}
+// reader's quality range check for one FASTQ read (fastx.c:118-135); non-zero when a byte is illegal
+__device__ __forceinline__ uint32_t clip_qual_bad(const ClipParams &P, int64_t g, int L)
+{
+    const uint8_t *qrow = P.qual + (size_t)g * P.stride;
+    uint32_t badbits = 0;
+    for (int c = 0; c * 16 < L; c++) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(qrow + c * 16));
+        const uint32_t qw[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+        for (int wd = 0; wd < 4; wd++)
+            badbits |= qual_bad_bits(qw[wd], qw[wd] | HI, P.qk) & HI & head_mask(L - 16 * c - 4 * wd);
+    }
+    return badbits;
+}
 
 template <int HMAX>
 __global__ void __launch_bounds__(128) k_clip(const __grid_constant__ ClipParams P)
@@ -221,9 +254,11 @@ __global__ void __launch_bounds__(128) k_clip_bits(const __grid_constant__ ClipP
 {
     const int H = P.alen;
     const int lane = threadIdx.x & 31;
-    for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ll; base < P.n; base += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t g = base + lane;
-        const bool active = g < P.n;
+    // list mode (second pass of the integer fast path): only the reads whose indices k_clip_dpx put on the list
+    const int64_t nn = P.list ? (int64_t)*P.list_count : P.n;
+    for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ll; base < nn; base += (int64_t)gridDim.x * blockDim.x) {
+        const bool active = base + lane < nn;
+        const int64_t g = !active ? 0 : (P.list ? (int64_t)P.list[base + lane] : base + lane);
         int cls = -1;
         if (active) {
             int L = P.len ? __ldg(P.len + g) : P.uniform_len;
@@ -270,35 +305,54 @@ __global__ void __launch_bounds__(128) k_clip_bits(const __grid_constant__ ClipP
                 lo = (uint32_t)matches | ((uint32_t)mism << 7) | ((uint32_t)neutral << 14) | ((uint32_t)tstart << TSTART_SHIFT);
                 hi = (uint32_t)gaps | ((uint32_t)qstart << QSTART_SHIFT);
             }
-            if (P.qual && !bad) {
-                const uint8_t *qrow = P.qual + (size_t)g * P.stride;
-                for (int c = 0; c * 16 < L; c++) {
-                    const uint4 q = __ldg(reinterpret_cast<const uint4 *>(qrow + c * 16));
-                    const uint32_t qw[4] = { q.x, q.y, q.z, q.w };
-#pragma unroll
-                    for (int wd = 0; wd < 4; wd++)
-                        badbits |= qual_bad_bits(qw[wd], qw[wd] | HI, P.qk) & HI & head_mask(L - 16 * c - 4 * wd);
-                }
-            }
+            if (P.qual && !bad) badbits |= clip_qual_bad(P, g, L);
             if (badbits || bad) atomicMin(&P.counters[CNT_FIRST_BAD], (unsigned long long)(P.index_base + g));
-
-            const int cut = bad ? -1 : cutoff_index(lo, hi, bx, L, P.min_adapter_len);
-            int newL = L;
-            if (cut > 0) { const int at = cut + P.keep_delta; if (at < newL) newL = at; }
-            if (cut == 0) cls = CLS_ADAPTER_ONLY;
-            else if ((unsigned)newL < (unsigned)P.min_length) cls = CLS_TOO_SHORT;
-            else if (cut == -1 && P.discard_non_clipped) cls = CLS_NON_CLIPPED;
-            else if (cut > 0 && P.discard_clipped) cls = CLS_CLIPPED;
-            else if (P.discard_unknown && firstN < newL) cls = CLS_HAS_N;
-            else cls = CLS_WRITE;
-            P.out_len[g] = (cls == CLS_WRITE) ? newL : -1;
-            if (P.out_class) P.out_class[g] = (uint8_t)cls;
-            if (P.out_cut) P.out_cut[g] = cut;
+            cls = clip_epilogue(P, g, L, bad, lo, hi, bx, firstN);
         }
 #pragma unroll
         for (int c = 0; c < 6; c++) {
             const unsigned m = __ballot_sync(0xffffffffu, cls == c);
             if (lane == 0 && m) atomicAdd(&P.counters[c == 0 ? CNT_OUT : CNT_AUX0 + c], (unsigned long long)__popc(m));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Integer fast path (fxg_clip_dpx.cuh): two reads per thread in packed s16x2 DPX arithmetic, for batches of
+// uniform length and adapters without 'N'.  Reads with an 'N' or an illegal character are appended to
+// P.list and redone by k_clip_bits (fp32, exact tie behaviour of the 0.1f score) in a second launch.
+// ------------------------------------------------------------------------------------------------
+template <int HMAX>
+__global__ void __launch_bounds__(128) k_clip_dpx(const __grid_constant__ ClipParams P)
+{
+    const int H = P.alen, L = P.uniform_len;
+    const int lane = threadIdx.x & 31;
+    const int64_t npairs = (P.n + 1) >> 1;
+    for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ll; base < npairs; base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pair = base + lane;
+        int cls0 = -1, cls1 = -1;
+        if (pair < npairs) {
+            const int64_t g0 = 2 * pair;
+            const bool has1 = g0 + 1 < P.n;
+            const int64_t g1 = has1 ? g0 + 1 : g0;
+            const uint8_t *row0 = P.seq + (size_t)g0 * P.stride, *row1 = P.seq + (size_t)g1 * P.stride;
+            dpx::PairOut o;
+            dpx::align_pair<HMAX, 256>(row0, row1, L, P.adapter, H, o);
+            if (P.qual) {
+                if (clip_qual_bad(P, g0, L)) atomicMin(&P.counters[CNT_FIRST_BAD], (unsigned long long)(P.index_base + g0));
+                if (has1 && clip_qual_bad(P, g1, L)) atomicMin(&P.counters[CNT_FIRST_BAD], (unsigned long long)(P.index_base + g1));
+            }
+            if (o.exact & 1u) P.list[atomicAdd(P.list_count, 1ull)] = (int32_t)g0;
+            else cls0 = clip_epilogue(P, g0, L, false, o.lo[0], o.hi[0], o.bx[0], 0x7FFFFFFF);
+            if (has1) {
+                if (o.exact & 2u) P.list[atomicAdd(P.list_count, 1ull)] = (int32_t)g1;
+                else cls1 = clip_epilogue(P, g1, L, false, o.lo[1], o.hi[1], o.bx[1], 0x7FFFFFFF);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+            const unsigned m0 = __ballot_sync(0xffffffffu, cls0 == c), m1 = __ballot_sync(0xffffffffu, cls1 == c);
+            if (lane == 0 && (m0 | m1)) atomicAdd(&P.counters[c == 0 ? CNT_OUT : CNT_AUX0 + c], (unsigned long long)(__popc(m0) + __popc(m1)));
         }
     }
 }
@@ -310,8 +364,24 @@ cudaError_t launch_clip(const ClipParams &p, int sm_count, int max_width, cudaSt
     const int64_t cap = (int64_t)sm_count * 16;
     if (blocks > cap) blocks = cap;
     const unsigned b = (unsigned)blocks;
+    if (p.list) {
+        // first pass of the integer fast path (the caller launches the list pass afterwards with list_pass = 1)
+        if (!p.list_pass) {
+            int64_t pb = ((p.n + 1) / 2 + 127) / 128;
+            if (pb > cap) pb = cap;
+            if (pb < 1) pb = 1;
+            const unsigned pbu = (unsigned)pb;
+            switch ((p.alen + 3) / 4) {
+            case 1: k_clip_dpx<4><<<pbu, 128, 0, st>>>(p); break;
+            case 2: k_clip_dpx<8><<<pbu, 128, 0, st>>>(p); break;
+            case 3: k_clip_dpx<12><<<pbu, 128, 0, st>>>(p); break;
+            default: k_clip_dpx<16><<<pbu, 128, 0, st>>>(p); break;
+            }
+            return cudaGetLastError();
+        }
+    }
     const char *force = getenv("FXG_CLIP_PAYLOAD");   // experimentation: force the forward-payload kernels
-    if (!(force && force[0] == '1') && p.alen <= 32 && max_width <= 1024) {
+    if ((p.list_pass || !(force && force[0] == '1')) && p.alen <= 32 && max_width <= 1024) {
         const int hb = (p.alen + 3) / 4;      // adapter length bucket (multiple of 4 rows)
 #define FXG_CLIPB(HM, WT)                                                                          \
         if (max_width <= 256) k_clip_bits<HM, 256, WT><<<b, 128, 0, st>>>(p);                      \

@@ -122,6 +122,11 @@ struct ClipParams {
     int32_t *out_cut;         // may be NULL
     int64_t index_base;
     unsigned long long *counters;
+    // integer fast path (k_clip_dpx): reads that need the fp32 kernel are appended here; the second launch
+    // (list_pass = 1) runs k_clip_bits over exactly those
+    int32_t *list;
+    unsigned long long *list_count;
+    int32_t list_pass;
 };
 
 cudaError_t launch_stats(const StatsParams &p, int g, int grid, uint32_t smem_bytes, cudaStream_t st);

@@ -200,3 +200,83 @@ def test_clip_golden_fixture(ctx):
     rep = ctx.sync()
     assert rep.first_bad_read == -1
     assert emit(recs, d_len.cpu().numpy(), 64) == golden("fastx_clipper1a.out")
+
+
+# ------------------------------------------------------------------- second-generation kernels (round 1, late)
+
+@pytest.mark.parametrize("L", [1, 2, 4, 5, 31, 32, 33, 63, 64, 65, 127, 128, 129, 131, 159, 160, 200, 320, 321])
+def test_stats2_length_sweep(ctx, L):
+    """k_stats2: A scheme (32-word superblock), B scheme (8-word blocks), tail bytes, multi-pass (> 160 cycles)."""
+    n = 4099
+    seq, qual = H.synth_slab(H.SEED_BASE + 11, n, L, H.WITH_N)
+    exp, cyc = H.o_stats_hist(seq, qual, None, L, seq.shape[1], 33, L)
+    got, rep = gpu_hist(ctx, seq, qual, None, L, 33, L)
+    assert cyc == L and rep.first_bad_read == -1 and np.array_equal(got, exp)
+    # ragged lengths over the same rows, junk in the padding
+    rng = np.random.default_rng(L)
+    seq2, qual2 = seq.copy(), qual.copy()
+    lens = H.ragged(seq2, qual2, rng, min_len=1)
+    exp2, _ = H.o_stats_hist(seq2, qual2, lens, 0, seq.shape[1], 33, L)
+    got2, rep2 = gpu_hist(ctx, seq2, qual2, lens, 0, 33, L)
+    assert rep2.first_bad_read == -1 and np.array_equal(got2, exp2)
+
+
+def test_stats_kernel_generations_agree(ctx, monkeypatch):
+    """FXG_STATS_V=1 (first kernel) and the default (k_stats2) give the same table; bad reads are found by both."""
+    n, L = 40001, 150
+    seq, qual = H.synth_slab(H.SEED_BASE + 12, n, L, H.WITH_N)
+    rng = np.random.default_rng(5)
+    qual[:, :L] = rng.integers(33 - 15, 127, size=(n, L), dtype=np.uint8)     # full legal range: q' >= 64 goes to the global table
+    exp, _ = H.o_stats_hist(seq, qual, None, L, seq.shape[1], 33, L)
+    got2, _ = gpu_hist(ctx, seq, qual, None, L, 33, L)
+    monkeypatch.setenv("FXG_STATS_V", "1")
+    got1, _ = gpu_hist(ctx, seq, qual, None, L, 33, L)
+    monkeypatch.delenv("FXG_STATS_V")
+    assert np.array_equal(got2, exp) and np.array_equal(got1, exp)
+    for pos, (arr, val) in enumerate([(seq, ord("a")), (qual, 17), (seq, 0), (qual, 200), (seq, ord("X"))]):
+        a2 = arr.copy()
+        r, c = 1000 + 7 * pos, [0, 37, 148, 149, 75][pos]
+        a2[r, c] = val
+        s2, q2 = (a2, qual) if arr is seq else (seq, a2)
+        _, rep = gpu_hist(ctx, s2, q2, None, L, 33, L)
+        assert rep.first_bad_read == r
+    # Q = 64 and an offset too large for the packed range test (falls back to the first kernel)
+    for Q in (64, 90):
+        q3 = np.zeros_like(qual)
+        q3[:, :L] = rng.integers(Q - 15, min(Q + 93, 127) + 1, size=(n, L), dtype=np.uint8)
+        exp3, _ = H.o_stats_hist(seq, q3, None, L, seq.shape[1], Q, L)
+        got3, rep3 = gpu_hist(ctx, seq, q3, None, L, Q, L)
+        assert rep3.first_bad_read == -1 and np.array_equal(got3, exp3)
+
+
+@pytest.mark.parametrize("adapter", [b"A", b"ACGT", b"CCTTA", b"CCTTAAGG", b"TGGAATTCTCGG", b"AGATCGGAAGAGC", b"AGATCGGAAGAGCACA"])
+def test_clip_dpx_sweep(ctx, adapter):
+    """Integer (packed s16x2) clipper path: every adapter-length bucket, odd batch sizes, reads with N (second pass)."""
+    for L, n, kind in ((150, 5001, H.ADAPTER), (36, 3333, H.WITH_N), (256, 801, H.WITH_N), (255, 500, H.PLAIN), (1, 77, H.PLAIN),
+                       (17, 1, H.PLAIN)):
+        seq, qual = H.synth_slab(H.SEED_BASE + 13, n, L, kind)
+        rng = np.random.default_rng(len(adapter) * 1000 + L)
+        for i in rng.choice(n, max(1, n // 2), replace=False):
+            st = int(rng.integers(0, L))
+            m = min(len(adapter), L - st)
+            ad = np.frombuffer(adapter[:m], np.uint8).copy()
+            if m > 2 and rng.random() < 0.5:
+                ad[int(rng.integers(0, m))] = ord("ACGT"[int(rng.integers(0, 4))])
+            if m > 5 and rng.random() < 0.3:          # a deletion inside the adapter copy
+                cut = int(rng.integers(1, m - 1))
+                ad = np.concatenate([ad[:cut], ad[cut + 1:]])
+            seq[i, st:st + len(ad)] = ad
+        for kw in (dict(min_length=5), dict(min_length=1, discard_unknown=0, discard_clipped=1)):
+            gpu_clip(ctx, seq, qual, None, None, L, adapter, kw)
+
+
+def test_clip_generations_agree(ctx, monkeypatch):
+    """FXG_CLIP_V=1 (fp32 kernel for everything) equals the default (integer path + fp32 second pass)."""
+    n, L = 20001, 100
+    seq, qual = H.synth_slab(H.SEED_BASE + 14, n, L, H.ADAPTER)
+    seq[::7, 50] = ord("N")
+    monkeypatch.setenv("FXG_CLIP_V", "1")
+    gpu_clip(ctx, seq, qual, None, None, L, b"AGATCGGAAGAGC", dict(min_length=20))
+    monkeypatch.delenv("FXG_CLIP_V")
+    gpu_clip(ctx, seq, qual, None, None, L, b"AGATCGGAAGAGC", dict(min_length=20))
+    gpu_clip(ctx, seq, None, None, None, L, b"AGATCGGAAGAGC", dict(min_length=20, discard_unknown=0))     # FASTA
