@@ -487,8 +487,8 @@ static int stats_enqueue(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint64_
     // which needs Q-15 <= 64 so that "0 <= q' < 64" implies the reader's range check
     const char *ev = getenv("FXG_STATS_V");
     const int ver = ev ? atoi(ev) : 2;
-    const int warps2 = (t_g == 12 || t_g == 16 || t_g == 24) ? t_g : 24;
-    long rfit2 = ((long)MAX_DYN_SMEM - (long)S2_HIST_BYTES) / warps2 / stages / (2L * b->stride);
+    const int warps2 = (t_g == 12 || t_g == 16 || t_g == 20 || t_g == 24) ? t_g : 24;
+    long rfit2 = ((long)MAX_DYN_SMEM - (long)S2_HIST_BYTES - S2_DUMMY_BYTES) / warps2 / (2L * b->stride);
     if (rfit2 > S2_TILE_READS) rfit2 = S2_TILE_READS;
     const bool fast2 = ver == 2 && b->qual && !weight && rfit2 >= 4 && t_ring != 0 && q_offset - 15 <= 64 && b->n / rfit2 < (1ll << 31);
     const int g = (t_g == 1 || t_g == 2 || t_g == 4) ? t_g : 4;     // k_stats: lanes per read; 6*g warps per CTA (measured: g=4 best)
@@ -497,8 +497,8 @@ static int stats_enqueue(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint64_
     if (rfit > 32 / g) rfit = 32 / g;
     const bool fast = b->qual && !weight && rfit * g >= 8 && t_ring != 0;
     if (fast2) {
-        p.tile_reads = (int)rfit2; p.stages = stages;
-        const uint32_t smem = (uint32_t)((size_t)S2_HIST_BYTES + (size_t)warps2 * stages * 2 * b->stride * rfit2);
+        p.tile_reads = (int)rfit2; p.stages = 1;
+        const uint32_t smem = (uint32_t)((size_t)S2_HIST_BYTES + S2_DUMMY_BYTES + (size_t)warps2 * 2 * b->stride * rfit2);
         const int64_t ntiles = (b->n + rfit2 - 1) / rfit2;
         int64_t grid = ctx->sm_count;
         const int64_t need = (ntiles + warps2 - 1) / warps2;

@@ -30,11 +30,17 @@
 namespace fxg {
 namespace dpx {
 
-constexpr uint32_t G0_2 = 0xFFB0FFB0u;      // gap * 16 = -80 in both halves
-constexpr uint32_t SENT2 = 0x8AD08AD0u;     // -30000: the banned "left" candidate (reference: -100000.0f), never wins
+// All packed values carry a bias of 0x4000 per half: they stay in (0, 0x8000), so a plain 32-bit add or subtract
+// of two packed words never carries or borrows across the halves and the compiler is free to issue it on either
+// integer pipe (IADD3 on the ALU pipe or IMAD on the FMA pipe) — the packed min/max (ALU pipe only) are the
+// scarce resource of this kernel.
+constexpr int BIAS = 0x4000;
+constexpr uint32_t G0_2 = 0x3FB03FB0u;      // bias + gap * 16 (= -80) in both halves
+constexpr uint32_t GAPSUB2 = 0x00500050u;   // subtracting it adds one gap to both halves
+constexpr uint32_t SENT2 = 0u;              // the banned "left" candidate (reference: -100000.0f): below every score
 constexpr uint32_t ONE2 = 0x00010001u;
-constexpr uint32_t CM_INIT2 = 0x80008000u;  // -32768
-constexpr int BEST_INIT = -32768;
+constexpr uint32_t CM_INIT2 = 0u;
+constexpr int BEST_INIT = 0;
 constexpr int MSP_MATCH = 96, MSP_MISMATCH = 64;   // (+-1 - gap) * 16
 
 FXG_DPX_HD uint32_t pack2(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
@@ -43,7 +49,7 @@ FXG_DPX_HD uint32_t pack2(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((
 FXG_DPX_HD uint32_t vadd2(uint32_t a, uint32_t b) { return __vadd2(a, b); }
 FXG_DPX_HD uint32_t vsub2(uint32_t a, uint32_t b) { return __vsub2(a, b); }
 FXG_DPX_HD uint32_t vmax2(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
-FXG_DPX_HD uint32_t vmin2(uint32_t a, uint32_t b) { return __vmins2(a, b); }
+FXG_DPX_HD uint32_t vminu2(uint32_t a, uint32_t b) { return __vminu2(a, b); }
 FXG_DPX_HD uint32_t vaddmax2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }
 // max per half; ge_lo / ge_hi = (a >= b) per half (one VIMNMX.S16x2 with two predicate outputs)
 FXG_DPX_HD uint32_t vbmax2(uint32_t a, uint32_t b, bool &ge_hi, bool &ge_lo) { return __vibmax_s16x2(a, b, &ge_hi, &ge_lo); }
@@ -60,7 +66,11 @@ FXG_DPX_HD int16_t h_hi(uint32_t a) { return (int16_t)(a >> 16); }
 FXG_DPX_HD uint32_t vadd2(uint32_t a, uint32_t b) { return pack2(h_lo(a) + h_lo(b), h_hi(a) + h_hi(b)); }
 FXG_DPX_HD uint32_t vsub2(uint32_t a, uint32_t b) { return pack2(h_lo(a) - h_lo(b), h_hi(a) - h_hi(b)); }
 FXG_DPX_HD uint32_t vmax2(uint32_t a, uint32_t b) { return pack2(h_lo(a) > h_lo(b) ? h_lo(a) : h_lo(b), h_hi(a) > h_hi(b) ? h_hi(a) : h_hi(b)); }
-FXG_DPX_HD uint32_t vmin2(uint32_t a, uint32_t b) { return pack2(h_lo(a) < h_lo(b) ? h_lo(a) : h_lo(b), h_hi(a) < h_hi(b) ? h_hi(a) : h_hi(b)); }
+FXG_DPX_HD uint32_t vminu2(uint32_t a, uint32_t b)
+{
+    const uint32_t al = a & 0xFFFFu, bl = b & 0xFFFFu, ah = a >> 16, bh = b >> 16;
+    return (al < bl ? al : bl) | ((ah < bh ? ah : bh) << 16);
+}
 FXG_DPX_HD uint32_t vaddmax2(uint32_t a, uint32_t b, uint32_t c) { return vmax2(vadd2(a, b), c); }
 FXG_DPX_HD uint32_t vbmax2(uint32_t a, uint32_t b, bool &ge_hi, bool &ge_lo)
 {
@@ -91,7 +101,7 @@ FXG_DPX_HD uint32_t profile_word(uint32_t tc)
     return a | (c << 8) | (t << 16) | (g << 24);
 }
 // target_border[y] + gap, scaled (sequence_alignment.cpp:340-363): 0 for y <= 3, -5*(y-3) below
-FXG_DPX_HD int border_g16(int y) { return (y <= 3 ? 0 : -80 * (y - 3)) - 80; }
+FXG_DPX_HD int border_g16(int y) { return BIAS + (y <= 3 ? 0 : -80 * (y - 3)) - 80; }
 
 // One DP column for both reads.  `sel` = 0x0404 | code(read0) | code(read1) << 8 (PRMT selector: the profile
 // byte of each read — bytes 4..7 of the operand pair — zero-extended to 16 bits by byte 0 of a zero word).  gp holds g(x-1, .) on entry and g(x, .) on exit.
@@ -105,22 +115,20 @@ FXG_DPX_HD void column(int H, int x, uint32_t sel, const uint32_t (&prof)[HMAX],
 #pragma unroll
     for (int y = 0; y < HMAX; y++) {
         const uint32_t msp = prmt(0u, prof[y], sel);                // profile word as the SECOND operand: it lives in a uniform register
-        const uint32_t ul = vadd2(diag, msp);                       // FROM_UPPER_LEFT candidate
+        const uint32_t ul = diag + msp;                             // FROM_UPPER_LEFT candidate (plain add: see BIAS)
         uint32_t left = gp[y];                                      // FROM_LEFT candidate
         if (BAN && y > 3 && y - 3 > x) left = SENT2;                // sequence_alignment.cpp:388-390
         diag = gp[y];
-        // strict '>' in the reference's candidate order (diagonal, up, left): the flags are the complements of
-        // the ">=" predicates the packed max delivers for free
-        bool d_hi, d_lo, m_hi, m_lo;
-        const uint32_t m2 = vbmax2(ul, up, d_hi, d_lo);             // !d: up > diagonal
-        const uint32_t sc = vbmax2(m2, left, m_hi, m_lo);           // !m: left > max(diagonal, up)
-        if (!d_lo) a1 |= 1u << y;
-        if (!d_hi) a1 |= 0x10000u << y;
-        if (!m_lo) a2 |= 1u << y;
-        if (!m_hi) a2 |= 0x10000u << y;
+        const uint32_t m2 = vmax2(ul, up);
+        const uint32_t sc = vmax2(m2, left);
+        // strict '>' in the reference's candidate order (diagonal, up, left); the differences are >= 0 per half
+        const uint32_t t1 = vminu2(m2 - ul, ONE2);                  // 1: up > diagonal
+        const uint32_t t2 = vminu2(sc - m2, ONE2);                  // 1: left > max(diagonal, up)
+        a1 += t1 << y;
+        a2 += t2 << y;
         const bool live = (y < HMAX - 3) || (y < H);                // only the last 3 rows can lie beyond the adapter
         if (live) cm = vaddmax2(sc, pack2(15 - y, 15 - y), cm);     // first maximum of the column, row in the low 4 bits
-        up = vadd2(sc, G0_2);
+        up = sc - GAPSUB2;
         gp[y] = up;
     }
 }
@@ -168,7 +176,7 @@ FXG_DPX_HD void align_pair(const uint8_t *row0, const uint8_t *row1, int L, cons
                 else column<HMAX, false>(H, x, sel, prof, gp, a1, a2, cm);
                 org1[x] = a1; org2[x] = a2;
                 // first maximum in (x outer, y inner) order: a later column wins only with a strictly larger score
-                const int cm0 = (int)(int16_t)(cm & 0xFFFFu), cm1 = (int)(int16_t)(cm >> 16);
+                const int cm0 = (int)(cm & 0xFFFFu), cm1 = (int)(cm >> 16);
                 if (cm0 > (best0 | 15)) { best0 = cm0; bx0 = x; }
                 if (cm1 > (best1 | 15)) { best1 = cm1; bx1 = x; }
             }

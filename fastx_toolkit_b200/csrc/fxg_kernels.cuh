@@ -83,6 +83,7 @@ constexpr int ST_MAXW = 40;                       // words (4 cycles each) per p
 // second-generation layout (k_stats2): [bin = nuc*64 + q'][column 40k + w] u32 — bank = (8k + w) mod 32
 constexpr int S2_PITCH = 4 * ST_MAXW * 4;         // bytes per bin: 160 columns x u32 = 640
 constexpr int S2_HIST_BYTES = 4 * ST_QWIN * S2_PITCH;   // 256 bins: 163 840 bytes
+constexpr int S2_DUMMY_BYTES = 128;               // 32 scratch counters behind the histogram (masked-off increments land here)
 constexpr int S2_TILE_READS = 8;                  // reads per warp tile (4 lanes per read)
 
 struct StatsParams {

@@ -226,10 +226,10 @@ __device__ __forceinline__ uint32_t stats2_byte(const StatsParams &P, uint32_t c
     return 0u;
 }
 // per-byte path of one full word (rare: 'N', q' >= 64 or an illegal byte somewhere in the word)
-__device__ __noinline__ uint32_t stats2_slow_word(const StatsParams &P, uint32_t sw, uint32_t qw, int wrel, uint32_t hs_addr)
+__device__ __noinline__ uint32_t stats2_slow_word(const StatsParams &P, uint32_t sw, uint32_t qw, int wrel, int nbytes, uint32_t hs_addr)
 {
     uint32_t bad = 0;
-    for (int k = 0; k < 4; k++) bad |= stats2_byte(P, (sw >> (8 * k)) & 0xFFu, (qw >> (8 * k)) & 0xFFu, wrel, k, hs_addr);
+    for (int k = 0; k < nbytes; k++) bad |= stats2_byte(P, (sw >> (8 * k)) & 0xFFu, (qw >> (8 * k)) & 0xFFu, wrel, k, hs_addr);
     return bad;
 }
 
@@ -273,7 +273,7 @@ __device__ __forceinline__ void stats2_word(const StatsParams &P, const Stats2K 
 {
     uint32_t comb;
     if (stats2_decode(K, sw, qw, comb) == 0u) stats2_emit<DYNK>(comb, o, hs_addr, ksel, koff);
-    else bad |= stats2_slow_word(P, sw, qw, (int)(o >> 2), hs_addr);
+    else bad |= stats2_slow_word(P, sw, qw, (int)(o >> 2), 4, hs_addr);
 }
 // two full words with one branch between them
 template <bool DYNK>
@@ -288,10 +288,56 @@ __device__ __forceinline__ void stats2_pair(const StatsParams &P, const Stats2K 
         stats2_emit<DYNK>(c1, o1, hs_addr, ksel, koff);
     } else {
         if (t0 == 0u) stats2_emit<DYNK>(c0, o0, hs_addr, ksel, koff);
-        else bad |= stats2_slow_word(P, sw0, qw0, (int)(o0 >> 2), hs_addr);
+        else bad |= stats2_slow_word(P, sw0, qw0, (int)(o0 >> 2), 4, hs_addr);
         if (t1 == 0u) stats2_emit<DYNK>(c1, o1, hs_addr, ksel, koff);
-        else bad |= stats2_slow_word(P, sw1, qw1, (int)(o1 >> 2), hs_addr);
+        else bad |= stats2_slow_word(P, sw1, qw1, (int)(o1 >> 2), 4, hs_addr);
     }
+}
+
+// B scheme: two words per lane, each with vb = 0..4 (or more) valid bytes.  Bytes past the end of the read are
+// replaced by a plain 'A' with q' = 0 so that the packed test still decides, and are simply not counted (their
+// ATOMS is predicated off); vb <= 0 switches the whole word off.  One code path for full words, the last 1..3
+// bases of a read and the words beyond it.
+__device__ __forceinline__ void stats2_emit_masked(uint32_t comb, uint32_t o, int vb, uint32_t hs_addr, const uint32_t (&ksel)[4],
+                                                   const uint32_t (&koff)[4])
+{
+    const uint32_t col = hs_addr + o;
+    const uint32_t dummy = hs_addr + (uint32_t)S2_HIST_BYTES + ((o >> 2) & 31u) * 4u;   // a counter nobody reads (branch-free masking)
+#pragma unroll
+    for (int i = 0; i < 4; i++) {        // byte k = ksel & 3 counts iff k < vb
+        const uint32_t addr = prmt_raw(comb, 0u, ksel[i]) * S2_PITCH + (col + koff[i]);
+        reds_inc((int)(ksel[i] & 3u) < vb ? addr : dummy);
+    }
+}
+__device__ __forceinline__ void stats2_pair_masked(const StatsParams &P, const Stats2K &K, uint32_t sw0, uint32_t qw0, uint32_t o0, int vb0,
+                                                   uint32_t sw1, uint32_t qw1, uint32_t o1, int vb1, uint32_t hs_addr,
+                                                   const uint32_t (&ksel)[4], const uint32_t (&koff)[4], uint32_t &bad)
+{
+    const uint32_t m0 = head_mask(vb0), m1 = head_mask(vb1), lo4 = 0u - K.neg_lo4;
+    uint32_t c0, c1;
+    const uint32_t t0 = stats2_decode(K, (sw0 & m0) | (0x41414141u & ~m0), (qw0 & m0) | (lo4 & ~m0), c0);
+    const uint32_t t1 = stats2_decode(K, (sw1 & m1) | (0x41414141u & ~m1), (qw1 & m1) | (lo4 & ~m1), c1);
+    if ((t0 | t1) == 0u) {
+        stats2_emit_masked(c0, o0, vb0, hs_addr, ksel, koff);
+        stats2_emit_masked(c1, o1, vb1, hs_addr, ksel, koff);
+    } else {
+        if (t0 == 0u) stats2_emit_masked(c0, o0, vb0, hs_addr, ksel, koff);
+        else bad |= stats2_slow_word(P, sw0, qw0, (int)(o0 >> 2), vb0 < 4 ? vb0 : 4, hs_addr);
+        if (t1 == 0u) stats2_emit_masked(c1, o1, vb1, hs_addr, ksel, koff);
+        else bad |= stats2_slow_word(P, sw1, qw1, (int)(o1 >> 2), vb1 < 4 ? vb1 : 4, hs_addr);
+    }
+}
+
+// A scheme, ragged tile: the word that holds the last 1..3 bases of a read (byte order k = 0..3 as in the A scheme)
+__device__ __forceinline__ void stats2_word_masked(const StatsParams &P, const Stats2K &K, uint32_t sw, uint32_t qw, uint32_t o, int vb,
+                                                   uint32_t hs_addr, uint32_t &bad)
+{
+    const uint32_t ksel_s[4] = { 0x4440u, 0x4441u, 0x4442u, 0x4443u };
+    const uint32_t koff_s[4] = { 0u, 4u * ST_MAXW, 8u * ST_MAXW, 12u * ST_MAXW };
+    const uint32_t m = head_mask(vb), lo4 = 0u - K.neg_lo4;
+    uint32_t c;
+    if (stats2_decode(K, (sw & m) | (0x41414141u & ~m), (qw & m) | (lo4 & ~m), c) == 0u) stats2_emit_masked(c, o, vb, hs_addr, ksel_s, koff_s);
+    else bad |= stats2_slow_word(P, sw, qw, (int)(o >> 2), vb, hs_addr);
 }
 
 template <int WARPS>
@@ -305,7 +351,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_stats2(const __grid_constant_
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int S = P.stride, R = P.tile_reads;                          // R <= 8
     const uint32_t slab_bytes = (uint32_t)R * (uint32_t)S;
-    uint8_t *wbase = smem + S2_HIST_BYTES + (size_t)w * (2u * slab_bytes);
+    uint8_t *wbase = smem + S2_HIST_BYTES + S2_DUMMY_BYTES + (size_t)w * (2u * slab_bytes);
     uint64_t *bar = &full_bar[w];
     const uint32_t ntiles = (uint32_t)((P.n + R - 1) / R);            // host guarantees n / R < 2^31
     const uint32_t gw = blockIdx.x * WARPS + w, GW = gridDim.x * WARPS;
@@ -317,13 +363,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_stats2(const __grid_constant_
     }
     __syncthreads();
 
+    // lane 0 keeps the global addresses of its warp's next tile and advances them by one grid stride per tile
+    const int64_t gstep = (int64_t)GW * R * S;
+    const uint8_t *gs = P.seq + (int64_t)gw * R * S, *gq = P.qual + (int64_t)gw * R * S;
     auto issue = [&](uint32_t tile) {
-        const int64_t r0 = (int64_t)tile * R;
-        const int64_t left = P.n - r0;
-        const uint32_t bytes = (uint32_t)(left < R ? left : R) * (uint32_t)S;
+        const uint32_t bytes = (tile + 1u == ntiles) ? (uint32_t)(P.n - (int64_t)tile * R) * (uint32_t)S : slab_bytes;
         mbar_arrive_expect_tx(bar, bytes * 2u);
-        bulk_g2s(wbase, P.seq + r0 * S, bytes, bar);
-        bulk_g2s(wbase + slab_bytes, P.qual + r0 * S, bytes, bar);
+        bulk_g2s(wbase, gs, bytes, bar);
+        bulk_g2s(wbase + slab_bytes, gq, bytes, bar);
+        gs += gstep; gq += gstep;
     };
     if (lane == 0 && gw < ntiles) issue(gw);
 
@@ -380,25 +428,20 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_stats2(const __grid_constant_
 #pragma unroll
                 for (int t = 0; t < 8; t++) {
                     const uint32_t o = 128u * (uint32_t)sb + ((uoj0 + 16u * t) & 0x7Fu);
-                    if ((int)o <= lim) stats2_word<false>(P, K, lds32(srow + o), lds32(qrow + o), o, hs_addr, ksel, koff, bad);
+                    const int vb = Lp - (int)o;
+                    if (vb >= 4) stats2_word<false>(P, K, lds32(srow + o), lds32(qrow + o), o, hs_addr, ksel, koff, bad);
+                    else if (vb > 0) stats2_word_masked(P, K, lds32(srow + o), lds32(qrow + o), o, vb, hs_addr, bad);   // last 1..3 bases
                 }
             }
         }
-        for (int b8 = nsb * 4; b8 < nb8; b8++) {
+        for (int b8 = nsb * 4; b8 < nb8; b8++) {                 // the words past the superblock, the read's last 1..3 bases included
             const uint32_t o0 = 32u * (uint32_t)b8 + 4u * (uint32_t)((2 * j + grr) & 7);
             const uint32_t o1 = 32u * (uint32_t)b8 + 4u * (uint32_t)((2 * j + 1 + grr) & 7);
-            const bool v0 = (int)o0 <= lim, v1 = (int)o1 <= lim;
-            if (v0 && v1)
-                stats2_pair<true>(P, K, lds32(srow + o0), lds32(qrow + o0), o0, lds32(srow + o1), lds32(qrow + o1), o1, hs_addr, ksel, koff, bad);
-            else if (v0)
-                stats2_word<true>(P, K, lds32(srow + o0), lds32(qrow + o0), o0, hs_addr, ksel, koff, bad);
-            else if (v1)
-                stats2_word<true>(P, K, lds32(srow + o1), lds32(qrow + o1), o1, hs_addr, ksel, koff, bad);
-        }
-        // the 1..3 bases after the last full word: lane j of the read takes byte j
-        if (Lp > 0 && j < (Lp & 3)) {
-            const uint32_t o = (uint32_t)(Lp & ~3);
-            bad |= stats2_byte(P, lds8(srow + o + j), lds8(qrow + o + j), (int)(o >> 2), j, hs_addr);
+            const int vb0 = Lp - (int)o0, vb1 = Lp - (int)o1;
+            uint32_t sw0 = 0, qw0 = 0, sw1 = 0, qw1 = 0;
+            if (vb0 > 0) { sw0 = lds32(srow + o0); qw0 = lds32(qrow + o0); }
+            if (vb1 > 0) { sw1 = lds32(srow + o1); qw1 = lds32(qrow + o1); }
+            stats2_pair_masked(P, K, sw0, qw0, o0, vb0, sw1, qw1, o1, vb1, hs_addr, ksel, koff, bad);
         }
         if ((bad != 0 || lenbad) && active)
             atomicMin(&P.counters[CNT_FIRST_BAD], (unsigned long long)(P.index_base + g));
@@ -482,6 +525,7 @@ cudaError_t launch_stats2(const StatsParams &p, int warps, int grid, uint32_t sm
         k_stats2<WV><<<grid, WV * 32, smem_bytes, st>>>(p);                                          \
     } while (0)
     if (warps == 24) FXG_STATS2_LAUNCH(24);
+    else if (warps == 20) FXG_STATS2_LAUNCH(20);
     else if (warps == 16) FXG_STATS2_LAUNCH(16);
     else if (warps == 12) FXG_STATS2_LAUNCH(12);
     else return cudaErrorInvalidValue;
