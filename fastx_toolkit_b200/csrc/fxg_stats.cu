@@ -381,7 +381,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_stats2(const __grid_constant_
     const uint32_t zero = (uint32_t)((unsigned long long)P.n >> 62);       // 0, but only known at run time
     K.vlut_lo = VLUT_LO + zero; K.n6_lo = N6_LO + zero; K.neg_lo4 = zero - P.qk.lo4;
     const int passoff = 4 * P.w0, ncols = 4 * P.nw;
-    const int nsb = P.nw >> 5;                                   // full 32-word superblocks (A scheme)
+    const int nsb = P.nw > 16 ? 1 : 0;                           // A scheme over words 0..31 (nw <= ST_MAXW = 40: one superblock;
+                                                                 // short windows use the 8-word blocks of the B scheme only)
     const int nb8 = (P.nw + 7) >> 3;                             // 8-word blocks in all
     uint32_t ksel[4], koff[4];
 #pragma unroll
@@ -414,7 +415,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_stats2(const __grid_constant_
         mbar_wait(bar, parity);
         parity ^= 1u;
 
-        if (nsb) {                                               // nw <= ST_MAXW = 40: at most one superblock
+        if (nsb) {
             constexpr int sb = 0;
             if (__all_sync(0xFFFFFFFFu, lim >= 128 * sb + 124)) {   // every read of the tile fills the superblock
 #pragma unroll
