@@ -301,7 +301,7 @@ def main():
     import ctypes as C
     import threading
     import numpy as np
-    chunk_reads = 250_000
+    chunk_reads = int(os.environ.get("FXG_BENCH_CHUNK_READS", "250000"))     # tuning knobs for the e2e leg only
     exe = os.path.join(ROOT, "bin", "fxg_synth")
     if not os.path.exists(exe):
         subprocess.check_call(["make", "-C", ROOT, "tools"], stdout=subprocess.DEVNULL)
@@ -311,7 +311,7 @@ def main():
     nchunks = max(1, args.e2e_reads // chunk_reads)
     host_in = torch.empty(cb, dtype=torch.uint8).pin_memory()
     host_in.numpy()[:] = np.frombuffer(chunk, np.uint8)
-    W = 3
+    W = int(os.environ.get("FXG_BENCH_WORKERS", "3"))
     workers = []
     for _ in range(W):
         wctx = F.Context(local_rank)

@@ -23,6 +23,7 @@ struct ExtraParams {
     uint8_t *keep;              // K-ARTIFACT
     int64_t index_base;
     unsigned long long *counters;   // CNT_OUT = kept / masked reads, CNT_AUX0 = masked nucleotides
+    unsigned long long chunk_magic; // ceil(2^64 / chunks): t / chunks == __umul64hi(t, chunk_magic) for t * chunks < 2^64
 };
 
 __device__ __forceinline__ int read_len(const ExtraParams &P, int64_t i) { return P.len ? __ldg(P.len + i) : P.uniform_len; }
@@ -34,8 +35,9 @@ __global__ void __launch_bounds__(256) k_chunks(const ExtraParams P)
     const int chunks = P.stride >> 4;
     const int64_t total = P.n * chunks;
     unsigned long long masked_nuc = 0;
+    const bool one = chunks == 1;          // a 16-byte stride: chunk index == read index
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t i = t / chunks;
+        const int64_t i = one ? t : (int64_t)__umul64hi((unsigned long long)t, P.chunk_magic);   // t / chunks without the 64-bit divide
         const int c = (int)(t - i * chunks);
         const int L = read_len(P, i);
         if (L <= 0 || L > P.stride) { if (c == 0) atomicMin(&P.counters[CNT_FIRST_BAD], (unsigned long long)(P.index_base + i)); continue; }
@@ -158,6 +160,8 @@ cudaError_t launch_extra(int op, const uint8_t *seq, const uint8_t *qual, const 
     p.qk = make_qualk(q_offset, thr_q);
     p.mask4 = (uint32_t)(uint8_t)mask_char * ONES;
     p.out_seq = out_seq; p.keep = flags; p.index_base = index_base; p.counters = counters;
+    p.chunk_magic = ~0ull / (unsigned long long)(stride >> 4) + 1ull;      // stride >> 4 == 1: wraps to 0, handled below
+    if ((stride >> 4) == 1) p.chunk_magic = 0;
     if (op == 0) k_chunks<false><<<egrid(n * (stride >> 4), sm_count), 256, 0, st>>>(p);
     else if (op == 1) {
         cudaMemsetAsync(flags, 0, (size_t)n, st);
