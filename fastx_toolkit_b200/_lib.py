@@ -99,6 +99,8 @@ def lib():
         "fxg_mask_host": (i32, [vp, BP, i32, i32, i32, vp, vp, RP]),
         "fxg_artifacts_dev": (i32, [vp, BP, i32, vp, i64]),
         "fxg_artifacts_host": (i32, [vp, BP, i32, vp, RP]),
+        "fxg_has_n_dev": (i32, [vp, BP, i32, vp, i64]),
+        "fxg_has_n_host": (i32, [vp, BP, i32, vp, RP]),
         "fxg_text_new": (i32, [vp, i32, sz, C.POINTER(vp)]),
         "fxg_text_free": (None, [vp]),
         "fxg_text_run_host": (i32, [vp, i32, vp, sz, i32, i32, i32, vp, C.POINTER(TextReport)]),
@@ -310,6 +312,14 @@ class Context:
 
     def artifacts_dev(self, b, q_offset, keep, index_base=0):
         self._ck(self.L.fxg_artifacts_dev(self.h, C.byref(b), q_offset, _ptr(keep), index_base))
+
+    def has_n_dev(self, b, q_offset, has_n, index_base=0):
+        self._ck(self.L.fxg_has_n_dev(self.h, C.byref(b), q_offset, _ptr(has_n), index_base))
+
+    def has_n_host(self, b, q_offset, has_n):
+        r = Report()
+        self._ck(self.L.fxg_has_n_host(self.h, C.byref(b), q_offset, _ptr(has_n), C.byref(r)))
+        return r
 
     def mask_host(self, b, q_offset, min_quality, mask_char, out_seq, masked_flag):
         r = Report()

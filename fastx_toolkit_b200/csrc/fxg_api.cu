@@ -656,7 +656,7 @@ static int extra_enqueue(fxg_ctx *ctx, int op, const fxg_batch *b, int q_offset,
     if (b->n == 0) return FXG_OK;
     CK(ctx, launch_extra(op, b->seq, b->qual, b->len, b->uniform_len, b->stride, b->n, q_offset, thr_q, mask_char, out_seq, flags,
                          index_base, ctx->d_counters, ctx->sm_count, st));
-    ctx->launches += (op == 1) ? 2 : 1;
+    ctx->launches += (op == 1 || op == 3) ? 2 : 1;
     ctx->report.n_in += b->n;
     return FXG_OK;
 }
@@ -688,6 +688,15 @@ extern "C" int fxg_artifacts_dev(fxg_ctx *ctx, const fxg_batch *b, int q_offset,
     return extra_enqueue(ctx, 2, b, q_offset, 0, 0, NULL, keep, index_base, ctx->stream);
 }
 
+extern "C" int fxg_has_n_dev(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint8_t *has_n, int64_t index_base)
+{
+    int rc = check_batch(ctx, b, true, false, q_offset);
+    if (rc) return rc;
+    if (!has_n) return arg_error(ctx, "has_n is NULL");
+    CK(ctx, cudaSetDevice(ctx->device));
+    return extra_enqueue(ctx, 3, b, q_offset, 0, 0, NULL, has_n, index_base, ctx->stream);
+}
+
 // ---- host-buffer pipelines ---------------------------------------------------------------------------
 // Chunks of the host slab travel H2D -> kernel -> D2H on PIPE_LANES side streams, so the copy of one
 // chunk overlaps the kernel and the result copy of its neighbours (both copy engines busy).
@@ -714,7 +723,7 @@ static int64_t chunk_reads(const fxg_batch *b)
     return cr;
 }
 
-enum { HOST_TRIM, HOST_FILTER, HOST_REVCOMP, HOST_STATS, HOST_CLIP, HOST_VALIDATE, HOST_MASK, HOST_ARTIFACT };
+enum { HOST_TRIM, HOST_FILTER, HOST_REVCOMP, HOST_STATS, HOST_CLIP, HOST_VALIDATE, HOST_MASK, HOST_ARTIFACT, HOST_HASN };
 
 struct HostOp {
     int op;
@@ -743,7 +752,7 @@ static int host_pipeline(fxg_ctx *ctx, const fxg_batch *b, const HostOp &h, fxg_
         else if (h.op == HOST_REVCOMP) { o0 = (size_t)cr * S; o1 = has_qual ? (size_t)cr * S : 0; }
         else if (h.op == HOST_CLIP) { o0 = (size_t)cr * sizeof(int32_t); o1 = h.out1 ? (size_t)cr : 0; }
         else if (h.op == HOST_MASK) { o0 = (size_t)cr * S; o1 = (size_t)cr; }
-        else if (h.op == HOST_ARTIFACT) o0 = (size_t)cr;
+        else if (h.op == HOST_ARTIFACT || h.op == HOST_HASN) o0 = (size_t)cr;
         if (has_seq && (rc = lane_reserve(ctx, lane, SLOT_SEQ, (size_t)cr * S))) return rc;
         if (has_qual && (rc = lane_reserve(ctx, lane, SLOT_QUAL, (size_t)cr * S))) return rc;
         if (b->len && (rc = lane_reserve(ctx, lane, SLOT_LEN, (size_t)cr * sizeof(int32_t)))) return rc;
@@ -795,7 +804,8 @@ static int host_pipeline(fxg_ctx *ctx, const fxg_batch *b, const HostOp &h, fxg_
             if (h.out1) CK(ctx, cudaMemcpyAsync((uint8_t *)h.out1 + r0, d1, (size_t)nr, cudaMemcpyDeviceToHost, st));
             break;
         case HOST_ARTIFACT:
-            if ((rc = extra_enqueue(ctx, 2, &db, h.q_offset, 0, 0, NULL, (uint8_t *)d0, r0, st))) return rc;
+        case HOST_HASN:
+            if ((rc = extra_enqueue(ctx, h.op == HOST_ARTIFACT ? 2 : 3, &db, h.q_offset, 0, 0, NULL, (uint8_t *)d0, r0, st))) return rc;
             CK(ctx, cudaMemcpyAsync((uint8_t *)h.out0 + r0, d0, (size_t)nr, cudaMemcpyDeviceToHost, st));
             break;
         }
@@ -881,6 +891,16 @@ extern "C" int fxg_mask_host(fxg_ctx *ctx, const fxg_batch *b, int q_offset, int
     if (!out_seq) return arg_error(ctx, "out_seq is NULL");
     HostOp h = {};
     h.op = HOST_MASK; h.q_offset = q_offset; h.a0 = min_quality; h.a1 = mask_char; h.out0 = out_seq; h.out1 = masked_flag;
+    return host_pipeline(ctx, b, h, report);
+}
+
+extern "C" int fxg_has_n_host(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint8_t *has_n, fxg_report *report)
+{
+    int rc = check_batch(ctx, b, true, false, q_offset);
+    if (rc) return rc;
+    if (!has_n) return arg_error(ctx, "has_n is NULL");
+    HostOp h = {};
+    h.op = HOST_HASN; h.q_offset = q_offset; h.out0 = has_n;
     return host_pipeline(ctx, b, h, report);
 }
 

@@ -4,6 +4,7 @@
 //   K-VALIDATE  reader checks only                  src/libfastx/fastx.c:45-54,118-135,361-362
 //   K-MASK      fastq_masker body                   src/fastq_masker/fastq_masker.c:92-107
 //   K-ARTIFACT  fastx_artifacts_filter decision     src/fastx_artifacts_filter/fastx_artifacts_filter.c:56-114
+//   K-HASN      fastq_to_fasta's test  src/fastq_to_fasta/fastq_to_fasta.c:79-82  strchr(nucleotides,'N')
 //
 // Streaming byte kernels on the same SoA slabs; thread-per-16-byte-chunk (mask, validate) or G lanes per read
 // (artifact counts) with plain coalesced global loads — HBM-bound, no shared-memory staging needed at 1-2 passes/byte.
@@ -28,10 +29,12 @@ struct ExtraParams {
 
 __device__ __forceinline__ int read_len(const ExtraParams &P, int64_t i) { return P.len ? __ldg(P.len + i) : P.uniform_len; }
 
-// one thread per 16-byte chunk: validation (+ masking when MASK)
-template <bool MASK>
+// one thread per 16-byte chunk: validation (+ masking when MODE == 1, + "read holds an N" flag when MODE == 3)
+template <int MODE>
 __global__ void __launch_bounds__(256) k_chunks(const ExtraParams P)
 {
+    constexpr bool MASK = MODE == 1;
+    constexpr bool HASN = MODE == 3;
     const int chunks = P.stride >> 4;
     const int64_t total = P.n * chunks;
     unsigned long long masked_nuc = 0;
@@ -49,11 +52,15 @@ __global__ void __launch_bounds__(256) k_chunks(const ExtraParams P)
         if (P.qual) q4 = __ldg(reinterpret_cast<const uint4 *>(P.qual + off));
         uint32_t sw[4] = { s4.x, s4.y, s4.z, s4.w };
         const uint32_t qw[4] = { q4.x, q4.y, q4.z, q4.w };
-        uint32_t bad = 0, any_masked = 0;
+        uint32_t bad = 0, any_masked = 0, has_n = 0;
 #pragma unroll
         for (int w = 0; w < 4; w++) {
             const uint32_t m = head_mask(nb - 4 * w);
             bad |= seq_bad_bits(sw[w]) & m;
+            if (HASN) {                                   // zero byte of (x ^ "NNNN"), exact for any byte value
+                const uint32_t z = sw[w] ^ 0x4E4E4E4Eu;
+                has_n |= ~(((z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | z) & HI & m;
+            }
             if (P.qual) {
                 const uint32_t xh = qw[w] | HI;
                 bad |= qual_bad_bits(qw[w], xh, P.qk) & HI & m;
@@ -73,6 +80,7 @@ __global__ void __launch_bounds__(256) k_chunks(const ExtraParams P)
             *reinterpret_cast<uint4 *>(P.out_seq + off) = make_uint4(sw[0], sw[1], sw[2], sw[3]);
             if (any_masked) P.keep[i] = 1;          // "this read had a masked base" flag (benign race: all writers store 1)
         }
+        if (HASN && has_n) P.keep[i] = 1;           // same idiom: flags start at 0, every writer stores 1
     }
     if (MASK) {
         masked_nuc = __reduce_add_sync(0xffffffffu, (unsigned)masked_nuc) ;
@@ -150,7 +158,7 @@ __global__ void k_count_flags(const uint8_t *flags, int64_t n, unsigned long lon
 
 static unsigned egrid(int64_t n, int sm) { int64_t b = (n + 255) / 256; if (b > (int64_t)sm * 32) b = (int64_t)sm * 32; if (b < 1) b = 1; return (unsigned)b; }
 
-// op: 0 validate, 1 mask, 2 artifacts
+// op: 0 validate, 1 mask, 2 artifacts, 3 has-N flags
 cudaError_t launch_extra(int op, const uint8_t *seq, const uint8_t *qual, const int32_t *len, int uniform_len, int stride, int64_t n,
                          int q_offset, int thr_q, int mask_char, uint8_t *out_seq, uint8_t *flags, int64_t index_base,
                          unsigned long long *counters, int sm_count, cudaStream_t st)
@@ -162,10 +170,11 @@ cudaError_t launch_extra(int op, const uint8_t *seq, const uint8_t *qual, const 
     p.out_seq = out_seq; p.keep = flags; p.index_base = index_base; p.counters = counters;
     p.chunk_magic = ~0ull / (unsigned long long)(stride >> 4) + 1ull;      // stride >> 4 == 1: wraps to 0, handled below
     if ((stride >> 4) == 1) p.chunk_magic = 0;
-    if (op == 0) k_chunks<false><<<egrid(n * (stride >> 4), sm_count), 256, 0, st>>>(p);
-    else if (op == 1) {
+    if (op == 0) k_chunks<0><<<egrid(n * (stride >> 4), sm_count), 256, 0, st>>>(p);
+    else if (op == 1 || op == 3) {
         cudaMemsetAsync(flags, 0, (size_t)n, st);
-        k_chunks<true><<<egrid(n * (stride >> 4), sm_count), 256, 0, st>>>(p);
+        if (op == 1) k_chunks<1><<<egrid(n * (stride >> 4), sm_count), 256, 0, st>>>(p);
+        else k_chunks<3><<<egrid(n * (stride >> 4), sm_count), 256, 0, st>>>(p);
         k_count_flags<<<egrid(n, sm_count), 256, 0, st>>>(flags, n, &counters[CNT_OUT]);
     } else k_artifact<<<egrid(n * 4, sm_count), 256, 0, st>>>(p);
     return cudaGetLastError();

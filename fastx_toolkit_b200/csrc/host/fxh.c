@@ -590,11 +590,17 @@ static inline void writer_room(fxh_writer *w, size_t n)
 
 void fxh_write_record(fxh_writer *w, const fxh_batch *b, int64_t i, const uint8_t *seq_row, const uint8_t *qual_row, int32_t out_len)
 {
-    const size_t nl = (size_t)b->name_len[i], n2l = (size_t)b->name2_len[i], L = (size_t)out_len;
+    fxh_write_record_named(w, b, i, seq_row, qual_row, out_len, b->name[i], b->name_len[i]);
+}
+
+void fxh_write_record_named(fxh_writer *w, const fxh_batch *b, int64_t i, const uint8_t *seq_row, const uint8_t *qual_row, int32_t out_len,
+                            const char *name, int32_t name_len)
+{
+    const size_t nl = (size_t)name_len, n2l = (size_t)b->name2_len[i], L = (size_t)out_len;
     writer_room(w, nl + n2l + L * (b->numeric_qual ? 5 : 1) + L + 16);
     char *p = w->buf + w->len;
     *p++ = w->fastq ? '@' : '>';
-    memcpy(p, b->name[i], nl); p += nl; *p++ = '\n';
+    memcpy(p, name, nl); p += nl; *p++ = '\n';
     memcpy(p, seq_row, L); p += L; *p++ = '\n';
     if (w->fastq) {
         *p++ = '+';

@@ -83,6 +83,9 @@ fxh_writer *fxh_writer_open(const char *filename, int fastq, int compress);
 /* emit record i of b with the sequence (and quality) cut to out_len; seq/qual rows may come from another slab */
 void        fxh_write_record(fxh_writer *w, const fxh_batch *b, int64_t i, const uint8_t *seq_row, const uint8_t *qual_row,
                              int32_t out_len);
+/* same, with another identifier line (fastq_to_fasta -r, fastq_to_fasta.c:84-85) */
+void        fxh_write_record_named(fxh_writer *w, const fxh_batch *b, int64_t i, const uint8_t *seq_row, const uint8_t *qual_row,
+                                   int32_t out_len, const char *name, int32_t name_len);
 void        fxh_write_raw(fxh_writer *w, const char *text, size_t bytes, int64_t records);   /* already formatted */
 void        fxh_writer_close(fxh_writer *w);
 size_t      fxh_num_output_sequences(const fxh_writer *w);

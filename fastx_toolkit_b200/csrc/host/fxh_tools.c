@@ -860,6 +860,62 @@ static int main_artifacts(int argc, char **argv)
     return 0;
 }
 
+/* ================================================================================ fastq_to_fasta
+ * src/fastq_to_fasta/fastq_to_fasta.c:50-103: FASTQ in, FASTA out; reads with an 'N' are dropped unless -n (the test runs on
+ * the GPU, K-HASN, fused with the reader's checks); -r renames the identifiers to the running output count. */
+static int f2a_rename = 0, f2a_discard_n = 1;
+static int f2a_parse(int optind_, int optc, char *optarg_)
+{
+    (void)optind_; (void)optarg_;
+    switch (optc) {
+    case 'n': f2a_discard_n = 0; break;
+    case 'r': f2a_rename = 1; break;
+    default: errx(1, "Unknown argument (%c)", optc);
+    }
+    return 1;
+}
+
+static int main_fastq_to_fasta(int argc, char **argv)
+{
+    fxh_parse_cmdline(argc, argv, "rn", f2a_parse, fxh_usage_fastq_to_fasta);
+    fxh_reader *rd = fxh_reader_open(fxh_input_filename(), FXH_FASTQ_ONLY, fxh_q_offset(), 0);
+    fxh_writer *wr = fxh_writer_open(fxh_output_filename(), 0 /* FASTA */, fxh_compress_output());
+    fxg_ctx *ctx = fxh_gpu_open();
+    pbuf fp = { 0, 0 };
+    fxh_batch *b;
+    while ((b = fxh_reader_next(rd, fxh_batch_reads())) != NULL) {
+        uint8_t *has_n = (uint8_t *)pbuf_get(&fp, (size_t)b->n);
+        fxg_batch gb = fxh_as_fxg_batch(b, 1);
+        fxg_report rep;
+        fxh_gpu_check(ctx, fxg_has_n_host(ctx, &gb, batch_q(b), has_n, &rep), "fxg_has_n_host");
+        const int64_t lim = rep.first_bad_read >= 0 ? rep.first_bad_read : b->n;
+        for (int64_t i = 0; i < lim; i++) {
+            if (f2a_discard_n && has_n[i]) continue;
+            const uint8_t *srow = b->seq + (size_t)i * b->stride;
+            if (f2a_rename) {
+                char num[32];
+                const int nl = snprintf(num, sizeof(num), "%zu", fxh_num_output_reads(wr) + 1);
+                fxh_write_record_named(wr, b, i, srow, NULL, b->len[i], num, nl);
+            } else {
+                fxh_write_record(wr, b, i, srow, NULL, b->len[i]);
+            }
+        }
+        if (rep.first_bad_read >= 0) { fxh_writer_close(wr); fxh_die_bad_record(rd, b, rep.first_bad_read); }
+    }
+    fxh_writer_close(wr);
+    if (fxh_verbose()) {
+        FILE *f = fxh_report_file();
+        fprintf(f, "Input: %zu reads.\n", fxh_num_input_reads(rd));
+        fprintf(f, "Output: %zu reads.\n", fxh_num_output_reads(wr));
+        if (f2a_discard_n) {
+            size_t discarded = fxh_num_input_reads(rd) - fxh_num_output_reads(wr);
+            fprintf(f, "discarded %zu (%zu%%) low-quality reads.\n", discarded, (discarded * 100) / fxh_num_input_reads(rd));
+        }
+    }
+    fxg_destroy(ctx);
+    return 0;
+}
+
 /* ================================================================================ dispatch */
 int main(int argc, char **argv)
 {
@@ -874,7 +930,8 @@ int main(int argc, char **argv)
     if (!strcmp(name, "fastx_trimmer")) return main_fastx_trimmer(argc, argv);
     if (!strcmp(name, "fastq_masker")) return main_masker(argc, argv);
     if (!strcmp(name, "fastx_artifacts_filter")) return main_artifacts(argc, argv);
+    if (!strcmp(name, "fastq_to_fasta")) return main_fastq_to_fasta(argc, argv);
     fprintf(stderr, "%s: multi-call binary; invoke it as fastq_quality_trimmer, fastq_quality_filter, fastx_reverse_complement, "
-                    "fastx_clipper, fastx_collapser, fastx_quality_stats, fastx_trimmer, fastq_masker or fastx_artifacts_filter\n", name);
+                    "fastx_clipper, fastx_collapser, fastx_quality_stats, fastx_trimmer, fastq_masker, fastx_artifacts_filter or fastq_to_fasta\n", name);
     return 1;
 }

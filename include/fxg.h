@@ -202,6 +202,12 @@ int fxg_mask_host(fxg_ctx *ctx, const fxg_batch *b, int q_offset, int min_qualit
 int fxg_artifacts_dev (fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint8_t *keep_dev, int64_t index_base);
 int fxg_artifacts_host(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint8_t *keep_host, fxg_report *report);
 
+/* ---- (f-4) fastq_to_fasta loop body (src/fastq_to_fasta/fastq_to_fasta.c:79-82): `strchr(fastx.nucleotides,'N') != NULL`
+ * with the reader's checks fused (fastx.c:45-54,118-135).  has_n[i] = 1 iff read i holds an 'N'; report.n_out = such reads.
+ * Dropping the quality line and renaming (-r, fastq_to_fasta.c:84-85) are writer-side and stay on the host. */
+int fxg_has_n_dev (fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint8_t *has_n_dev, int64_t index_base);
+int fxg_has_n_host(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint8_t *has_n_host, fxg_report *report);
+
 /* ---- next to the loop: FASTQ text in, FASTQ text out, parsed / packed / emitted on the GPU --------
  * fxg_text_run_host(): `text_host` holds raw 4-line FASTQ (any number of bytes; an incomplete trailing record is left
  * alone, see consumed_bytes).  The GPU indexes the lines (fastx.c:324-378 fgets/chomp), checks the record structure

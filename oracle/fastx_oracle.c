@@ -711,6 +711,18 @@ void fxo_artifacts_batch(const uint8_t *seq, const int32_t *len, int uniform_len
     }
 }
 
+/* src/fastq_to_fasta/fastq_to_fasta.c:79-82: the discard test of fastq_to_fasta */
+void fxo_has_n_batch(const uint8_t *seq, const int32_t *len, int uniform_len, int stride, int64_t n, uint8_t *has_n)
+{
+    for (int64_t i = 0; i < n; i++) {
+        const int L = rec_len(len, uniform_len, i);
+        uint8_t f = 0;
+        for (int k = 0; k < L; k++)
+            if (seq[i * (int64_t)stride + k] == 'N') { f = 1; break; }
+        has_n[i] = f;
+    }
+}
+
 /* src/fastx_trimmer/fastx_trimmer.c:120-148 — pointer arithmetic only */
 int fxo_fastx_trimmer_record(int len, int first, int last, int trim_last, int min_len, int *start)
 {

@@ -119,6 +119,8 @@ void fxo_mask_batch(const uint8_t *seq, const uint8_t *qual, const int32_t *len,
                     int q_offset, int min_quality, int mask_char, uint8_t *out_seq, uint8_t *masked_flag,
                     int64_t *masked_reads, int64_t *masked_bases);
 void fxo_artifacts_batch(const uint8_t *seq, const int32_t *len, int uniform_len, int stride, int64_t n, uint8_t *keep);
+/* (f-4) fastq_to_fasta (src/fastq_to_fasta/fastq_to_fasta.c:79-82): has_n[i] = strchr(nucleotides, 'N') != NULL */
+void fxo_has_n_batch(const uint8_t *seq, const int32_t *len, int uniform_len, int stride, int64_t n, uint8_t *has_n);
 /* first/last: -f/-l (1-based, last 0 = none); trim_last/min_len: -t/-m.  Returns the new length (>=0) and *start, or -1 = discard */
 int fxo_fastx_trimmer_record(int len, int first, int last, int trim_last, int min_len, int *start);
 

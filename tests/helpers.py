@@ -67,6 +67,7 @@ def oracle():
     L.fxo_clip_batch.argtypes = [u8p, i32p, i32p, C.c_int, C.c_int, C.c_int64, u8p, C.c_int, C.POINTER(FxoClipOpts), i32p, u8p, i32p]
     L.fxo_mask_batch.argtypes = [u8p, u8p, i32p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, u8p, u8p, i64p, i64p]
     L.fxo_artifacts_batch.argtypes = [u8p, i32p, C.c_int, C.c_int, C.c_int64, u8p]
+    L.fxo_has_n_batch.argtypes = [u8p, i32p, C.c_int, C.c_int, C.c_int64, u8p]
     L.fxo_fastx_trimmer_record.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
     L.fxo_hash_bytes.restype = C.c_uint64
     L.fxo_hash_bytes.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64]
@@ -139,6 +140,13 @@ def o_mask(seq, qual, lens, L, stride, Q, q, ch):
     oracle().fxo_mask_batch(_p(seq, u8p), _p(qual, u8p), _p(lens, i32p), L, stride, n, Q, q, ch, _p(out, u8p), _p(flag, u8p),
                             C.byref(mr), C.byref(mb))
     return out, flag, mr.value, mb.value
+
+
+def o_has_n(seq, lens, L, stride):
+    n = seq.shape[0]
+    f = np.empty(n, np.uint8)
+    oracle().fxo_has_n_batch(_p(seq, u8p), _p(lens, i32p), L, stride, n, _p(f, u8p))
+    return f
 
 
 def o_artifacts(seq, lens, L, stride):

@@ -10,7 +10,18 @@ from helpers import GOLDEN
 from test_oracle_golden import emit, golden
 from test_tools_cli import BIN, assert_same, needs_bin, needs_ref, run_tool
 
-EXTRA = ["fastx_trimmer", "fastq_masker", "fastx_artifacts_filter"]
+EXTRA = ["fastx_trimmer", "fastq_masker", "fastx_artifacts_filter", "fastq_to_fasta"]
+
+
+def fastq_to_fasta_expected(recs, has_n, keep_n, rename):
+    """src/fastq_to_fasta/fastq_to_fasta.c:79-88 over parsed records, with the oracle's N flags"""
+    out, k = [], 0
+    for (name, s, _n2, _q), f in zip(recs, has_n):
+        if f and not keep_n:
+            continue
+        k += 1
+        out.append(b">" + (b"%d" % k if rename else name) + b"\n" + s + b"\n")
+    return b"".join(out)
 
 
 def fastx_trimmer_expected(recs, first, last, t, m, q_offset):
@@ -39,6 +50,12 @@ def test_oracle_golden_extra():
     oseq, flag, mr, mb = H.o_mask(seq, qual, lens, 0, stride, 64, 29, ord("x"))
     recs2 = [(r[0], oseq[i, :lens[i]].tobytes(), r[2], r[3]) for i, r in enumerate(recs)]
     assert emit(recs2, lens, 64) == golden("fastq_masker.out")
+    # fastq_to_fasta: the .xml's two tests are (default flags) and (-n -r) (galaxy/tools/fastx_toolkit/fastq_to_fasta.xml:28-43)
+    recs = H.read_fastx(os.path.join(GOLDEN, "fastq_to_fasta1.fastq"))
+    seq, qual, lens, stride, _ = H.slab_from_records(recs, 64)
+    fl = H.o_has_n(seq, lens, 0, stride)
+    assert fastq_to_fasta_expected(recs, fl, False, False) == golden("fastq_to_fasta1a.out")
+    assert fastq_to_fasta_expected(recs, fl, True, True) == golden("fastq_to_fasta1b.out")
     for fin, fout in (("fastx_artifacts1.fasta", "fastx_artifacts1.out"), ("fastx_artifacts2.fastq", "fastx_artifacts2.out")):
         recs = H.read_fastx(os.path.join(GOLDEN, fin))
         seq, qual, lens, stride, _ = H.slab_from_records(recs, 33)
@@ -58,6 +75,9 @@ def test_extra_usage_and_flag_errors(tool, tmp_path):
     if tool == "fastx_trimmer":
         for a in (["-f", "0"], ["-l", "25000"], ["-t", "0"], ["-m", "0"], ["-f", "2", "-t", "3"]):
             assert_same(tool, a + ["-i", str(fa)])
+    if tool == "fastq_to_fasta":
+        assert_same(tool, ["-i", str(fa)])      # FASTA into a FASTQ-only tool
+        assert_same(tool, ["-x"])
     if tool == "fastq_masker":
         assert_same(tool, ["-q", "-41", "-i", str(fa)])
         assert_same(tool, ["-r", "xy", "-i", str(fa)])
@@ -119,6 +139,21 @@ def test_extra_kernels_vs_oracle():
         kh = np.empty(n, np.uint8)
         rep = ctx.artifacts_host(ctx.batch(seq, qual, n, stride, L if lens is None else 0, lens), 33, kh)
         assert np.array_equal(kh, exp)
+        # K-HASN (fastq_to_fasta's discard test), junk in the padding must not count
+        jseq = seq.copy()
+        if lens is not None:
+            for i in range(0, n, 3):
+                jseq[i, int(lens[i]):] = ord("N")
+        djs = torch.from_numpy(jseq).cuda()
+        fl = torch.full((n,), 7, dtype=torch.uint8, device="cuda")
+        ctx.report_reset()
+        ctx.has_n_dev(ctx.batch(djs, dqual, n, stride, L if lens is None else 0, dlens), 33, fl)
+        rep = ctx.sync()
+        efl = H.o_has_n(jseq, lens, L, stride)
+        assert np.array_equal(fl.cpu().numpy(), efl) and rep.n_out == int(efl.sum()) and rep.first_bad_read == -1
+        fh = np.empty(n, np.uint8)
+        rep = ctx.has_n_host(ctx.batch(jseq, None, n, stride, L if lens is None else 0, lens), 33, fh)
+        assert np.array_equal(fh, efl) and rep.n_in == n
     ctx.close()
 
 
@@ -132,7 +167,9 @@ def test_extra_binaries_vs_reference(tmp_path):
             ("fastx_trimmer", ["-t", "2", "-m", "16"], "fastx_trimmer_from_end1.fasta", "fastx_trimmer_from_end1.out"),
             ("fastq_masker", ["-Q", "64", "-q", "29", "-r", "x"], "fastq_masker.fastq", "fastq_masker.out"),
             ("fastx_artifacts_filter", [], "fastx_artifacts1.fasta", "fastx_artifacts1.out"),
-            ("fastx_artifacts_filter", [], "fastx_artifacts2.fastq", "fastx_artifacts2.out")):
+            ("fastx_artifacts_filter", [], "fastx_artifacts2.fastq", "fastx_artifacts2.out"),
+            ("fastq_to_fasta", ["-Q", "64"], "fastq_to_fasta1.fastq", "fastq_to_fasta1a.out"),
+            ("fastq_to_fasta", ["-Q", "64", "-n", "-r"], "fastq_to_fasta1.fastq", "fastq_to_fasta1b.out")):
         rc, out, errs = run_tool(os.path.join(BIN, tool), args + ["-i", os.path.join(G, fin)])
         assert rc == 0 and out == open(os.path.join(G, fout), "rb").read(), (tool, args, errs)
         assert_same(tool, args + ["-v", "-i", os.path.join(G, fin)])
@@ -155,6 +192,10 @@ def test_extra_binaries_vs_reference(tmp_path):
             assert_same("fastq_masker", args + ["-i", fq])
         assert_same("fastx_artifacts_filter", ["-v", "-i", fq])
         assert_same("fastx_artifacts_filter", ["-v", "-i", fa])
+        for args in (["-v"], ["-n", "-v"], ["-r"], ["-n", "-r", "-v"], ["-z", "-r"]):
+            assert_same("fastq_to_fasta", args + ["-i", fq])
+        assert_same("fastq_to_fasta", ["-v", "-r", "-i", fq, "-o", str(tmp_path / "o.fa")])
+        assert_same("fastq_to_fasta", ["-n", "-i", os.path.join(G, "fastx_rev_comp2.fastq")])                # numeric qualities
         assert_same("fastx_trimmer", ["-f", "2", "-l", "9", "-i", os.path.join(G, "fastx_rev_comp2.fastq")])   # numeric qualities
         assert_same("fastq_masker", ["-q", "20", "-v", "-i", os.path.join(G, "fastx_rev_comp2.fastq")])
         # a broken record: prefix of the output, then the reference's message
@@ -162,7 +203,7 @@ def test_extra_binaries_vs_reference(tmp_path):
         lines[4 * 20000 + 1] = b"ACGTxACGT"; lines[4 * 20000 + 3] = b"IIIIIIIII"
         bad = str(tmp_path / "bad.fq")
         open(bad, "wb").write(b"\n".join(lines) + b"\n")
-        for tool, args in (("fastx_trimmer", ["-f", "2"]), ("fastq_masker", []), ("fastx_artifacts_filter", [])):
+        for tool, args in (("fastx_trimmer", ["-f", "2"]), ("fastq_masker", []), ("fastx_artifacts_filter", []), ("fastq_to_fasta", ["-r"])):
             assert_same(tool, args + ["-i", bad])
     finally:
         os.environ.pop("FASTX_BATCH_READS", None)
