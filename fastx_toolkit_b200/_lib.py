@@ -21,6 +21,12 @@ class Batch(C.Structure):
                 ("uniform_len", C.c_int32), ("stride", C.c_int32), ("n", C.c_int64)]
 
 
+class BarcodeTable(C.Structure):
+    """struct fxg_barcode_table (entries / entry_len are host arrays kept alive by the caller)"""
+    _fields_ = [("entries", C.c_void_p), ("entry_len", C.c_void_p), ("n_entries", C.c_int32), ("barcode_len", C.c_int32),
+                ("allowed_mismatches", C.c_int32)]
+
+
 class ClipOpts(C.Structure):
     """struct fxg_clip_opts"""
     _fields_ = [("adapter", C.c_char_p), ("min_length", C.c_int32), ("keep_delta", C.c_int32),
@@ -99,6 +105,8 @@ def lib():
         "fxg_mask_host": (i32, [vp, BP, i32, i32, i32, vp, vp, RP]),
         "fxg_artifacts_dev": (i32, [vp, BP, i32, vp, i64]),
         "fxg_artifacts_host": (i32, [vp, BP, i32, vp, RP]),
+        "fxg_barcode_dev": (i32, [vp, BP, vp, vp]),
+        "fxg_barcode_host": (i32, [vp, BP, vp, vp, RP]),
         "fxg_has_n_dev": (i32, [vp, BP, i32, vp, i64]),
         "fxg_has_n_host": (i32, [vp, BP, i32, vp, RP]),
         "fxg_text_new": (i32, [vp, i32, sz, C.POINTER(vp)]),
@@ -312,6 +320,14 @@ class Context:
 
     def artifacts_dev(self, b, q_offset, keep, index_base=0):
         self._ck(self.L.fxg_artifacts_dev(self.h, C.byref(b), q_offset, _ptr(keep), index_base))
+
+    def barcode_dev(self, b, table, best):
+        self._ck(self.L.fxg_barcode_dev(self.h, C.byref(b), C.byref(table), _ptr(best)))
+
+    def barcode_host(self, b, table, best):
+        r = Report()
+        self._ck(self.L.fxg_barcode_host(self.h, C.byref(b), C.byref(table), _ptr(best), C.byref(r)))
+        return r
 
     def has_n_dev(self, b, q_offset, has_n, index_base=0):
         self._ck(self.L.fxg_has_n_dev(self.h, C.byref(b), q_offset, _ptr(has_n), index_base))

@@ -697,6 +697,83 @@ extern "C" int fxg_has_n_dev(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uin
     return extra_enqueue(ctx, 3, b, q_offset, 0, 0, NULL, has_n, index_base, ctx->stream);
 }
 
+// ---- (f-4) barcode splitter ------------------------------------------------------------------------------
+static int barcode_check(fxg_ctx *ctx, const fxg_batch *b, const fxg_barcode_table *t)
+{
+    if (!ctx) return FXG_ERR_ARG;
+    if (!b || !t || !b->seq || !b->len) return arg_error(ctx, "barcode: fragments need seq and len");
+    if (b->n < 0 || b->stride <= 0 || (b->stride & 15) || b->stride > BC_MAX_STRIDE) {
+        snprintf(ctx->err, sizeof(ctx->err), "barcode: stride %d unsupported (16..%d, multiple of 16)", b->stride, BC_MAX_STRIDE);
+        return FXG_ERR_UNSUPPORTED;
+    }
+    if (((uintptr_t)b->seq & 15)) return arg_error(ctx, "slab base must be 16-byte aligned");
+    if (!t->entries || !t->entry_len || t->n_entries <= 0 || t->barcode_len <= 0 || t->barcode_len > b->stride || t->allowed_mismatches < 0)
+        return arg_error(ctx, "barcode table");
+    return FXG_OK;
+}
+
+// fragments already in device memory; runs on `st`
+static int barcode_enqueue(fxg_ctx *ctx, const uint8_t *dfrag, const int32_t *dlen, int64_t n, int stride, const fxg_barcode_table *t,
+                           int32_t *dbest, cudaStream_t st)
+{
+    if (n == 0) return FXG_OK;
+    const size_t tb = (size_t)t->n_entries * stride, lb = (size_t)t->n_entries * sizeof(int32_t);
+    const size_t off_len = (tb + 15) & ~(size_t)15, off_mm = (off_len + lb + 15) & ~(size_t)15;
+    void *scratch = NULL;
+    CK(ctx, cudaMallocAsync(&scratch, off_mm + (size_t)n * sizeof(int32_t), st));
+    CK(ctx, cudaMemcpyAsync(scratch, t->entries, tb, cudaMemcpyHostToDevice, st));
+    CK(ctx, cudaMemcpyAsync((char *)scratch + off_len, t->entry_len, lb, cudaMemcpyHostToDevice, st));
+    BarcodeParams p;
+    memset(&p, 0, sizeof(p));
+    p.frag = dfrag; p.flen = dlen; p.n = n; p.stride = stride;
+    p.entries = (const uint8_t *)scratch; p.elen = (const int32_t *)((char *)scratch + off_len);
+    p.barcode_len = t->barcode_len; p.allowed = t->allowed_mismatches;
+    p.best_mm = (int32_t *)((char *)scratch + off_mm); p.best = dbest;
+    for (int e0 = 0; e0 < t->n_entries; e0 += BC_TILE_ENTRIES) {       // long lists: several launches, running minimum
+        p.e0 = e0; p.e1 = e0 + BC_TILE_ENTRIES < t->n_entries ? e0 + BC_TILE_ENTRIES : t->n_entries;
+        p.last = p.e1 == t->n_entries;
+        CK(ctx, launch_barcode(p, ctx->sm_count, st));
+        ctx->launches++;
+    }
+    CK(ctx, cudaFreeAsync(scratch, st));
+    ctx->report.n_in += n;
+    return FXG_OK;
+}
+
+extern "C" int fxg_barcode_dev(fxg_ctx *ctx, const fxg_batch *b, const fxg_barcode_table *t, int32_t *best)
+{
+    int rc = barcode_check(ctx, b, t);
+    if (rc) return rc;
+    if (!best) return arg_error(ctx, "best is NULL");
+    CK(ctx, cudaSetDevice(ctx->device));
+    return barcode_enqueue(ctx, b->seq, b->len, b->n, b->stride, t, best, ctx->stream);
+}
+
+extern "C" int fxg_barcode_host(fxg_ctx *ctx, const fxg_batch *b, const fxg_barcode_table *t, int32_t *best, fxg_report *report)
+{
+    int rc = barcode_check(ctx, b, t);
+    if (rc) return rc;
+    if (!best) return arg_error(ctx, "best is NULL");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if ((rc = fxg_report_reset(ctx))) return rc;
+    cudaStream_t st = ctx->lane_stream[0];
+    if (b->n > 0) {
+        const size_t fb = (size_t)b->n * b->stride, lb = (size_t)b->n * sizeof(int32_t);
+        void *d = NULL;
+        CK(ctx, cudaMallocAsync(&d, fb + 2 * lb, st));
+        uint8_t *dfrag = (uint8_t *)d;
+        int32_t *dlen = (int32_t *)((char *)d + fb), *dbest = dlen + b->n;
+        CK(ctx, cudaMemcpyAsync(dfrag, b->seq, fb, cudaMemcpyHostToDevice, st));
+        CK(ctx, cudaMemcpyAsync(dlen, b->len, lb, cudaMemcpyHostToDevice, st));
+        if ((rc = barcode_enqueue(ctx, dfrag, dlen, b->n, b->stride, t, dbest, st))) return rc;
+        CK(ctx, cudaMemcpyAsync(best, dbest, lb, cudaMemcpyDeviceToHost, st));
+        CK(ctx, cudaFreeAsync(d, st));
+    }
+    if ((rc = refresh_report(ctx, st))) return rc;
+    if (report) *report = ctx->report;
+    return FXG_OK;
+}
+
 // ---- host-buffer pipelines ---------------------------------------------------------------------------
 // Chunks of the host slab travel H2D -> kernel -> D2H on PIPE_LANES side streams, so the copy of one
 // chunk overlaps the kernel and the result copy of its neighbours (both copy engines busy).

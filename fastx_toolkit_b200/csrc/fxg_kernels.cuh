@@ -130,6 +130,27 @@ struct ClipParams {
     int32_t list_pass;
 };
 
+// ---- K-BARCODE (fxg_barcode.cu) -----------------------------------------------------------------------
+constexpr int BC_MAX_STRIDE = 64;        // barcodes of up to 64 characters
+constexpr int BC_TILE_ENTRIES = 512;     // entries per launch (32 KB of shared memory at stride 64)
+
+struct BarcodeParams {
+    const uint8_t *frag;      // [n][stride]
+    const int32_t *flen;      // [n]
+    int64_t n;
+    int32_t stride;           // 16, 32, 48 or 64
+    const uint8_t *entries;   // device, [n_entries][stride], zero padded
+    const int32_t *elen;      // device, [n_entries]
+    int32_t e0, e1;           // entries handled by this launch
+    int32_t barcode_len;      // B
+    int32_t allowed;          // --mismatches
+    int32_t last;             // 1: final launch, turn (best_mm, best) into the result
+    int32_t *best_mm;         // [n] running minimum (first launch initialises it to B)
+    int32_t *best;            // [n] running entry index, -1 = none; after the last launch: the answer
+};
+
+cudaError_t launch_barcode(const BarcodeParams &p, int sm_count, cudaStream_t st);
+
 cudaError_t launch_stats(const StatsParams &p, int g, int grid, uint32_t smem_bytes, cudaStream_t st);
 cudaError_t launch_stats2(const StatsParams &p, int warps, int grid, uint32_t smem_bytes, cudaStream_t st);
 cudaError_t launch_stats_simple(const StatsParams &p, int sm_count, cudaStream_t st);

@@ -208,6 +208,23 @@ int fxg_artifacts_host(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint8_t *
 int fxg_has_n_dev (fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint8_t *has_n_dev, int64_t index_base);
 int fxg_has_n_host(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint8_t *has_n_host, fxg_report *report);
 
+/* ---- (f-4) barcode splitter matching loop (scripts/fastx_barcode_splitter.pl:208-290, mismatch_count :296) ---------
+ * `fragments` is an ordinary batch whose rows are the read fragments the script compares (the first --bol / last --eol
+ * barcode_len characters of each sequence line; shorter reads give shorter fragments, an empty line length 0): seq =
+ * fragment bytes, len = fragment lengths (required), stride = 16/32/48/64.  The table holds the script's @barcodes list in
+ * order: every barcode followed by its --partial forms (:170-176), rows of the same stride, zero padded.
+ * best[i] = index of the FIRST entry with the lowest mismatch count if that count <= allowed_mismatches, else -1
+ * ('unmatched'); the count is length(fragment) - equal positions + (barcode_len - entry length), exactly as the Perl. */
+typedef struct {
+    const uint8_t *entries;       /* host memory, n_entries x stride */
+    const int32_t *entry_len;     /* host memory */
+    int32_t n_entries;
+    int32_t barcode_len;          /* length of the full barcodes */
+    int32_t allowed_mismatches;   /* --mismatches (0 with --exact) */
+} fxg_barcode_table;
+int fxg_barcode_dev (fxg_ctx *ctx, const fxg_batch *fragments, const fxg_barcode_table *t, int32_t *best_dev);
+int fxg_barcode_host(fxg_ctx *ctx, const fxg_batch *fragments, const fxg_barcode_table *t, int32_t *best_host, fxg_report *report);
+
 /* ---- next to the loop: FASTQ text in, FASTQ text out, parsed / packed / emitted on the GPU --------
  * fxg_text_run_host(): `text_host` holds raw 4-line FASTQ (any number of bytes; an incomplete trailing record is left
  * alone, see consumed_bytes).  The GPU indexes the lines (fastx.c:324-378 fgets/chomp), checks the record structure

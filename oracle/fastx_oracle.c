@@ -711,6 +711,33 @@ void fxo_artifacts_batch(const uint8_t *seq, const int32_t *len, int uniform_len
     }
 }
 
+/* scripts/fastx_barcode_splitter.pl:296 — length(a) - (number of NUL bytes of the string XOR): the XOR is as long as the
+ * longer string and a position counts as equal only where both strings have the same character */
+static int fxo_perl_mismatch_count(const uint8_t *a, int la, const uint8_t *b, int lb)
+{
+    int zeros = 0;
+    const int lx = la > lb ? la : lb;
+    for (int p = 0; p < lx; p++) {
+        const uint8_t ca = p < la ? a[p] : 0, cb = p < lb ? b[p] : 0;
+        if ((ca ^ cb) == 0) zeros++;
+    }
+    return la - zeros;
+}
+
+/* scripts/fastx_barcode_splitter.pl:232-275 */
+int fxo_barcode_match(const uint8_t *fragment, int frag_len, const uint8_t *const *entries, const int32_t *entry_len, int n_entries,
+                      int barcode_len, int allowed_mismatches)
+{
+    int best_mm = barcode_len, best = -1;
+    for (int e = 0; e < n_entries; e++) {
+        int mm = fxo_perl_mismatch_count(fragment, frag_len, entries[e], entry_len[e]);
+        mm += barcode_len - entry_len[e];                    /* partial entries: the missing bases are mismatches */
+        if (mm < best_mm) { best_mm = mm; best = e; }
+    }
+    if (best < 0 || best_mm > allowed_mismatches) return -1;
+    return best;
+}
+
 /* src/fastq_to_fasta/fastq_to_fasta.c:79-82: the discard test of fastq_to_fasta */
 void fxo_has_n_batch(const uint8_t *seq, const int32_t *len, int uniform_len, int stride, int64_t n, uint8_t *has_n)
 {

@@ -119,6 +119,10 @@ void fxo_mask_batch(const uint8_t *seq, const uint8_t *qual, const int32_t *len,
                     int q_offset, int min_quality, int mask_char, uint8_t *out_seq, uint8_t *masked_flag,
                     int64_t *masked_reads, int64_t *masked_bases);
 void fxo_artifacts_batch(const uint8_t *seq, const int32_t *len, int uniform_len, int stride, int64_t n, uint8_t *keep);
+/* (f-4) barcode splitter, scripts/fastx_barcode_splitter.pl:208-290 + mismatch_count (:296): index of the entry that gets
+ * the fragment, -1 = 'unmatched'.  entries: the script's @barcodes in order (each barcode, then its --partial forms). */
+int fxo_barcode_match(const uint8_t *fragment, int frag_len, const uint8_t *const *entries, const int32_t *entry_len, int n_entries,
+                      int barcode_len, int allowed_mismatches);
 /* (f-4) fastq_to_fasta (src/fastq_to_fasta/fastq_to_fasta.c:79-82): has_n[i] = strchr(nucleotides, 'N') != NULL */
 void fxo_has_n_batch(const uint8_t *seq, const int32_t *len, int uniform_len, int stride, int64_t n, uint8_t *has_n);
 /* first/last: -f/-l (1-based, last 0 = none); trim_last/min_len: -t/-m.  Returns the new length (>=0) and *start, or -1 = discard */
