@@ -340,7 +340,26 @@ __device__ __forceinline__ void stats2_word_masked(const StatsParams &P, const S
     else bad |= stats2_slow_word(P, sw, qw, (int)(o >> 2), vb, hs_addr);
 }
 
-template <int WARPS>
+__device__ __noinline__ uint32_t stats2_byte_exact(const StatsParams &P, uint32_t c, uint32_t q, int wrel, int k, uint32_t hs_addr)
+{
+    return stats2_byte(P, c, q, wrel, k, hs_addr);
+}
+// one of the last 1..3 bases of a read (static B scheme): a plain base with 0 <= q' < 64 is one increment, anything else
+// takes the exact path.  (q - lo) mod 256 < 64 implies lo <= q <= hi because this kernel runs with lo <= 64 only.
+__device__ __forceinline__ uint32_t stats2_tail_byte(const StatsParams &P, const Stats2K &K, uint32_t c, uint32_t q, int wrel, int k, uint32_t hs_addr)
+{
+    const uint32_t code = c & 7u;
+    const uint32_t legal = prmt_raw(K.vlut_lo, V2LUT_HI, code) & 0xFFu;       // 'N' poisoned: goes to the exact path
+    const uint32_t n6 = prmt_raw(K.n6_lo, N6_HI, code) & 0xFFu;
+    const uint32_t qp = (q + K.neg_lo4) & 0xFFu;
+    if (legal == c && qp < (uint32_t)ST_QWIN) {
+        reds_inc(hs_addr + (n6 + qp) * S2_PITCH + (uint32_t)k * (4u * ST_MAXW) + 4u * (uint32_t)wrel);
+        return 0u;
+    }
+    return stats2_byte_exact(P, c, q, wrel, k, hs_addr);
+}
+
+template <int WARPS, int BS>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_stats2(const __grid_constant__ StatsParams P)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -435,14 +454,32 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_stats2(const __grid_constant_
                 }
             }
         }
-        for (int b8 = nsb * 4; b8 < nb8; b8++) {                 // the words past the superblock, the read's last 1..3 bases included
-            const uint32_t o0 = 32u * (uint32_t)b8 + 4u * (uint32_t)((2 * j + grr) & 7);
-            const uint32_t o1 = 32u * (uint32_t)b8 + 4u * (uint32_t)((2 * j + 1 + grr) & 7);
-            const int vb0 = Lp - (int)o0, vb1 = Lp - (int)o1;
-            uint32_t sw0 = 0, qw0 = 0, sw1 = 0, qw1 = 0;
-            if (vb0 > 0) { sw0 = lds32(srow + o0); qw0 = lds32(qrow + o0); }
-            if (vb1 > 0) { sw1 = lds32(srow + o1); qw1 = lds32(qrow + o1); }
-            stats2_pair_masked(P, K, sw0, qw0, o0, vb0, sw1, qw1, o1, vb1, hs_addr, ksel, koff, bad);
+        if (BS == 0) {
+            for (int b8 = nsb * 4; b8 < nb8; b8++) {             // the words past the superblock, the read's last 1..3 bases included
+                const uint32_t o0 = 32u * (uint32_t)b8 + 4u * (uint32_t)((2 * j + grr) & 7);
+                const uint32_t o1 = 32u * (uint32_t)b8 + 4u * (uint32_t)((2 * j + 1 + grr) & 7);
+                const int vb0 = Lp - (int)o0, vb1 = Lp - (int)o1;
+                uint32_t sw0 = 0, qw0 = 0, sw1 = 0, qw1 = 0;
+                if (vb0 > 0) { sw0 = lds32(srow + o0); qw0 = lds32(qrow + o0); }
+                if (vb1 > 0) { sw1 = lds32(srow + o1); qw1 = lds32(qrow + o1); }
+                stats2_pair_masked(P, K, sw0, qw0, o0, vb0, sw1, qw1, o1, vb1, hs_addr, ksel, koff, bad);
+            }
+        } else {
+            // static B scheme: the 8-word blocks past the superblock with the A scheme's code (k static, full words only);
+            // the four reads of a warp that meet in one column cost three extra wavefronts per ATOMS, but there is no
+            // masking and no per-lane byte order — 2 x 30 instructions per block instead of 140
+            for (int b8 = nsb * 4; b8 < nb8; b8++) {
+#pragma unroll
+                for (int t = 0; t < 2; t++) {
+                    const uint32_t o = 32u * (uint32_t)b8 + 16u * (uint32_t)((t + rr) & 1) + 4u * (uint32_t)j;
+                    if ((int)o <= lim) stats2_word<false>(P, K, lds32(srow + o), lds32(qrow + o), o, hs_addr, ksel, koff, bad);
+                }
+            }
+            // the last 1..3 bases, unless the ragged A path already took them: lane j of the read takes byte j
+            if (Lp > 0 && j < (Lp & 3) && (Lp >> 2) >= 32 * nsb) {
+                const uint32_t ob = (uint32_t)(Lp & ~3) + (uint32_t)j;
+                bad |= stats2_tail_byte(P, K, lds8(srow + ob), lds8(qrow + ob), Lp >> 2, j, hs_addr);
+            }
         }
         if ((bad != 0 || lenbad) && active)
             atomicMin(&P.counters[CNT_FIRST_BAD], (unsigned long long)(P.index_base + g));
@@ -520,15 +557,17 @@ cudaError_t launch_stats(const StatsParams &p, int g, int grid, uint32_t smem_by
 
 cudaError_t launch_stats2(const StatsParams &p, int warps, int grid, uint32_t smem_bytes, cudaStream_t st)
 {
-#define FXG_STATS2_LAUNCH(WV)                                                                        \
-    do {                                                                                            \
-        cudaFuncSetAttribute(k_stats2<WV>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM); \
-        k_stats2<WV><<<grid, WV * 32, smem_bytes, st>>>(p);                                          \
+#define FXG_STATS2_LAUNCH(WV, BV)                                                                        \
+    do {                                                                                                \
+        cudaFuncSetAttribute(k_stats2<WV, BV>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM); \
+        k_stats2<WV, BV><<<grid, WV * 32, smem_bytes, st>>>(p);                                          \
     } while (0)
-    if (warps == 24) FXG_STATS2_LAUNCH(24);
-    else if (warps == 20) FXG_STATS2_LAUNCH(20);
-    else if (warps == 16) FXG_STATS2_LAUNCH(16);
-    else if (warps == 12) FXG_STATS2_LAUNCH(12);
+    // p.stages doubles as the B-scheme selector: 0 = masked blocks with per-lane byte order, 1 = static blocks
+    if (warps == 24 && p.stages == 0) FXG_STATS2_LAUNCH(24, 0);
+    else if (warps == 24) FXG_STATS2_LAUNCH(24, 1);
+    else if (warps == 20) FXG_STATS2_LAUNCH(20, 1);
+    else if (warps == 16) FXG_STATS2_LAUNCH(16, 1);
+    else if (warps == 12) FXG_STATS2_LAUNCH(12, 1);
     else return cudaErrorInvalidValue;
 #undef FXG_STATS2_LAUNCH
     return cudaGetLastError();
