@@ -498,7 +498,7 @@ static int stats_enqueue(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint64_
     const bool fast = b->qual && !weight && rfit * g >= 8 && t_ring != 0;
     if (fast2) {
         p.tile_reads = (int)rfit2;
-        { const char *eb = getenv("FXG_STATS_B"); p.stages = eb ? atoi(eb) : 1; }     // B scheme (see launch_stats2)
+        { const char *eb = getenv("FXG_STATS_B"); p.stages = eb ? atoi(eb) : 0; }     // B scheme (see launch_stats2): masked blocks by default
         const uint32_t smem = (uint32_t)((size_t)S2_HIST_BYTES + S2_DUMMY_BYTES + (size_t)warps2 * 2 * b->stride * rfit2);
         const int64_t ntiles = (b->n + rfit2 - 1) / rfit2;
         int64_t grid = ctx->sm_count;

@@ -465,9 +465,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_stats2(const __grid_constant_
                 stats2_pair_masked(P, K, sw0, qw0, o0, vb0, sw1, qw1, o1, vb1, hs_addr, ksel, koff, bad);
             }
         } else {
-            // static B scheme: the 8-word blocks past the superblock with the A scheme's code (k static, full words only);
-            // the four reads of a warp that meet in one column cost three extra wavefronts per ATOMS, but there is no
-            // masking and no per-lane byte order — 2 x 30 instructions per block instead of 140
+            // static B scheme (FXG_STATS_B=1, measured and NOT the default): the 8-word blocks past the superblock with the
+            // A scheme's code (k static, full words only).  Fewer instructions (125 instead of 165 per tile at 150 bp),
+            // but the four reads of a warp that meet in one column cost three extra wavefronts per ATOMS: 13.08 vs 13.02
+            // Greads/s at 150 bp, 14.9 vs 17.8 at 50 bp, 3.05 vs 3.80 at 250 bp (B200, round 1)
             for (int b8 = nsb * 4; b8 < nb8; b8++) {
 #pragma unroll
                 for (int t = 0; t < 2; t++) {
@@ -565,9 +566,9 @@ cudaError_t launch_stats2(const StatsParams &p, int warps, int grid, uint32_t sm
     // p.stages doubles as the B-scheme selector: 0 = masked blocks with per-lane byte order, 1 = static blocks
     if (warps == 24 && p.stages == 0) FXG_STATS2_LAUNCH(24, 0);
     else if (warps == 24) FXG_STATS2_LAUNCH(24, 1);
-    else if (warps == 20) FXG_STATS2_LAUNCH(20, 1);
-    else if (warps == 16) FXG_STATS2_LAUNCH(16, 1);
-    else if (warps == 12) FXG_STATS2_LAUNCH(12, 1);
+    else if (warps == 20) FXG_STATS2_LAUNCH(20, 0);
+    else if (warps == 16) FXG_STATS2_LAUNCH(16, 0);
+    else if (warps == 12) FXG_STATS2_LAUNCH(12, 0);
     else return cudaErrorInvalidValue;
 #undef FXG_STATS2_LAUNCH
     return cudaGetLastError();
