@@ -496,7 +496,23 @@ static int stats_enqueue(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint64_
     long rfit = ((long)MAX_DYN_SMEM - (long)hist_al) / warps / stages / (2L * b->stride);
     if (rfit > 32 / g) rfit = 32 / g;
     const bool fast = b->qual && !weight && rfit * g >= 8 && t_ring != 0;
-    if (fast2) {
+    // FXG_STATS_V=3: experimental u16-counter / double-buffered kernel (fxg_stats3.cu), same preconditions as k_stats2
+    long rfit3 = ((long)MAX_DYN_SMEM - 98432L) / 24 / (4L * b->stride);
+    if (rfit3 > S2_TILE_READS) rfit3 = S2_TILE_READS;
+    const bool fast3 = ver == 3 && b->qual && !weight && rfit3 >= 4 && t_ring != 0 && q_offset - 15 <= 64 && b->n / rfit3 < (1ll << 31);
+    if (fast3) {
+        p.tile_reads = (int)rfit3; p.stages = 2;
+        const uint32_t smem = (uint32_t)(98432u + (size_t)24 * 4 * b->stride * rfit3);
+        const int64_t ntiles = (b->n + rfit3 - 1) / rfit3;
+        int64_t grid = ctx->sm_count;
+        const int64_t need = (ntiles + 23) / 24;
+        if (grid > need) grid = need;
+        for (int w0 = 0; w0 < words; w0 += ST_MAXW) {
+            p.w0 = w0; p.nw = (words - w0 < ST_MAXW) ? (words - w0) : ST_MAXW;
+            CK(ctx, launch_stats3(p, (int)grid, smem, st));
+            ctx->launches++;
+        }
+    } else if (fast2) {
         p.tile_reads = (int)rfit2;
         { const char *eb = getenv("FXG_STATS_B"); p.stages = eb ? atoi(eb) : 0; }     // B scheme (see launch_stats2): masked blocks by default
         const uint32_t smem = (uint32_t)((size_t)S2_HIST_BYTES + S2_DUMMY_BYTES + (size_t)warps2 * 2 * b->stride * rfit2);

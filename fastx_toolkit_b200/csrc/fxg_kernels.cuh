@@ -153,6 +153,7 @@ cudaError_t launch_barcode(const BarcodeParams &p, int sm_count, cudaStream_t st
 
 cudaError_t launch_stats(const StatsParams &p, int g, int grid, uint32_t smem_bytes, cudaStream_t st);
 cudaError_t launch_stats2(const StatsParams &p, int warps, int grid, uint32_t smem_bytes, cudaStream_t st);
+cudaError_t launch_stats3(const StatsParams &p, int grid, uint32_t smem_bytes, cudaStream_t st);   // experimental (fxg_stats3.cu)
 cudaError_t launch_stats_simple(const StatsParams &p, int sm_count, cudaStream_t st);
 cudaError_t launch_clip(const ClipParams &p, int sm_count, int max_width, cudaStream_t st);
 cudaError_t stats_set_smem_attrs();

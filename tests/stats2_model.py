@@ -7,6 +7,10 @@ for integer so that the design can be checked WITHOUT a GPU:
   * every shared-memory increment instruction of the A scheme and of the masked B scheme must be bank-conflict free
     (32 lanes on 32 distinct banks — the point of the [bin][40k + w] layout), as must the tile loads at stride 160.
 
+layout16=True models the experimental third-generation layout (fxg_stats3.cu): u16 counters paired along k (bytes k and
+k+2 of a word share one 32-bit word, increments 1 / 65536), where only the A scheme stays strictly conflict free (the
+masked B scheme meets the partner byte's lane on the SAME word: a 2-way same-address collision by design).
+
 Test infrastructure only (tests/test_stats2_model.py); nothing here is on the product path.
 """
 
@@ -41,13 +45,20 @@ def decode(sw, qw, lo4):
 
 
 class Pass:
-    def __init__(self, q_offset, w0, nw, max_cycles):
+    def __init__(self, q_offset, w0, nw, max_cycles, layout16=False):
+        self.layout16 = layout16
         self.lo, self.hi = q_offset - 15, min(q_offset + 93, 127)
         self.lo4 = (self.lo * 0x01010101) & M32
-        self.hs = [0] * (256 * 160)          # the shared histogram, u32 [bin][40k + w]
+        self.hs = [0] * (256 * 160)          # the shared histogram, u32 [bin][40k + w]  (layout16: [bin][40(k&1) + w], two u16 halves)
         self.glob = {}                       # the global u64 table (cycle, nuc, q')
         self.w0, self.nw, self.max_cycles = w0, nw, max_cycles
         self.conflicts = 0
+
+    def counter(self, bin_, k, o):
+        """(byte address, increment) of the counter of (bin, byte k of the word at byte offset o)"""
+        if self.layout16:
+            return bin_ * 384 + (k & 1) * 160 + o, (65536 if k & 2 else 1)      # pitch padded to 96 words: a multiple of 32 banks
+        return bin_ * PITCH + k * 160 + o, 1
 
     def gadd(self, cyc, nuc, qp, v=1):
         if cyc < self.max_cycles:
@@ -62,20 +73,33 @@ class Pass:
         if legal != c or qp > self.hi - self.lo:
             return 1
         if nuc < 4 and qp < 64:
-            self.hs[((nuc * 64 + qp) * PITCH + k * 160 + 4 * wrel) // 4] += 1
+            a, inc = self.counter(nuc * 64 + qp, k, 4 * wrel)
+            self.hs[a // 4] += inc
         else:
             self.gadd(4 * (self.w0 + wrel) + k, nuc, qp)
         return 0
 
     def flush(self):
         for i, v in enumerate(self.hs):
-            if v:
+            if not v:
+                continue
+            if self.layout16:
+                b, r = divmod(i, 96)
+                assert r < 80
+                kk, wr = divmod(r, 40)
+                lo, hi = v & 0xFFFF, v >> 16
+                assert hi < 65536
+                if lo:
+                    self.gadd(4 * (self.w0 + wr) + kk, b >> 6, b & 63, lo)
+                if hi:
+                    self.gadd(4 * (self.w0 + wr) + kk + 2, b >> 6, b & 63, hi)
+            else:
                 b, pc = divmod(i, 160)
                 k, wr = divmod(pc, 40)
                 self.gadd(4 * (self.w0 + wr) + k, b >> 6, b & 63, v)
 
 
-def run_model(seqs, quals, lens, stride, q_offset, bscheme=0, tile_reads=8):
+def run_model(seqs, quals, lens, stride, q_offset, bscheme=0, tile_reads=8, layout16=False):
     """seqs/quals: rows of `stride` byte values; returns (global histogram dict, set of bad reads)"""
     n = len(lens)
     ragged = any(l != lens[0] for l in lens)
@@ -84,7 +108,7 @@ def run_model(seqs, quals, lens, stride, q_offset, bscheme=0, tile_reads=8):
     bad_reads, hist = set(), {}
     for w0 in range(0, words, MAXW):
         nw = min(words - w0, MAXW)
-        P = Pass(q_offset, w0, nw, max_cycles)
+        P = Pass(q_offset, w0, nw, max_cycles, layout16)
         passoff, ncols = 4 * w0, 4 * nw
         nsb, nb8 = (1 if nw > 16 else 0), (nw + 7) >> 3
         for tile in range((n + tile_reads - 1) // tile_reads):
@@ -127,9 +151,9 @@ def run_model(seqs, quals, lens, stride, q_offset, bscheme=0, tile_reads=8):
                             k = (j + i) & 3 if dyn_k else i
                             if k >= vb:
                                 continue
-                            a = ((comb >> (8 * k)) & 0xFF) * PITCH + o + k * 160
+                            a, inc = P.counter((comb >> (8 * k)) & 0xFF, k, o)
                             addrs[i][lane] = a
-                            P.hs[a // 4] += 1
+                            P.hs[a // 4] += inc
                     else:
                         bd = 0
                         for k in range(min(vb, 4)):
@@ -149,7 +173,8 @@ def run_model(seqs, quals, lens, stride, q_offset, bscheme=0, tile_reads=8):
             if bscheme == 0:                          # masked B scheme: words (2j+s+g(rr))&7 of each 8-word block, bytes k = (j+i)&3
                 for b8 in range(nsb * 4, nb8):
                     for s in range(2):
-                        step([32 * b8 + 4 * ((2 * j + s + (((rr & 3) << 1) | (rr >> 2))) & 7) for (j, rr, g, Lp) in lanes], dyn_k=True, masked=True)
+                        step([32 * b8 + 4 * ((2 * j + s + (((rr & 3) << 1) | (rr >> 2))) & 7) for (j, rr, g, Lp) in lanes], dyn_k=True, masked=True,
+                             may_conflict=layout16)
             else:                                     # static B scheme: A-scheme code on the blocks, tails byte by byte
                 for b8 in range(nsb * 4, nb8):
                     for t in range(2):

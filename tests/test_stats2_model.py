@@ -32,11 +32,11 @@ def make_rows(rng, n, L, S, Q, ragged, junk):
     (37, 150, 160, 33, False, False), (21, 100, 112, 33, False, True), (19, 50, 64, 64, True, True), (9, 300, 304, 33, True, False),
     (11, 36, 48, 33, False, False), (13, 127, 128, 33, True, True), (10, 160, 160, 33, False, False), (6, 163, 176, 33, False, False),
     (9, 129, 144, 33, False, False), (17, 68, 80, 64, True, False), (5, 3, 16, 33, False, False)])
-@pytest.mark.parametrize("bscheme", [0, 1])
-def test_model_equals_direct_histogram(n, L, S, Q, ragged, junk, bscheme):
+@pytest.mark.parametrize("bscheme,layout16", [(0, False), (1, False), (0, True)])
+def test_model_equals_direct_histogram(n, L, S, Q, ragged, junk, bscheme, layout16):
     rng = random.Random(1000 * L + S + bscheme)
     seqs, quals, lens = make_rows(rng, n, L, S, Q, ragged, junk)
-    hist, bad = SM.run_model(seqs, quals, lens, S, Q, bscheme=bscheme)
+    hist, bad = SM.run_model(seqs, quals, lens, S, Q, bscheme=bscheme, layout16=layout16)
     exp, exp_bad = SM.direct_hist(seqs, quals, lens, Q)
     assert bad == exp_bad
     assert hist == exp
