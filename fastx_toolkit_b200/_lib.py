@@ -27,6 +27,11 @@ class BarcodeTable(C.Structure):
                 ("allowed_mismatches", C.c_int32)]
 
 
+class Stage(C.Structure):
+    """struct fxg_stage (op: 0 trim, 1 filter, 2 clip)"""
+    _fields_ = [("op", C.c_int32), ("a0", C.c_int32), ("a1", C.c_int32), ("clip", C.c_void_p)]
+
+
 class ClipOpts(C.Structure):
     """struct fxg_clip_opts"""
     _fields_ = [("adapter", C.c_char_p), ("min_length", C.c_int32), ("keep_delta", C.c_int32),
@@ -107,6 +112,7 @@ def lib():
         "fxg_artifacts_host": (i32, [vp, BP, i32, vp, RP]),
         "fxg_barcode_dev": (i32, [vp, BP, vp, vp]),
         "fxg_barcode_host": (i32, [vp, BP, vp, vp, RP]),
+        "fxg_pipeline_dev": (i32, [vp, BP, i32, vp, i32, vp, vp]),
         "fxg_has_n_dev": (i32, [vp, BP, i32, vp, i64]),
         "fxg_has_n_host": (i32, [vp, BP, i32, vp, RP]),
         "fxg_text_new": (i32, [vp, i32, sz, C.POINTER(vp)]),
@@ -328,6 +334,13 @@ class Context:
         r = Report()
         self._ck(self.L.fxg_barcode_host(self.h, C.byref(b), C.byref(table), _ptr(best), C.byref(r)))
         return r
+
+    def pipeline_dev(self, b, q_offset, stages, final_len):
+        """stages: list of Stage; returns the number of surviving reads (blocking)"""
+        arr = (Stage * len(stages))(*stages)
+        alive = C.c_int64(0)
+        self._ck(self.L.fxg_pipeline_dev(self.h, C.byref(b), q_offset, C.cast(arr, C.c_void_p), len(stages), _ptr(final_len), C.byref(alive)))
+        return alive.value
 
     def has_n_dev(self, b, q_offset, has_n, index_base=0):
         self._ck(self.L.fxg_has_n_dev(self.h, C.byref(b), q_offset, _ptr(has_n), index_base))

@@ -791,6 +791,102 @@ extern "C" int fxg_barcode_host(fxg_ctx *ctx, const fxg_batch *b, const fxg_barc
     return FXG_OK;
 }
 
+// ---- (f-3) fused pipelines (experimental) -------------------------------------------------------------------
+extern "C" int fxg_pipeline_dev(fxg_ctx *ctx, const fxg_batch *b, int q_offset, const fxg_stage *stages, int n_stages, int32_t *final_len,
+                                int64_t *n_survivors)
+{
+    int rc = check_batch(ctx, b, true, true, q_offset);
+    if (rc) return rc;
+    if (!stages || n_stages <= 0 || !final_len) return arg_error(ctx, "pipeline: stages / final_len");
+    if (b->n >= (1ll << 31)) return arg_error(ctx, "pipeline: more than 2^31 reads in one batch");
+    for (int k = 0; k < n_stages; k++) {
+        if (stages[k].op == FXG_STAGE_CLIP) {
+            if (k != 0 || b->len) {
+                snprintf(ctx->err, sizeof(ctx->err), "pipeline: the clipper must be stage 0 on a batch of one read length (stale-buffer semantics)");
+                return FXG_ERR_UNSUPPORTED;
+            }
+            if ((rc = check_clip_opts(ctx, stages[k].clip))) return rc;
+        } else if (stages[k].op == FXG_STAGE_FILTER) {
+            if (stages[k].a1 < 0 || stages[k].a1 > 100) return arg_error(ctx, "min_percent must be 0..100");
+        } else if (stages[k].op != FXG_STAGE_TRIM) return arg_error(ctx, "pipeline: unknown stage");
+    }
+    CK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int S = b->stride;
+    const int64_t n = b->n;
+    if (n_survivors) *n_survivors = 0;
+    if (n == 0) return FXG_OK;
+    CK(ctx, cudaMemsetAsync(final_len, 0xFF, (size_t)n * sizeof(int32_t), st));
+
+    // per-stage scratch, sized by the input: decision (int32 or bytes), flags, positions, scan workspace
+    const size_t tmp_bytes = pipe_scan_tmp_bytes(n);
+    const size_t ib = (((size_t)n * sizeof(int32_t)) + 255) & ~(size_t)255;
+    void *scr = NULL;
+    CK(ctx, cudaMallocAsync(&scr, 3 * ib + ((tmp_bytes + 255) & ~(size_t)255), st));
+    int32_t *d_dec = (int32_t *)scr, *d_flags = (int32_t *)((char *)scr + ib), *d_pos = (int32_t *)((char *)scr + 2 * ib);
+    void *d_tmp = (char *)scr + 3 * ib;
+    // working slabs of the survivors (ping-pong), allocated when the first compaction's size is known
+    void *work[2] = { NULL, NULL };
+    uint8_t *wseq[2] = { NULL, NULL }, *wqual[2] = { NULL, NULL };
+    int32_t *wlen[2] = { NULL, NULL }, *widx[2] = { NULL, NULL };
+
+    fxg_batch cur = *b;
+    const int32_t *cur_idx = NULL;
+    int64_t cur_n = n;
+    int which = 0;
+    rc = FXG_OK;
+    for (int k = 0; k < n_stages && cur_n > 0; k++) {
+        const fxg_stage &sg = stages[k];
+        cur.n = cur_n;
+        const bool bytes = sg.op == FXG_STAGE_FILTER;
+        if (sg.op == FXG_STAGE_TRIM) rc = scan_enqueue(ctx, MODE_TRIM, &cur, q_offset, sg.a0, sg.a1, 0, d_dec, 0, st);
+        else if (sg.op == FXG_STAGE_FILTER) rc = scan_enqueue(ctx, MODE_FILTER, &cur, q_offset, sg.a0, 0, sg.a1, d_dec, 0, st);
+        else rc = clip_enqueue(ctx, &cur, NULL, q_offset, sg.clip, d_dec, NULL, NULL, 0, st);
+        if (rc) break;
+        cudaError_t e = launch_pipe_flags_scan(bytes ? NULL : d_dec, bytes ? (const uint8_t *)d_dec : NULL, cur_n, d_flags, d_pos, d_tmp, tmp_bytes,
+                                              ctx->sm_count, st);
+        int32_t last_pos = 0, last_flag = 0;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&last_pos, d_pos + (cur_n - 1), 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&last_flag, d_flags + (cur_n - 1), 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "pipeline stage %d: %s", k, cudaGetErrorString(e)); rc = FXG_ERR_CUDA; break; }
+        ctx->launches += 2;
+        const int64_t alive = (int64_t)last_pos + last_flag;
+        if (k == n_stages - 1 || alive == 0) {
+            if (alive > 0) {
+                e = launch_pipe_scatter(cur_n, d_flags, bytes ? NULL : d_dec, cur.len, cur.uniform_len, cur_idx, final_len, ctx->sm_count, st);
+                if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "pipeline scatter: %s", cudaGetErrorString(e)); rc = FXG_ERR_CUDA; break; }
+                ctx->launches++;
+            }
+            cur_n = alive;
+            break;
+        }
+        // compact the survivors into the other working slab pair
+        const int dst = which;
+        if (!work[dst]) {
+            const size_t sb = (((size_t)alive * S) + 255) & ~(size_t)255, lb = (((size_t)alive * sizeof(int32_t)) + 255) & ~(size_t)255;
+            e = cudaMallocAsync(&work[dst], 2 * sb + 2 * lb, st);
+            if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "pipeline: cudaMallocAsync: %s", cudaGetErrorString(e)); rc = FXG_ERR_CUDA; break; }
+            wseq[dst] = (uint8_t *)work[dst]; wqual[dst] = wseq[dst] + sb;
+            wlen[dst] = (int32_t *)(wqual[dst] + sb); widx[dst] = (int32_t *)((char *)wlen[dst] + lb);
+        }
+        e = launch_pipe_gather(cur.seq, cur.qual, S, cur_n, d_flags, d_pos, bytes ? NULL : d_dec, cur.len, cur.uniform_len, cur_idx, wseq[dst], wqual[dst],
+                               wlen[dst], widx[dst], ctx->sm_count, st);
+        if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "pipeline gather: %s", cudaGetErrorString(e)); rc = FXG_ERR_CUDA; break; }
+        ctx->launches++;
+        cur.seq = wseq[dst]; cur.qual = wqual[dst]; cur.len = wlen[dst]; cur.uniform_len = 0;
+        cur_idx = widx[dst];
+        cur_n = alive;
+        which ^= 1;                      // survivors only shrink: the slab sized for stage k's survivors fits every later stage
+    }
+    cudaStreamSynchronize(st);
+    for (int w = 0; w < 2; w++) if (work[w]) cudaFreeAsync(work[w], st);
+    cudaFreeAsync(scr, st);
+    if (rc) return rc;
+    if (n_survivors) *n_survivors = cur_n;
+    return refresh_report(ctx, st);
+}
+
 // ---- host-buffer pipelines ---------------------------------------------------------------------------
 // Chunks of the host slab travel H2D -> kernel -> D2H on PIPE_LANES side streams, so the copy of one
 // chunk overlaps the kernel and the result copy of its neighbours (both copy engines busy).

@@ -153,6 +153,15 @@ cudaError_t launch_barcode(const BarcodeParams &p, int sm_count, cudaStream_t st
 
 cudaError_t launch_stats(const StatsParams &p, int g, int grid, uint32_t smem_bytes, cudaStream_t st);
 cudaError_t launch_stats2(const StatsParams &p, int warps, int grid, uint32_t smem_bytes, cudaStream_t st);
+// ---- fused pipelines (fxg_pipeline.cu, experimental) ----
+size_t pipe_scan_tmp_bytes(int64_t n);
+cudaError_t launch_pipe_flags_scan(const int32_t *new_len, const uint8_t *keep, int64_t n, int32_t *flags, int32_t *pos, void *tmp, size_t tmp_bytes,
+                                   int sm_count, cudaStream_t st);
+cudaError_t launch_pipe_gather(const uint8_t *src_seq, const uint8_t *src_qual, int stride, int64_t n, const int32_t *flags, const int32_t *pos,
+                               const int32_t *new_len, const int32_t *cur_len, int uniform_len, const int32_t *cur_idx, uint8_t *dst_seq,
+                               uint8_t *dst_qual, int32_t *dst_len, int32_t *dst_idx, int sm_count, cudaStream_t st);
+cudaError_t launch_pipe_scatter(int64_t n, const int32_t *flags, const int32_t *new_len, const int32_t *cur_len, int uniform_len, const int32_t *cur_idx,
+                                int32_t *final_len, int sm_count, cudaStream_t st);
 cudaError_t launch_stats3(const StatsParams &p, int grid, uint32_t smem_bytes, cudaStream_t st);   // experimental (fxg_stats3.cu)
 cudaError_t launch_stats_simple(const StatsParams &p, int sm_count, cudaStream_t st);
 cudaError_t launch_clip(const ClipParams &p, int sm_count, int max_width, cudaStream_t st);

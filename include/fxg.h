@@ -225,6 +225,23 @@ typedef struct {
 int fxg_barcode_dev (fxg_ctx *ctx, const fxg_batch *fragments, const fxg_barcode_table *t, int32_t *best_dev);
 int fxg_barcode_host(fxg_ctx *ctx, const fxg_batch *fragments, const fxg_barcode_table *t, int32_t *best_host, fxg_report *report);
 
+/* ---- (f-3) fused pipelines, first version (EXPERIMENTAL: not yet validated on a GPU) ---------------------------------
+ * The map-type tools chained on the device, e.g. fastx_clipper | fastq_quality_trimmer | fastq_quality_filter: every
+ * stage runs the tool's own kernel on the survivors of the stage before (compacted in HBM, exactly the records the next
+ * process of a shell pipe would read).  All three tools only shorten reads at the 3' end, so the result is one length
+ * per ORIGINAL read: final_len[i] = length after the last stage, -1 = dropped by some stage.
+ * FXG_STAGE_CLIP may only be stage 0 and needs a batch of one read length (len == NULL): after a trimming stage the
+ * reference's aligner depends on the order of mixed-length reads -> FXG_ERR_UNSUPPORTED.
+ * Blocking (one small device-to-host read per stage); report.first_bad_read refers to the input batch. */
+enum { FXG_STAGE_TRIM = 0, FXG_STAGE_FILTER = 1, FXG_STAGE_CLIP = 2 };
+typedef struct {
+    int32_t op;                   /* FXG_STAGE_*                                                            */
+    int32_t a0, a1;               /* TRIM: -t, -l    FILTER: -q, -p                                         */
+    const fxg_clip_opts *clip;    /* CLIP                                                                   */
+} fxg_stage;
+int fxg_pipeline_dev(fxg_ctx *ctx, const fxg_batch *b, int q_offset, const fxg_stage *stages, int n_stages, int32_t *final_len_dev,
+                     int64_t *n_survivors);
+
 /* ---- next to the loop: FASTQ text in, FASTQ text out, parsed / packed / emitted on the GPU --------
  * fxg_text_run_host(): `text_host` holds raw 4-line FASTQ (any number of bytes; an incomplete trailing record is left
  * alone, see consumed_bytes).  The GPU indexes the lines (fastx.c:324-378 fgets/chomp), checks the record structure
