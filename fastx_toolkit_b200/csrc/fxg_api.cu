@@ -791,7 +791,7 @@ extern "C" int fxg_barcode_host(fxg_ctx *ctx, const fxg_batch *b, const fxg_barc
     return FXG_OK;
 }
 
-// ---- (f-3) fused pipelines (experimental) -------------------------------------------------------------------
+// ---- (f-3) fused pipelines, first version ---------------------------------------------------------------------
 extern "C" int fxg_pipeline_dev(fxg_ctx *ctx, const fxg_batch *b, int q_offset, const fxg_stage *stages, int n_stages, int32_t *final_len,
                                 int64_t *n_survivors)
 {

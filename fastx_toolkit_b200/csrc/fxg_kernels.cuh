@@ -153,7 +153,7 @@ cudaError_t launch_barcode(const BarcodeParams &p, int sm_count, cudaStream_t st
 
 cudaError_t launch_stats(const StatsParams &p, int g, int grid, uint32_t smem_bytes, cudaStream_t st);
 cudaError_t launch_stats2(const StatsParams &p, int warps, int grid, uint32_t smem_bytes, cudaStream_t st);
-// ---- fused pipelines (fxg_pipeline.cu, experimental) ----
+// ---- fused pipelines (fxg_pipeline.cu) ----
 size_t pipe_scan_tmp_bytes(int64_t n);
 cudaError_t launch_pipe_flags_scan(const int32_t *new_len, const uint8_t *keep, int64_t n, int32_t *flags, int32_t *pos, void *tmp, size_t tmp_bytes,
                                    int sm_count, cudaStream_t st);

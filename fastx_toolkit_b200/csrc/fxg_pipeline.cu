@@ -1,4 +1,4 @@
-// fxg_pipeline.cu — SURVEY.md §8(f-3), first version (EXPERIMENTAL): the map-type tools chained on the device, the reads
+// fxg_pipeline.cu — SURVEY.md §8(f-3), first version: the map-type tools chained on the device, the reads
 // never leaving HBM between stages.  What a user runs today as
 //     fastx_clipper ... | fastq_quality_trimmer ... | fastq_quality_filter ...
 // becomes one call (fxg_pipeline_dev, fxg_api.cu): each stage is the tool's own kernel (K-CLIP, K-TRIM, K-FILTER,
