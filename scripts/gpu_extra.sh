@@ -1,3 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-(timeout 48 python -m pytest tests/test_gpu_pipeline.py -m gpu -x -q 2>&1 | tail -12) | tee gpurun_out/pytest_pipeline.log
+(timeout 32 python scripts/run_ops.py pipeline 20000000 150 2>&1 | tail -3) | tee gpurun_out/pipeline_timing.log

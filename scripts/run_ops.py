@@ -18,7 +18,7 @@ ctx = F.Context(0)
 st = torch.cuda.Stream()
 torch.cuda.set_stream(st)
 ctx.set_stream(st.cuda_stream)
-kind = {"clip": 2, "collapse": 3}.get(op, 0)
+kind = {"clip": 2, "pipeline": 2, "collapse": 3}.get(op, 0)
 dseq = torch.empty((n, S), dtype=torch.uint8, device="cuda")
 dqual = torch.empty((n, S), dtype=torch.uint8, device="cuda")
 ctx.synth_dev(dseq, dqual, n, L, S, 20260926, kind, 33)
@@ -55,6 +55,16 @@ elif op == "clip":
     o = F.ClipOpts(adapter=b"AGATCGGAAGAGC", min_length=20, keep_delta=0, discard_non_clipped=0, discard_clipped=0, discard_unknown=1, min_adapter_len=0)
     ms = timed(lambda: ctx.clip_dev(b, None, 33, o, out)); bytes_ = n * (L + 4)
     print("clip: %.1f Gcells/s" % (n * L * 13 / ms / 1e6))
+elif op == "pipeline":
+    import ctypes as C
+    fin = torch.empty(n, dtype=torch.int32, device="cuda")
+    co = F.ClipOpts(adapter=b"AGATCGGAAGAGC", min_length=20, keep_delta=0, discard_non_clipped=0, discard_clipped=0, discard_unknown=1, min_adapter_len=0)
+    stages = [F.Stage(2, 0, 0, C.addressof(co)), F.Stage(0, 20, 20, None), F.Stage(1, 20, 90, None)]
+    alive = [0]
+    def run_pipe():
+        alive[0] = ctx.pipeline_dev(b, 33, stages, fin)
+    ms = timed(run_pipe); bytes_ = n * (2 * L + 4)
+    print("pipeline clip|trim|filter: %d of %d reads survive" % (alive[0], n))
 elif op == "mask":
     os_ = torch.empty_like(dseq); fl = torch.empty(n, dtype=torch.uint8, device="cuda")
     ms = timed(lambda: ctx.mask_dev(b, 33, 20, ord("N"), os_, fl)); bytes_ = n * 3 * L
