@@ -225,7 +225,7 @@ typedef struct {
 int fxg_barcode_dev (fxg_ctx *ctx, const fxg_batch *fragments, const fxg_barcode_table *t, int32_t *best_dev);
 int fxg_barcode_host(fxg_ctx *ctx, const fxg_batch *fragments, const fxg_barcode_table *t, int32_t *best_host, fxg_report *report);
 
-/* ---- (f-3) fused pipelines, first version (parity-checked on B200 against the composed oracle; not yet timed) ----------
+/* ---- (f-3) fused pipelines, first version (parity-checked on B200 against the composed oracle) ----------
  * The map-type tools chained on the device, e.g. fastx_clipper | fastq_quality_trimmer | fastq_quality_filter: every
  * stage runs the tool's own kernel on the survivors of the stage before (compacted in HBM, exactly the records the next
  * process of a shell pipe would read).  All three tools only shorten reads at the 3' end, so the result is one length
