@@ -801,7 +801,10 @@ extern "C" int fxg_pipeline_dev(fxg_ctx *ctx, const fxg_batch *b, int q_offset, 
     if (b->n >= (1ll << 31)) return arg_error(ctx, "pipeline: more than 2^31 reads in one batch");
     for (int k = 0; k < n_stages; k++) {
         if (stages[k].op == FXG_STAGE_CLIP) {
-            if (k != 0 || b->len) {
+            // FXG_PIPE_STALE=1 (EXPERIMENTAL, not yet run on a GPU): build the aligner's stale-buffer rows with a scan
+            const char *es = getenv("FXG_PIPE_STALE");
+            const bool stale_ok = es && es[0] == '1' && b->stride <= 160;
+            if ((k != 0 || b->len) && !stale_ok) {
                 snprintf(ctx->err, sizeof(ctx->err), "pipeline: the clipper must be stage 0 on a batch of one read length (stale-buffer semantics)");
                 return FXG_ERR_UNSUPPORTED;
             }
@@ -841,7 +844,27 @@ extern "C" int fxg_pipeline_dev(fxg_ctx *ctx, const fxg_batch *b, int q_offset, 
         const bool bytes = sg.op == FXG_STAGE_FILTER;
         if (sg.op == FXG_STAGE_TRIM) rc = scan_enqueue(ctx, MODE_TRIM, &cur, q_offset, sg.a0, sg.a1, 0, d_dec, 0, st);
         else if (sg.op == FXG_STAGE_FILTER) rc = scan_enqueue(ctx, MODE_FILTER, &cur, q_offset, sg.a0, 0, sg.a1, d_dec, 0, st);
-        else rc = clip_enqueue(ctx, &cur, NULL, q_offset, sg.clip, d_dec, NULL, NULL, 0, st);
+        else if (!cur.len) rc = clip_enqueue(ctx, &cur, NULL, q_offset, sg.clip, d_dec, NULL, NULL, 0, st);
+        else {
+            // mixed lengths: the clipper works on the reference's stale-buffer rows (one scan over the survivors, in order)
+            size_t need = 0;
+            cudaError_t e2 = launch_stale_rows(cur.seq, cur.len, S, cur_n, NULL, NULL, NULL, 0, &need, ctx->sm_count, st);
+            void *sscr = NULL, *srows = NULL;
+            const size_t rb = (((size_t)cur_n * S) + 255) & ~(size_t)255;
+            if (e2 == cudaSuccess) e2 = cudaMallocAsync(&sscr, need, st);
+            if (e2 == cudaSuccess) e2 = cudaMallocAsync(&srows, rb + (size_t)cur_n * sizeof(int32_t), st);
+            if (e2 == cudaSuccess) e2 = launch_stale_rows(cur.seq, cur.len, S, cur_n, (uint8_t *)srows, (int32_t *)((char *)srows + rb), sscr, need, NULL,
+                                                          ctx->sm_count, st);
+            if (e2 != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "pipeline stale rows: %s", cudaGetErrorString(e2)); rc = FXG_ERR_CUDA; }
+            else {
+                fxg_batch sb = cur;
+                sb.seq = (const uint8_t *)srows;
+                rc = clip_enqueue(ctx, &sb, (const int32_t *)((char *)srows + rb), q_offset, sg.clip, d_dec, NULL, NULL, 0, st);
+                ctx->launches += 2;
+            }
+            if (sscr) cudaFreeAsync(sscr, st);
+            if (srows) cudaFreeAsync(srows, st);
+        }
         if (rc) break;
         cudaError_t e = launch_pipe_flags_scan(bytes ? NULL : d_dec, bytes ? (const uint8_t *)d_dec : NULL, cur_n, d_flags, d_pos, d_tmp, tmp_bytes,
                                               ctx->sm_count, st);

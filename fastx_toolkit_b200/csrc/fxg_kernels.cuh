@@ -160,6 +160,8 @@ cudaError_t launch_pipe_flags_scan(const int32_t *new_len, const uint8_t *keep, 
 cudaError_t launch_pipe_gather(const uint8_t *src_seq, const uint8_t *src_qual, int stride, int64_t n, const int32_t *flags, const int32_t *pos,
                                const int32_t *new_len, const int32_t *cur_len, int uniform_len, const int32_t *cur_idx, uint8_t *dst_seq,
                                uint8_t *dst_qual, int32_t *dst_len, int32_t *dst_idx, int sm_count, cudaStream_t st);
+cudaError_t launch_stale_rows(const uint8_t *seq, const int32_t *len, int stride, int64_t n, uint8_t *out_seq, int32_t *out_width, void *scratch,
+                              size_t scratch_bytes, size_t *need, int sm_count, cudaStream_t st);   // experimental
 cudaError_t launch_pipe_scatter(int64_t n, const int32_t *flags, const int32_t *new_len, const int32_t *cur_len, int uniform_len, const int32_t *cur_idx,
                                 int32_t *final_len, int sm_count, cudaStream_t st);
 cudaError_t launch_stats3(const StatsParams &p, int grid, uint32_t smem_bytes, cudaStream_t st);   // experimental (fxg_stats3.cu)

@@ -10,6 +10,8 @@
 // trimming stage the reference's aligner works on mixed lengths with its stale-buffer semantics,
 // which needs a scan over the reads that is not written yet (the target is pinned: tests/test_pipeline_oracle.py).
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
 
 #include "fxg_kernels.cuh"
 
@@ -84,6 +86,117 @@ cudaError_t launch_pipe_scatter(int64_t n, const int32_t *flags, const int32_t *
 {
     k_pipe_scatter<<<pgrid(n, sm_count), 256, 0, st>>>(n, flags, new_len, cur_len, uniform_len, cur_idx, final_len);
     return cudaGetLastError();
+}
+
+}  // namespace fxg
+
+// ------------------------------------------------------------------------------------------------------------------
+// EXPERIMENTAL (FXG_PIPE_STALE=1; not yet run on a GPU): the rows the reference's aligner sees for MIXED-length reads
+// (SURVEY Appendix D.1), needed when the clipper is not the first stage.  Its query buffer only grows and keeps stale
+// bytes, so row i = the buffer after reads 0..i: read i's bases, a NUL, then whatever longer earlier reads left behind,
+// up to the running maximum length.  "Overwrite a prefix" is closed under composition and associative
+// (tests/test_stale_scan_model.py), so all rows come from ONE inclusive scan over the reads.
+// ------------------------------------------------------------------------------------------------------------------
+namespace fxg {
+
+template <int Q16>                 // a row of Q16 * 16 bytes + the length of the valid prefix
+struct __align__(16) StaleRow {
+    uint4 d[Q16];
+    int32_t p;
+    int32_t pad[3];
+};
+
+template <int Q16>
+struct StaleCompose {              // (g after f): g's prefix wins, f shows through behind it
+    __device__ __forceinline__ StaleRow<Q16> operator()(const StaleRow<Q16> &f, const StaleRow<Q16> &g) const
+    {
+        StaleRow<Q16> r;
+        r.p = f.p > g.p ? f.p : g.p;
+        r.pad[0] = r.pad[1] = r.pad[2] = 0;
+        const uint8_t *fb = reinterpret_cast<const uint8_t *>(f.d), *gb = reinterpret_cast<const uint8_t *>(g.d);
+#pragma unroll
+        for (int q = 0; q < Q16; q++) {
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int x = 16 * q + 4 * k;                      // first byte of this 32-bit word
+                const uint32_t fw = reinterpret_cast<const uint32_t *>(fb)[x >> 2], gw = reinterpret_cast<const uint32_t *>(gb)[x >> 2];
+                const uint32_t m = head_mask(g.p - x);             // bytes x .. x+3 that lie inside g's prefix
+                w[k] = (gw & m) | (fw & ~m);
+            }
+            r.d[q] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        return r;
+    }
+};
+
+template <int Q16>
+struct StaleLoad {                 // read i as an operator: (bases + NUL, len + 1)
+    const uint8_t *seq;
+    const int32_t *len;
+    int stride;
+    __device__ __forceinline__ StaleRow<Q16> operator()(int64_t i) const
+    {
+        StaleRow<Q16> r;
+        const int L = len[i];
+        r.p = L + 1;
+        r.pad[0] = r.pad[1] = r.pad[2] = 0;
+        const uint4 *src = reinterpret_cast<const uint4 *>(seq + (size_t)i * stride);
+#pragma unroll
+        for (int q = 0; q < Q16; q++) {
+            uint4 v = (16 * q < stride) ? __ldg(src + q) : make_uint4(0, 0, 0, 0);
+            uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+            for (int k = 0; k < 4; k++) w[k] &= head_mask(L - (16 * q + 4 * k));      // NUL at L and nothing behind it
+            r.d[q] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        return r;
+    }
+};
+
+template <int Q16>
+__global__ void __launch_bounds__(256) k_stale_split(const StaleRow<Q16> *rows, int64_t n, int stride, uint8_t *out_seq, int32_t *out_width)
+{
+    const int chunks = stride >> 4;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n * chunks; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t / chunks;
+        const int c = (int)(t - i * chunks);
+        *reinterpret_cast<uint4 *>(out_seq + (size_t)i * stride + 16 * c) = rows[i].d[c];
+        if (c == 0) out_width[i] = rows[i].p - 1;              // running maximum read length = the aligner's matrix width
+    }
+}
+
+template <int Q16>
+static cudaError_t stale_rows_t(const uint8_t *seq, const int32_t *len, int stride, int64_t n, uint8_t *out_seq, int32_t *out_width, void *scratch,
+                                size_t scratch_bytes, size_t *need, int sm_count, cudaStream_t st)
+{
+    typedef StaleRow<Q16> Row;
+    StaleLoad<Q16> ld = { seq, len, stride };
+    thrust::transform_iterator<StaleLoad<Q16>, thrust::counting_iterator<int64_t>, Row, Row> in(thrust::counting_iterator<int64_t>(0), ld);
+    const size_t rows_bytes = (((size_t)n * sizeof(Row)) + 255) & ~(size_t)255;
+    size_t tmp = 0;
+    cudaError_t e = cub::DeviceScan::InclusiveScan(NULL, tmp, in, (Row *)NULL, StaleCompose<Q16>(), (int)n, st);
+    if (e != cudaSuccess) return e;
+    if (need) { *need = rows_bytes + tmp; return cudaSuccess; }
+    if (scratch_bytes < rows_bytes + tmp) return cudaErrorInvalidValue;
+    Row *rows = (Row *)scratch;
+    e = cub::DeviceScan::InclusiveScan((char *)scratch + rows_bytes, tmp, in, rows, StaleCompose<Q16>(), (int)n, st);
+    if (e != cudaSuccess) return e;
+    k_stale_split<Q16><<<pgrid(n * (stride >> 4), sm_count), 256, 0, st>>>(rows, n, stride, out_seq, out_width);
+    return cudaGetLastError();
+}
+
+// need != NULL: only report the scratch size.  Strides of 16..160 bytes (reads up to 159 bases + the NUL).
+cudaError_t launch_stale_rows(const uint8_t *seq, const int32_t *len, int stride, int64_t n, uint8_t *out_seq, int32_t *out_width, void *scratch,
+                              size_t scratch_bytes, size_t *need, int sm_count, cudaStream_t st)
+{
+    switch (stride >> 4) {
+    case 1: case 2: return stale_rows_t<2>(seq, len, stride, n, out_seq, out_width, scratch, scratch_bytes, need, sm_count, st);
+    case 3: case 4: return stale_rows_t<4>(seq, len, stride, n, out_seq, out_width, scratch, scratch_bytes, need, sm_count, st);
+    case 5: case 6: case 7: return stale_rows_t<7>(seq, len, stride, n, out_seq, out_width, scratch, scratch_bytes, need, sm_count, st);
+    case 8: case 9: case 10: return stale_rows_t<10>(seq, len, stride, n, out_seq, out_width, scratch, scratch_bytes, need, sm_count, st);
+    default: return cudaErrorInvalidValue;
+    }
 }
 
 }  // namespace fxg

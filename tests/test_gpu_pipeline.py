@@ -66,3 +66,22 @@ def test_pipeline_matches_composed_oracle():
         ctx.pipeline_dev(ctx.batch(dseq, dqual, n, stride, L), 33, [F.Stage(0, 20, 20, None), F.Stage(2, 0, 0, C.addressof(clip))],
                          torch.empty(n, dtype=torch.int32, device="cuda"))
     ctx.close()
+
+
+@pytest.mark.skipif(os.environ.get("FXG_PIPE_STALE") != "1", reason="experimental: the device-side stale-buffer scan has not run on a GPU yet (set FXG_PIPE_STALE=1)")
+def test_pipeline_clipper_after_trimmer_experimental():
+    """trim | clip: the clipper on mixed lengths, stale-buffer rows from the prefix-overwrite scan (fxg_pipeline.cu)"""
+    import ctypes as C
+    import fastx_toolkit_b200 as F
+    ctx = F.Context(0)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    seq, qual, L = synth_input()
+    n, stride = seq.shape
+    clip = F.ClipOpts(adapter=ADAPTER, min_length=15, keep_delta=0, discard_non_clipped=0, discard_clipped=0, discard_unknown=0, min_adapter_len=0)
+    final = torch.full((n,), 12345, dtype=torch.int32, device="cuda")
+    alive = ctx.pipeline_dev(ctx.batch(torch.from_numpy(seq).cuda(), torch.from_numpy(qual).cuda(), n, stride, L), 33,
+                             [F.Stage(0, 25, 30, None), F.Stage(2, 0, 0, C.addressof(clip))], final)
+    exp = oracle_final_len(seq, qual, np.full(n, L, np.int32),
+                           [lambda s, q, l: stage_trim(s, q, l, 25, 30), lambda s, q, l: stage_clip(s, q, l, 15, discard_unknown=0)])
+    assert np.array_equal(final.cpu().numpy(), exp) and alive == int((exp >= 0).sum())
+    ctx.close()
