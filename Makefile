@@ -11,9 +11,17 @@ HDR      := include/fxg.h include/fxg_synth.h $(CSRC)/fxg_device.cuh $(CSRC)/fxg
 .PHONY: all lib tools oracle clean ptxas
 all: lib tools oracle
 
-lib: $(LIB)
-$(LIB): $(CU) $(HDR)
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(CU) -ldl
+OBJDIR   := build/obj
+OBJ      := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU))
+
+# one object per .cu so that `make -j` compiles them side by side (the CUB scans of fxg_pipeline.cu / fxg_collapse.cu dominate)
+lib:
+	@$(MAKE) --no-print-directory -j$(shell nproc) $(LIB)
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(HDR)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -c -o $@ $<
+$(LIB): $(OBJ)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -ldl
 
 ptxas: $(CU) $(HDR)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $(CSRC)/fxg_kernels.cu -o /dev/null
@@ -25,4 +33,4 @@ oracle:
 	$(MAKE) --no-print-directory -C oracle all
 
 clean:
-	rm -f $(LIB); rm -rf bin; $(MAKE) -C oracle clean
+	rm -f $(LIB); rm -rf bin build; $(MAKE) -C oracle clean
