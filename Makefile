@@ -14,14 +14,17 @@ all: lib tools oracle
 OBJDIR   := build/obj
 OBJ      := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU))
 
-# one object per .cu so that `make -j` compiles them side by side (the CUB scans of fxg_pipeline.cu / fxg_collapse.cu dominate)
-lib:
-	@$(MAKE) --no-print-directory -j$(shell nproc) $(LIB)
+# one object per .cu, compiled side by side (the CUB scans of fxg_pipeline.cu / fxg_collapse.cu dominate).  The library
+# depends on the SOURCES, not on the objects: a tree that ships libfxg.so without build/ (the GPU box) is up to date.
+lib: $(LIB)
+$(LIB): $(CU) $(HDR)
+	@$(MAKE) --no-print-directory -j$(shell nproc) objs
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -ldl
+.PHONY: objs
+objs: $(OBJ)
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(HDR)
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -c -o $@ $<
-$(LIB): $(OBJ)
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -ldl
 
 ptxas: $(CU) $(HDR)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $(CSRC)/fxg_kernels.cu -o /dev/null
