@@ -160,7 +160,7 @@ def run_reference_arm(args, rank, world):
     if rank != 0:
         return
     procs = host_threads()
-    sample = args.ref_sample
+    sample = max(100_000, min(args.ref_sample, 32_000_000 // max(procs, 1)))     # bounds the temp files to ~10 GB in + ~10 GB out per step
     val, kind, procs, sec = time_reference_cpu(sample, procs, args.steps, args.warmup)
     what = ("%d x fastq_quality_trimmer -t 20 -l 20 -Q33 (reference 0.0.14, gcc -O3) on the same %d x %d bp synthetic FASTQ, "
             "file->file, one process per host core" % (procs, sample, L)) if kind == "reference" else \
@@ -178,6 +178,133 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def leg_stats(args, ctx, comm, stream, dseq, dqual, n, rank, world, barrier, max_over_ranks, parity, H):
+    """BASELINE config (d), this GPU's share: K-STATS over the shard + the native all-reduce of u64 hist[150][5][109]
+    (fxg_comm_allreduce_u64 = ncclAllReduce on the launch stream), both inside the timed region."""
+    import numpy as np
+    import torch
+    ns = min(args.stats_reads, n)
+    words = L * 5 * 109
+    hist = torch.zeros((L, 5, 109), dtype=torch.int64, device="cuda")
+    b = ctx.batch(dseq, dqual, ns, STRIDE, L)
+
+    def step():
+        hist.zero_()
+        ctx.stats_accum_dev(b, Q, hist, L, None, rank * ns)
+        comm.allreduce_u64([hist], words)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0, c0, b0 = ctx.launches(), comm.collectives(), comm.bytes_sent()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    launches, colls, sent = ctx.launches() - l0, comm.collectives() - c0, comm.bytes_sent() - b0
+    total = int(hist.sum().item())
+    ok_sum = total == world * ns * L
+    # the collective alone
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        comm.allreduce_u64([hist], words)
+    e1.record(stream)
+    barrier()
+    ms_ar = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    # K-STATS alone (no collective)
+    e0.record(stream)
+    for _ in range(args.steps):
+        ctx.stats_accum_dev(b, Q, hist, L, None, rank * ns)
+    e1.record(stream)
+    barrier()
+    ms_k = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    # parity: every rank's prefix, all-reduced natively, against the oracle over all the prefixes
+    mpar = min(args.parity_reads, ns)
+    hist.zero_()
+    ctx.stats_accum_dev(ctx.batch(dseq, dqual, mpar, STRIDE, L), Q, hist, L, None, rank * ns)
+    comm.allreduce_u64([hist], words)
+    comm.sync()
+    if rank == 0:
+        exp = np.zeros((L, 5, 109), np.uint64)
+        for r in range(world):
+            ps, pq = H.synth_slab(SEED, mpar, L, H.PLAIN, first=r * n)
+            eh, _ = H.o_stats_hist(ps, pq, None, L, STRIDE, Q, L)
+            exp += eh
+        parity["stats_allreduce"] = bool(np.array_equal(hist.cpu().numpy().astype(np.uint64), exp)) and ok_sum
+    peak, _ = measured_hbm_peak()
+    return {"workload": "fastx_quality_stats on %d x %d bp per GPU (BASELINE config (d): 500 M reads over 8 GPUs) + all-reduce of u64 hist[%d][5][109]" % (ns, L, L),
+            "ms_per_step": ms, "value": world * ns / (ms * 1e-3) / 1e6, "unit": UNIT, "kernel_ms": ms_k, "allreduce_ms": ms_ar,
+            "allreduce_bytes": words * 8, "nvlink_bytes_per_step_rank0": sent // max(args.steps, 1), "nccl_groups_per_step": colls / max(args.steps, 1),
+            "comm_nranks_seen": comm.nranks, "gpu_launches": launches, "hist_sum_ok": ok_sum,
+            "roofline": {"bound": "hbm", "achieved": ns * 2 * L / (ms_k * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": ns * 2 * L / (ms_k * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_read": 2 * L, "kernel": "K-STATS"}}
+
+
+def leg_collapse(args, ctx, comm, stream, rank, world, barrier, max_over_ranks, parity, H):
+    """BASELINE config (e), this GPU's share: 200 M / 8 reads x 50 bp, ~40 % repeats.  One step = fxg_dcollapse_run: K-ROUTE ->
+    exchange over NVLink (grouped ncclSend/ncclRecv) -> K-DEDUP on the owners -> gather of (hash, first, count) -> K-ORDER on rank 0."""
+    import numpy as np
+    import torch
+    import fastx_toolkit_b200 as F
+    Lc, Sc, seed = 50, 64, 20260925 + 4
+    nc = args.collapse_reads
+    cseq = torch.empty((nc, Sc), dtype=torch.uint8, device="cuda")
+    cq = torch.empty((nc, Sc), dtype=torch.uint8, device="cuda")
+    ctx.synth_dev(cseq, cq, nc, Lc, Sc, seed, H.DUPS, Q, first_read=rank * nc, n_total=world * nc)
+    ctx.sync()
+    del cq
+    dc = F.DCollapser(comm, Sc)
+    batch = F.Batch(cseq.data_ptr(), None, None, Lc, Sc, nc)
+    rep = None
+    for _ in range(max(args.warmup, 3)):
+        rep = dc.run([batch], [rank * nc])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0, c0, b0 = dc.launches(), comm.collectives(), comm.bytes_sent()
+    phases = np.zeros(5)
+    e0.record(stream)
+    for _ in range(args.steps):
+        rep = dc.run([batch], [rank * nc])
+        phases += np.array(list(rep.ms))
+    e1.record(stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    launches, colls, sent = dc.launches() - l0, comm.collectives() - c0, comm.bytes_sent() - b0
+    U = int(rep.n_unique)
+    ok = rep.first_bad_read == -1
+    if rank == 0:
+        oc = np.empty(U, np.uint64)
+        dc.fetch_order(None, None, None, oc)
+        ok = ok and int(oc.sum()) == world * nc and bool((oc[:-1] >= oc[1:]).all())
+    # parity: a small job through the same object against the oracle over the whole small input
+    mpar = min(args.parity_reads, nc)
+    pseq, _ = H.synth_slab(seed, world * mpar, Lc, H.DUPS)
+    dps = torch.from_numpy(pseq[rank * mpar:(rank + 1) * mpar]).cuda()
+    torch.cuda.synchronize()
+    prep = dc.run([F.Batch(dps.data_ptr(), None, None, Lc, Sc, mpar)], [rank * mpar])
+    if rank == 0:
+        pu = int(prep.n_unique)
+        pf, pc = np.empty(pu, np.int64), np.empty(pu, np.uint64)
+        dc.fetch_order(None, None, pf, pc)
+        efirst, ecnt = H.o_collapse(pseq, None, Lc, Sc)
+        parity["collapse_exchange"] = pu == len(ecnt) and bool(np.array_equal(pf, efirst)) and bool(np.array_equal(pc, ecnt)) and ok
+    else:
+        parity["collapse_exchange"] = bool(ok)
+    dc.close()
+    names = ["route", "exchange", "dedup", "gather", "order"]
+    return {"workload": "fastx_collapser on %d x %d bp per GPU, ~40 %% repeats (BASELINE config (e): 200 M reads over 8 GPUs), global dedup by "
+                        "owner = std::hash mod %d over NCCL send/recv, ordering pass on rank 0" % (nc, Lc, world),
+            "ms_per_step": ms, "value": world * nc / (ms * 1e-3) / 1e6, "unit": UNIT, "keys_per_s": world * nc / (ms * 1e-3),
+            "n_unique": U, "phase_ms_rank0": {k: float(v) / args.steps for k, v in zip(names, phases)},
+            "nvlink_bytes_per_step_rank0": sent // max(args.steps, 1), "nccl_groups_per_step": colls / max(args.steps, 1),
+            "comm_nranks_seen": comm.nranks, "gpu_launches": launches,
+            "timing": "CUDA events on the communicator's (= launch) stream around K blocking fxg_dcollapse_run calls, max over ranks"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -187,8 +314,12 @@ def main():
     ap.add_argument("--reads", type=int, default=100_000_000, help="reads per GPU (HBM-resident batch)")
     ap.add_argument("--e2e-reads", type=int, default=8_000_000, help="reads per GPU per e2e step (pinned host slabs)")
     ap.add_argument("--cpu-sample", type=int, default=3_000_000, help="reads in the single-core CPU baseline sample")
-    ap.add_argument("--ref-sample", type=int, default=100_000, help="reads per process per step for --impl reference")
+    ap.add_argument("--ref-sample", type=int, default=1_000_000, help="reads per process per step for --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stats-reads", type=int, default=62_500_000, help="reads per GPU in the quality_stats leg (config (d): 500 M / 8)")
+    ap.add_argument("--collapse-reads", type=int, default=25_000_000, help="reads per GPU in the collapser leg (config (e): 200 M / 8)")
+    ap.add_argument("--parity-reads", type=int, default=100_000, help="reads per GPU in the oracle parity checks (outside every timed region)")
+    ap.add_argument("--no-legs", action="store_true", help="skip the quality_stats / collapser legs")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -274,6 +405,34 @@ def main():
             ctx.trim_dev(batch, Q, T, MINLEN, out, rank * n)
         torch.cuda.synchronize()
     clocks = sampler.stop()
+
+    # ---------------- parity of the sharded result (outside every timed region; the oracle is the checker) ----------------
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import helpers as H          # oracle bindings + the numpy twin of the generator
+    mpar = min(args.parity_reads, n)
+    pseq, pqual = H.synth_slab(SEED, mpar, L, H.PLAIN, first=rank * n)
+    ptrim, _ = H.o_trim(pseq, pqual, None, L, STRIDE, Q, T, MINLEN)
+    parity = {"trim": bool(np.array_equal(out[:mpar].cpu().numpy(), ptrim))}
+
+    def all_ranks_true(flag):
+        if world == 1:
+            return bool(flag)
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    legs = {}
+    comm = None
+    if not args.no_legs:
+        from fastx_toolkit_b200 import dist as D
+        comm = D.native_comm(local_rank)                  # fxg_comm_init_rank: the product's own NCCL communicator
+        comm.set_stream(0, stream.cuda_stream)
+        legs["stats"] = leg_stats(args, ctx, comm, stream, dseq, dqual, n, rank, world, barrier, max_over_ranks, parity, H)
+        legs["collapse"] = leg_collapse(args, ctx, comm, stream, rank, world, barrier, max_over_ranks, parity, H)
+    parity_ok = all_ranks_true(all(parity.values()))
+    if not parity_ok:
+        raise SystemExit("bench.py: rank %d: sharded result differs from the oracle: %r" % (rank, parity))
 
     # ---------------- end to end, slab level: pinned SoA slabs -> H2D -> K-TRIM -> D2H (fxg_trim_host) ----------------
     ne = min(args.e2e_reads, n)
@@ -383,6 +542,9 @@ def main():
                                "h2d_bytes_per_step": world * ne * 2 * STRIDE, "d2h_bytes_per_step": world * ne * 4}},
         "gpu_launches": launches,
         "clocks": clocks,
+        "parity_checked": parity_ok,
+        "parity": {"checked_against": "oracle (CPU restatement) on %d reads per rank, outside the timed regions" % mpar, "results_rank0": parity},
+        "legs": legs,
     }
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -396,6 +558,8 @@ def main():
         }
     if rank == 0:
         print(json.dumps(line), flush=True)
+    if comm is not None:
+        comm.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

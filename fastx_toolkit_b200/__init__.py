@@ -5,6 +5,6 @@ The product is the C-ABI shared library ``libfxg.so`` (hand-written sm_100a CUDA
 ctypes binding used by the tests and ``bench.py``; there is no Python or CPU fallback — if the
 library is missing, or no GPU is usable, every call fails loudly.
 """
-from ._lib import FxgError, Context, Collapser, TextPipe, TextReport, Batch, BarcodeTable, ClipOpts, Stage, Report, collapse_order_dev, lib, lib_path  # noqa: F401
+from ._lib import FxgError, Context, Collapser, Comm, DCollapser, DCollapseReport, TextPipe, TextReport, Batch, BarcodeTable, ClipOpts, Stage, Report, collapse_order_dev, lib, lib_path  # noqa: F401
 
-__all__ = ["FxgError", "Context", "Collapser", "TextPipe", "TextReport", "Batch", "BarcodeTable", "ClipOpts", "Stage", "Report", "collapse_order_dev", "lib", "lib_path"]
+__all__ = ["FxgError", "Context", "Collapser", "Comm", "DCollapser", "DCollapseReport", "TextPipe", "TextReport", "Batch", "BarcodeTable", "ClipOpts", "Stage", "Report", "collapse_order_dev", "lib", "lib_path"]

@@ -46,6 +46,12 @@ class TextReport(C.Structure):
                 ("min_len", C.c_int32), ("reserved", C.c_int32), ("clip_class", C.c_int64 * 6)]
 
 
+class DCollapseReport(C.Structure):
+    """struct fxg_dcollapse_report"""
+    _fields_ = [("n_unique", C.c_int64), ("first_bad_read", C.c_int64), ("n_reads_local", C.c_int64), ("rows_received", C.c_int64),
+                ("n_unique_local", C.c_int64), ("bytes_sent", C.c_int64), ("ms", C.c_float * 5), ("reserved", C.c_float)]
+
+
 class Report(C.Structure):
     """struct fxg_report"""
     _fields_ = [("n_in", C.c_int64), ("n_out", C.c_int64), ("first_bad_read", C.c_int64), ("aux", C.c_int64 * 6)]
@@ -102,6 +108,26 @@ def lib():
         "fxg_hash_dev": (i32, [vp, BP, vp]),
         "fxg_comm_init_all": (i32, [i32, C.POINTER(i32), C.POINTER(vp)]),
         "fxg_comm_allreduce_u64": (i32, [vp, C.POINTER(vp), sz]),
+        "fxg_comm_unique_id": (i32, [vp]),
+        "fxg_comm_init_rank": (i32, [i32, i32, i32, vp, C.POINTER(vp)]),
+        "fxg_comm_nranks": (i32, [vp]),
+        "fxg_comm_nlocal": (i32, [vp]),
+        "fxg_comm_rank": (i32, [vp, i32]),
+        "fxg_comm_device": (i32, [vp, i32]),
+        "fxg_comm_set_stream": (i32, [vp, i32, vp, i32]),
+        "fxg_comm_sync": (i32, [vp]),
+        "fxg_comm_allgather": (i32, [vp, C.POINTER(vp), C.POINTER(vp), sz]),
+        "fxg_comm_alltoallv": (i32, [vp, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), sz]),
+        "fxg_comm_gatherv": (i32, [vp, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), vp, i32, sz]),
+        "fxg_comm_bytes_sent": (i64, [vp]),
+        "fxg_comm_collectives": (i64, [vp]),
+        "fxg_dcollapse_new": (i32, [vp, C.c_int32, C.POINTER(vp)]),
+        "fxg_dcollapse_free": (None, [vp]),
+        "fxg_dcollapse_run": (i32, [vp, BP, C.POINTER(i64), C.POINTER(vp), i32, C.POINTER(DCollapseReport)]),
+        "fxg_dcollapse_fetch_local": (i32, [vp, i32, vp, vp, vp, vp, vp]),
+        "fxg_dcollapse_fetch_order": (i32, [vp, vp, vp, vp, vp]),
+        "fxg_dcollapse_error": (C.c_char_p, [vp]),
+        "fxg_dcollapse_launches": (i64, [vp]),
         "fxg_comm_free": (None, [vp]),
         "fxg_comm_error": (C.c_char_p, [vp]),
         "fxg_validate_dev": (i32, [vp, BP, i32, i64]),
@@ -188,6 +214,116 @@ class Collapser:
             self.h = None
 
     __del__ = close
+
+
+class Comm:
+    """fxg_comm: the native NCCL communicator over the GPUs this process drives.
+    Comm.all(devices)              one process, several GPUs (ncclCommInitAll)
+    Comm.rank(device, n, r, id)    one GPU per process; `id` = Comm.unique_id() made on one rank and handed to the others"""
+
+    def __init__(self, handle):
+        self.L, self.h = lib(), handle
+
+    @staticmethod
+    def unique_id():
+        buf = C.create_string_buffer(128)
+        rc = lib().fxg_comm_unique_id(buf)
+        if rc != FXG_OK:
+            raise FxgError(rc, "fxg_comm_unique_id: " + lib().fxg_comm_error(None).decode())
+        return buf.raw
+
+    @classmethod
+    def all(cls, devices):
+        h = C.c_void_p()
+        arr = (C.c_int * len(devices))(*devices)
+        rc = lib().fxg_comm_init_all(len(devices), arr, C.byref(h))
+        if rc != FXG_OK:
+            raise FxgError(rc, "fxg_comm_init_all: " + lib().fxg_comm_error(None).decode())
+        return cls(h)
+
+    @classmethod
+    def rank(cls, device, nranks, rank, uid):
+        h = C.c_void_p()
+        rc = lib().fxg_comm_init_rank(device, nranks, rank, C.c_char_p(uid), C.byref(h))
+        if rc != FXG_OK:
+            raise FxgError(rc, "fxg_comm_init_rank: " + lib().fxg_comm_error(None).decode())
+        return cls(h)
+
+    def _ck(self, rc):
+        if rc != FXG_OK:
+            raise FxgError(rc, self.L.fxg_comm_error(self.h).decode() or self.L.fxg_strerror(rc).decode())
+
+    @property
+    def nranks(self):
+        return self.L.fxg_comm_nranks(self.h)
+
+    @property
+    def nlocal(self):
+        return self.L.fxg_comm_nlocal(self.h)
+
+    def set_stream(self, local_index, stream_handle, adopt=True):
+        self._ck(self.L.fxg_comm_set_stream(self.h, local_index, C.c_void_p(stream_handle), 1 if adopt else 0))
+
+    def sync(self):
+        self._ck(self.L.fxg_comm_sync(self.h))
+
+    def allreduce_u64(self, bufs, count):
+        """bufs: one device tensor / address per local GPU (u64 counters), summed in place across all ranks"""
+        arr = (C.c_void_p * len(bufs))(*[_ptr(b) for b in bufs])
+        self._ck(self.L.fxg_comm_allreduce_u64(self.h, arr, count))
+
+    def bytes_sent(self):
+        return int(self.L.fxg_comm_bytes_sent(self.h))
+
+    def collectives(self):
+        return int(self.L.fxg_comm_collectives(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.fxg_comm_free(self.h)
+            self.h = None
+
+
+class DCollapser:
+    """fxg_dcollapse: fastx_collapser across the GPUs of a Comm (owner = std::hash mod nranks)."""
+
+    def __init__(self, comm, stride):
+        self.L, self.comm, self.stride = lib(), comm, stride
+        h = C.c_void_p()
+        rc = self.L.fxg_dcollapse_new(comm.h, stride, C.byref(h))
+        if rc != FXG_OK:
+            raise FxgError(rc, "fxg_dcollapse_new: " + self.L.fxg_strerror(rc).decode())
+        self.h = h
+
+    def _ck(self, rc):
+        if rc != FXG_OK:
+            raise FxgError(rc, self.L.fxg_dcollapse_error(self.h).decode() or self.L.fxg_strerror(rc).decode())
+
+    def run(self, batches, index_bases, weights=None, root=0):
+        """batches: one Batch per local GPU (device slabs); returns DCollapseReport"""
+        n = len(batches)
+        arr = (Batch * n)(*batches)
+        bases = (C.c_int64 * n)(*index_bases)
+        w = None
+        if weights is not None:
+            w = (C.c_void_p * n)(*[_ptr(x) for x in weights])
+        rep = DCollapseReport()
+        self._ck(self.L.fxg_dcollapse_run(self.h, arr, bases, w, root, C.byref(rep)))
+        return rep
+
+    def fetch_local(self, local_index, out_seq=None, out_len=None, out_count=None, out_first=None, out_hash=None):
+        self._ck(self.L.fxg_dcollapse_fetch_local(self.h, local_index, _ptr(out_seq), _ptr(out_len), _ptr(out_count), _ptr(out_first), _ptr(out_hash)))
+
+    def fetch_order(self, perm_owner=None, perm_index=None, ordered_first=None, ordered_count=None):
+        self._ck(self.L.fxg_dcollapse_fetch_order(self.h, _ptr(perm_owner), _ptr(perm_index), _ptr(ordered_first), _ptr(ordered_count)))
+
+    def launches(self):
+        return int(self.L.fxg_dcollapse_launches(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.fxg_dcollapse_free(self.h)
+            self.h = None
 
 
 class TextPipe:

@@ -16,6 +16,7 @@
 
 #include "fxg.h"
 #include "fxg_kernels.cuh"
+#include "fxg_collapse.cuh"
 
 namespace fxg {
 
@@ -68,27 +69,15 @@ __device__ __forceinline__ bool rows_equal(const uint8_t *a, const uint8_t *b, i
     return true;
 }
 
-struct DedupParams {
-    const uint8_t *keys;        // owned slab: row r at keys + r*stride
-    const int32_t *len;         // per-row length
-    int32_t stride;
-    int64_t row0, n;            // rows [row0, row0+n) are inserted by this launch
-    const int32_t *weight;      // per-row (relative to row0) weight, NULL = 1
-    const int64_t *first;       // per-row explicit first-occurrence index, NULL = index_base + row
-    int64_t index_base;
-    uint64_t *hash;             // per-row hash (out)
-    unsigned long long *slots;  // table: (tag32 << 32) | (rep_row + 1), 0 = empty
-    uint64_t mask;              // table size - 1
-    unsigned long long *count;  // per slot
-    unsigned long long *firsts; // per slot (min)
-    unsigned long long *counters;
-};
-
 __global__ void __launch_bounds__(256) k_hash_dedup(const DedupParams P)
 {
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < P.n; t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = P.row0 + t;
-        const int L = __ldg(P.len + r);
+        RowMeta m;
+        if (P.meta) m = P.meta[r];
+        const int L = P.meta ? m.len : __ldg(P.len + r);
+        const unsigned long long f = P.meta ? (unsigned long long)m.first
+                                            : (P.first ? (unsigned long long)__ldg(P.first + t) : (unsigned long long)(P.index_base + t));
         const uint8_t *row = P.keys + (size_t)r * P.stride;
         // validate bases (the reader would have rejected the record: fastx.c:45-54, 361-364)
         bool bad = (L <= 0 || L > P.stride);
@@ -101,7 +90,7 @@ __global__ void __launch_bounds__(256) k_hash_dedup(const DedupParams P)
                     if (seq_bad_bits(ws[w]) & head_mask(L - 16 * c - 4 * w)) bad = true;
             }
         }
-        if (bad) { atomicMin(&P.counters[CNT_FIRST_BAD], (unsigned long long)(P.index_base + t)); continue; }
+        if (bad) { atomicMin(&P.counters[CNT_FIRST_BAD], P.meta ? f : (unsigned long long)(P.index_base + t)); continue; }
 
         const uint64_t h = hash_row(row, L);
         P.hash[r] = h;
@@ -115,12 +104,12 @@ __global__ void __launch_bounds__(256) k_hash_dedup(const DedupParams P)
             }
             if ((cur >> 32) == (h >> 32)) {
                 const int64_t rep = (int64_t)(cur & 0xFFFFFFFFull) - 1;
-                if (__ldg(P.len + rep) == L && rows_equal(P.keys + (size_t)rep * P.stride, row, L)) break;
+                const int Lr = P.meta ? P.meta[rep].len : __ldg(P.len + rep);
+                if (Lr == L && rows_equal(P.keys + (size_t)rep * P.stride, row, L)) break;
             }
             slot = (slot + 1) & P.mask;
         }
-        const unsigned long long w = P.weight ? (unsigned long long)__ldg(P.weight + t) : 1ull;
-        const unsigned long long f = P.first ? (unsigned long long)__ldg(P.first + t) : (unsigned long long)(P.index_base + t);
+        const unsigned long long w = P.meta ? (unsigned long long)m.weight : (P.weight ? (unsigned long long)__ldg(P.weight + t) : 1ull);
         atomicAdd(&P.count[slot], w);
         atomicMin(&P.firsts[slot], f);
     }
@@ -169,40 +158,39 @@ __global__ void __launch_bounds__(256) k_compact(const unsigned long long *slots
 // ---------------------------------------------------------------------------------------------------
 __global__ void k_iota(uint32_t *p, uint32_t n) { for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) p[t] = t; }
 
-// seq[p] = id of the unique at position p; bucket[p] = hash[id] % B
-__global__ void k_bucket(const uint32_t *seq, const uint64_t *hash, uint64_t B, uint32_t m, uint32_t *bucket, uint32_t *pos)
+// One epoch of the map's life (bucket count B, node sequence seq[0..m)): a node goes to the front of its bucket's chain,
+// or to the global list head when the bucket is still empty.  So the epoch's result is seq sorted by (first-touch position
+// of the node's bucket: descending, own position: descending) = the REVERSE of a stable ascending sort by the bucket's
+// first-touch position alone (the input already is in position order).  k_touch_min finds that position per bucket
+// (atomicMin into a table over the B buckets), k_touch_key reads it back as the 32-bit sort key.
+__global__ void __launch_bounds__(256) k_touch_min(const uint32_t *seq, const uint64_t *hash, uint64_t B, uint32_t m, uint32_t *bucket, uint32_t *touch)
 {
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < m; t += gridDim.x * blockDim.x) {
-        bucket[t] = (uint32_t)(hash[seq[t]] % B);
-        pos[t] = t;
+        const uint32_t b = (uint32_t)(hash[seq[t]] % B);
+        bucket[t] = b;
+        atomicMin(&touch[b], t);
     }
 }
-// after sorting (bucket, pos) by bucket (stable): head index of each run (0 elsewhere) for a max-scan
-__global__ void k_run_heads(const uint32_t *bucket_sorted, uint32_t m, uint32_t *head)
+__global__ void __launch_bounds__(256) k_touch_key(const uint32_t *bucket, const uint32_t *touch, uint32_t m, uint32_t *key)
 {
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < m; t += gridDim.x * blockDim.x)
-        head[t] = (t == 0 || bucket_sorted[t] != bucket_sorted[t - 1]) ? t : 0u;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < m; t += gridDim.x * blockDim.x) key[t] = touch[bucket[t]];
 }
-// key = (first-touch position of the bucket << 32) | own position ; value = unique id
-__global__ void k_touch_keys(const uint32_t *pos_sorted, const uint32_t *head_scanned, const uint32_t *seq, uint32_t m,
-                             uint64_t *key, uint32_t *val)
-{
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < m; t += gridDim.x * blockDim.x) {
-        const uint32_t p = pos_sorted[t];
-        const uint32_t touch = pos_sorted[head_scanned[t]];
-        key[t] = ((uint64_t)touch << 32) | p;
-        val[t] = seq[p];
-    }
-}
-__global__ void k_reverse(const uint32_t *in, uint32_t *out, uint32_t n)
+__global__ void __launch_bounds__(256) k_reverse(const uint32_t *in, uint32_t *out, uint32_t n)
 {
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) out[t] = in[n - 1 - t];
 }
-__global__ void k_gather_u64(const uint64_t *src, const uint32_t *idx, uint64_t *dst, uint32_t n)
+__global__ void __launch_bounds__(256) k_gather_u64(const uint64_t *src, const uint32_t *idx, uint64_t *dst, uint32_t n)
 {
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) dst[t] = src[idx[t]];
 }
-__global__ void k_gather_rows(const uint8_t *keys, const int32_t *len, const uint32_t *rep, const uint32_t *perm, int stride,
+__global__ void __launch_bounds__(256) k_max_u64(const uint64_t *src, uint32_t n, unsigned long long *out)
+{
+    unsigned long long m = 0;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) { const unsigned long long v = src[t]; m = v > m ? v : m; }
+    for (int o = 16; o; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xffffffffu, m, o); m = v > m ? v : m; }
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+__global__ void k_gather_rows(const uint8_t *keys, const int32_t *len, const RowMeta *meta, const uint32_t *rep, const uint32_t *perm, int stride,
                               uint32_t n, uint8_t *out_rows, int32_t *out_len)
 {
     const int chunks = stride >> 4;
@@ -212,11 +200,9 @@ __global__ void k_gather_rows(const uint8_t *keys, const int32_t *len, const uin
         const int c = (int)(t - (uint64_t)i * chunks);
         const uint32_t r = rep[perm ? perm[i] : i];
         reinterpret_cast<uint4 *>(out_rows + (size_t)i * stride)[c] = __ldg(reinterpret_cast<const uint4 *>(keys + (size_t)r * stride) + c);
-        if (c == 0 && out_len) out_len[i] = len[r];
+        if (c == 0 && out_len) out_len[i] = meta ? meta[r].len : len[r];
     }
 }
-
-struct MaxOp { __device__ __forceinline__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; } };
 
 }  // namespace fxg
 
@@ -240,40 +226,61 @@ static const int kLadderN = (int)(sizeof(kLadder) / sizeof(kLadder[0]));
     } while (0)
 
 static inline unsigned grid_for(uint64_t n) { uint64_t b = (n + 255) / 256; if (b > 148 * 32) b = 148 * 32; if (b < 1) b = 1; return (unsigned)b; }
+static inline int bits_for(uint64_t max_value) { int b = 1; while (b < 64 && (max_value >> b)) b++; return b; }
+
+// scratch of the ordering pass: stream-ordered allocations from the device's default pool (kept cached between calls)
+static void pool_keep_memory(void)
+{
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess) return;
+    uint64_t thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+}
 
 // Final permutation of U uniques from (hash, first, count) — usable on one GPU or on the gathered triples
 // of many.  perm[k] = index (into the input arrays) of the unique printed at rank k.
 int fxg_order_impl(const uint64_t *d_hash, const uint64_t *d_first, const uint64_t *d_count, uint32_t U, uint32_t *d_perm,
-                   cudaStream_t st, char *errbuf, size_t errlen, int64_t *launches)
+                   uint64_t max_first, cudaStream_t st, char *errbuf, size_t errlen, int64_t *launches)
 {
     int rc = FXG_OK;
     if (U == 0) return rc;
-    uint32_t *ids_a = NULL, *ids_b = NULL, *bucket_a = NULL, *bucket_b = NULL, *pos_a = NULL, *pos_b = NULL, *head = NULL, *ord = NULL;
-    uint64_t *key_a = NULL, *key_b = NULL, *cnt_g = NULL, *cnt_s = NULL;
+    uint32_t *ids_a = NULL, *ids_b = NULL, *ord = NULL, *ord_s = NULL, *bucket = NULL, *key = NULL, *key_s = NULL, *touch = NULL;
+    uint64_t *k64_a = NULL, *k64_b = NULL;
+    unsigned long long *d_max = NULL, h_max = 0;
     void *tmp = NULL;
     size_t tmp_bytes = 0, need = 0;
     const unsigned G = grid_for(U);
+    const int ubits = bits_for(U);
+    const int fbits = max_first ? bits_for(max_first) : 64;
+    uint64_t Bmax = kLadder[kLadderN - 1];
+    for (int k = 0; k < kLadderN; k++) if (kLadder[k] >= (uint64_t)U) { Bmax = kLadder[k]; break; }
+    if (Bmax < (uint64_t)U) { snprintf(errbuf, errlen, "collapser: more than %llu unique sequences", (unsigned long long)kLadder[kLadderN - 1]); return FXG_ERR_UNSUPPORTED; }
 
-    CKC(cudaMalloc(&ids_a, (size_t)U * 4)); CKC(cudaMalloc(&ids_b, (size_t)U * 4));
-    CKC(cudaMalloc(&bucket_a, (size_t)U * 4)); CKC(cudaMalloc(&bucket_b, (size_t)U * 4));
-    CKC(cudaMalloc(&pos_a, (size_t)U * 4)); CKC(cudaMalloc(&pos_b, (size_t)U * 4));
-    CKC(cudaMalloc(&head, (size_t)U * 4)); CKC(cudaMalloc(&ord, (size_t)U * 4));
-    CKC(cudaMalloc(&key_a, (size_t)U * 8)); CKC(cudaMalloc(&key_b, (size_t)U * 8));
-    CKC(cudaMalloc(&cnt_g, (size_t)U * 8)); CKC(cudaMalloc(&cnt_s, (size_t)U * 8));
+    pool_keep_memory();
+    CKC(cudaMallocAsync(&ids_a, (size_t)U * 4, st)); CKC(cudaMallocAsync(&ids_b, (size_t)U * 4, st));
+    CKC(cudaMallocAsync(&ord, (size_t)U * 4, st)); CKC(cudaMallocAsync(&ord_s, (size_t)U * 4, st));
+    CKC(cudaMallocAsync(&bucket, (size_t)U * 4, st)); CKC(cudaMallocAsync(&key, (size_t)U * 4, st)); CKC(cudaMallocAsync(&key_s, (size_t)U * 4, st));
+    CKC(cudaMallocAsync(&touch, (size_t)Bmax * 4, st));
+    CKC(cudaMallocAsync(&k64_a, (size_t)U * 8, st)); CKC(cudaMallocAsync(&k64_b, (size_t)U * 8, st));
+    CKC(cudaMallocAsync(&d_max, 8, st));
     // temp storage large enough for every CUB call below at size U
-    cub::DeviceRadixSort::SortPairs(NULL, need, key_a, key_b, ids_a, ids_b, (int)U, 0, 64, st); tmp_bytes = need;
-    cub::DeviceRadixSort::SortPairsDescending(NULL, need, key_a, key_b, ids_a, ids_b, (int)U, 0, 64, st); if (need > tmp_bytes) tmp_bytes = need;
-    cub::DeviceRadixSort::SortPairs(NULL, need, bucket_a, bucket_b, pos_a, pos_b, (int)U, 0, 32, st); if (need > tmp_bytes) tmp_bytes = need;
-    cub::DeviceScan::InclusiveScan(NULL, need, head, head, MaxOp(), (int)U, st); if (need > tmp_bytes) tmp_bytes = need;
-    CKC(cudaMalloc(&tmp, tmp_bytes + 16));
+    cub::DeviceRadixSort::SortPairs(NULL, need, k64_a, k64_b, ids_a, ids_b, (int)U, 0, 64, st); tmp_bytes = need;
+    cub::DeviceRadixSort::SortPairsDescending(NULL, need, k64_a, k64_b, ids_a, ids_b, (int)U, 0, 64, st); if (need > tmp_bytes) tmp_bytes = need;
+    cub::DeviceRadixSort::SortPairs(NULL, need, key, key_s, ord, ord_s, (int)U, 0, 32, st); if (need > tmp_bytes) tmp_bytes = need;
+    CKC(cudaMallocAsync(&tmp, tmp_bytes + 16, st));
 
     // 1. first-occurrence order: ids sorted by `first` ascending  -> ids_b
     k_iota<<<G, 256, 0, st>>>(ids_a, U);
-    CKC(cudaMemcpyAsync(key_a, d_first, (size_t)U * 8, cudaMemcpyDeviceToDevice, st));
+    CKC(cudaMemcpyAsync(k64_a, d_first, (size_t)U * 8, cudaMemcpyDeviceToDevice, st));
     need = tmp_bytes;
-    CKC(cub::DeviceRadixSort::SortPairs(tmp, need, key_a, key_b, ids_a, ids_b, (int)U, 0, 64, st));
-    *launches += 8;
-    // ids_b = ids in first-occurrence order; `ord` holds the map's iteration order over the first m keys
+    CKC(cub::DeviceRadixSort::SortPairs(tmp, need, k64_a, k64_b, ids_a, ids_b, (int)U, 0, fbits, st));
+    // the largest count sizes the last sort's passes
+    CKC(cudaMemsetAsync(d_max, 0, 8, st));
+    k_max_u64<<<G, 256, 0, st>>>(d_count, U, d_max);
+    CKC(cudaMemcpyAsync(&h_max, d_max, 8, cudaMemcpyDeviceToHost, st));
+    *launches += 2 + (fbits + 7) / 8 + 1;
+    // 2. the epochs.  ord[0..m) = the map's iteration order over the first m keys; ord_s = its reverse after the last epoch
     {
         uint32_t m = 0;   // keys already in the map
         for (int k = 0; k < kLadderN && m < U; k++) {
@@ -282,30 +289,30 @@ int fxg_order_impl(const uint64_t *d_hash, const uint64_t *d_first, const uint64
             // seq = ord[0..m) ++ ids_b[m..m2)
             if (m2 > m) CKC(cudaMemcpyAsync(ord + m, ids_b + m, (size_t)(m2 - m) * 4, cudaMemcpyDeviceToDevice, st));
             const unsigned g2 = grid_for(m2);
-            k_bucket<<<g2, 256, 0, st>>>(ord, d_hash, B, m2, bucket_a, pos_a);
+            CKC(cudaMemsetAsync(touch, 0xFF, (size_t)B * 4, st));
+            k_touch_min<<<g2, 256, 0, st>>>(ord, d_hash, B, m2, bucket, touch);
+            k_touch_key<<<g2, 256, 0, st>>>(bucket, touch, m2, key);
             need = tmp_bytes;
-            CKC(cub::DeviceRadixSort::SortPairs(tmp, need, bucket_a, bucket_b, pos_a, pos_b, (int)m2, 0, 32, st));
-            k_run_heads<<<g2, 256, 0, st>>>(bucket_b, m2, head);
-            need = tmp_bytes;
-            CKC(cub::DeviceScan::InclusiveScan(tmp, need, head, head, MaxOp(), (int)m2, st));
-            k_touch_keys<<<g2, 256, 0, st>>>(pos_b, head, ord, m2, key_a, ids_a);
-            need = tmp_bytes;
-            CKC(cub::DeviceRadixSort::SortPairsDescending(tmp, need, key_a, key_b, ids_a, ord, (int)m2, 0, 64, st));
-            *launches += 12;
+            CKC(cub::DeviceRadixSort::SortPairs(tmp, need, key, key_s, ord, ord_s, (int)m2, 0, bits_for(m2), st));
+            *launches += 3 + (bits_for(m2) + 7) / 8 + 1;
             m = m2;
+            if (m < U) { k_reverse<<<g2, 256, 0, st>>>(ord_s, ord, m2); *launches += 1; }
         }
-        if (m < U) { snprintf(errbuf, errlen, "collapser: more than %llu unique sequences", (unsigned long long)kLadder[kLadderN - 1]); rc = FXG_ERR_UNSUPPORTED; goto done; }
     }
-    // 2. count descending, ties by iteration position descending: reverse the order, then a stable sort by count
-    k_reverse<<<G, 256, 0, st>>>(ord, ids_a, U);
-    k_gather_u64<<<G, 256, 0, st>>>(d_count, ids_a, cnt_g, U);
+    // 3. count descending, ties by iteration position descending: ord_s already is the reversed iteration order, so a
+    //    stable descending sort by count finishes it
+    CKC(cudaStreamSynchronize(st));      // h_max
+    k_gather_u64<<<G, 256, 0, st>>>(d_count, ord_s, k64_a, U);
     need = tmp_bytes;
-    CKC(cub::DeviceRadixSort::SortPairsDescending(tmp, need, cnt_g, cnt_s, ids_a, d_perm, (int)U, 0, 64, st));
-    *launches += 6;
+    CKC(cub::DeviceRadixSort::SortPairsDescending(tmp, need, k64_a, k64_b, ord_s, d_perm, (int)U, 0, bits_for(h_max), st));
+    *launches += 2 + (bits_for(h_max) + 7) / 8;
+    (void)ubits;
     CKC(cudaStreamSynchronize(st));
 done:
-    cudaFree(ids_a); cudaFree(ids_b); cudaFree(bucket_a); cudaFree(bucket_b); cudaFree(pos_a); cudaFree(pos_b);
-    cudaFree(head); cudaFree(ord); cudaFree(key_a); cudaFree(key_b); cudaFree(cnt_g); cudaFree(cnt_s); cudaFree(tmp);
+    {
+        void *scratch[] = { ids_a, ids_b, ord, ord_s, bucket, key, key_s, touch, k64_a, k64_b, d_max, tmp };
+        for (void *q : scratch) if (q) cudaFreeAsync(q, st);
+    }
     return rc;
 }
 
@@ -402,7 +409,7 @@ extern "C" int fxg_collapse_add(fxg_collapser *c, const fxg_batch *b, const int3
         const int64_t nr = (b->n - r < chunk) ? (b->n - r) : chunk;
         CKO(c, cudaMemcpyAsync(c->keys + (size_t)(row0 + r) * S, b->seq + (size_t)r * S, (size_t)nr * S, cudaMemcpyDefault, c->st));
         DedupParams p;
-        p.keys = c->keys; p.len = c->len; p.stride = c->stride; p.row0 = row0 + r; p.n = nr;
+        p.keys = c->keys; p.len = c->len; p.meta = NULL; p.stride = c->stride; p.row0 = row0 + r; p.n = nr;
         p.weight = d_w ? d_w + r : NULL; p.first = d_f ? d_f + r : NULL; p.index_base = index_base + r;
         p.hash = c->hash; p.slots = c->slots; p.mask = c->nslots - 1; p.count = c->count; p.firsts = c->firsts;
         p.counters = c->d_counters;
@@ -443,7 +450,7 @@ extern "C" int fxg_collapse_finish(fxg_collapser *c, int order, int64_t *n_uniqu
     if (n_unique) *n_unique = c->U;
     if (order && U > 0) {
         CKO(c, cudaMalloc(&c->perm, (size_t)U * 4));
-        int rc = fxg_order_impl(c->u_hash, c->u_first, c->u_count, (uint32_t)U, c->perm, c->st, c->err, sizeof(c->err), &c->launches);
+        int rc = fxg_order_impl(c->u_hash, c->u_first, c->u_count, (uint32_t)U, c->perm, 0, c->st, c->err, sizeof(c->err), &c->launches);
         if (rc) return rc;
     }
     return FXG_OK;
@@ -473,7 +480,7 @@ extern "C" int fxg_collapse_fetch(fxg_collapser *c, uint8_t *out_seq, int32_t *o
     if (out_seq || out_len) {
         uint8_t *rows = NULL; int32_t *lens = NULL;
         CKO(c, cudaMalloc(&rows, (size_t)U * c->stride)); CKO(c, cudaMalloc(&lens, (size_t)U * 4));
-        k_gather_rows<<<grid_for((uint64_t)U * (c->stride >> 4)), 256, 0, c->st>>>(c->keys, c->len, c->u_rep, c->perm, c->stride, U, rows, lens);
+        k_gather_rows<<<grid_for((uint64_t)U * (c->stride >> 4)), 256, 0, c->st>>>(c->keys, c->len, NULL, c->u_rep, c->perm, c->stride, U, rows, lens);
         c->launches++;
         if (out_seq) CKO(c, cudaMemcpyAsync(out_seq, rows, (size_t)U * c->stride, cudaMemcpyDefault, c->st));
         if (out_len) CKO(c, cudaMemcpyAsync(out_len, lens, (size_t)U * 4, cudaMemcpyDefault, c->st));
@@ -494,13 +501,31 @@ extern "C" int fxg_collapse_order_dev(int device, const uint64_t *hash_dev, cons
     cudaStream_t st;
     if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return FXG_ERR_CUDA;
     cudaDeviceSynchronize();   // the triples usually come from another stream (collective output)
-    int rc = fxg_order_impl(hash_dev, first_dev, count_dev, (uint32_t)n_unique, perm_dev, st, err, sizeof(err), &launches);
+    int rc = fxg_order_impl(hash_dev, first_dev, count_dev, (uint32_t)n_unique, perm_dev, 0, st, err, sizeof(err), &launches);
     if (rc) fprintf(stderr, "fxg_collapse_order_dev: %s\n", err);
     cudaStreamDestroy(st);
     return rc;
 }
 
 namespace fxg {
+cudaError_t launch_hash_dedup(const DedupParams &p, cudaStream_t st)
+{
+    k_hash_dedup<<<grid_for((uint64_t)p.n), 256, 0, st>>>(p);
+    return cudaGetLastError();
+}
+cudaError_t launch_compact(const unsigned long long *slots, const unsigned long long *count, const unsigned long long *firsts,
+                           const uint64_t *hash, int64_t nslots, unsigned long long *n_out, uint32_t *u_rep, uint64_t *u_hash,
+                           uint64_t *u_first, uint64_t *u_count, cudaStream_t st)
+{
+    k_compact<<<grid_for((uint64_t)nslots), 256, 0, st>>>(slots, count, firsts, hash, nslots, n_out, u_rep, u_hash, u_first, u_count);
+    return cudaGetLastError();
+}
+cudaError_t launch_gather_rows(const uint8_t *keys, const int32_t *len, const RowMeta *meta, const uint32_t *rep, const uint32_t *perm,
+                               int stride, uint32_t n, uint8_t *out_rows, int32_t *out_len, cudaStream_t st)
+{
+    k_gather_rows<<<grid_for((uint64_t)n * (stride >> 4)), 256, 0, st>>>(keys, len, meta, rep, perm, stride, n, out_rows, out_len);
+    return cudaGetLastError();
+}
 cudaError_t launch_hash(const uint8_t *seq, const int32_t *len, int uniform_len, int stride, int64_t n, uint64_t *out, cudaStream_t st)
 {
     k_hash<<<grid_for((uint64_t)n), 256, 0, st>>>(seq, len, uniform_len, stride, n, out);

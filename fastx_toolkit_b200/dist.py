@@ -1,17 +1,27 @@
-"""Multi-GPU plumbing (one process per GPU, torch.distributed): the only places where the FASTX hot path really
-exchanges data.
+"""Multi-GPU plumbing for jobs launched one process per GPU (torchrun).
+
+The data-path collectives are NATIVE (include/fxg.h: fxg_comm_allreduce_u64 for fastx_quality_stats, fxg_dcollapse_* for the
+collapser's owner exchange); torch.distributed only hands the 128-byte NCCL id from rank 0 to the others -> `native_comm`.
 
   * trim / filter / clip / revcomp are pure maps: ranks own contiguous read blocks (`shard_bounds`), no collective.
-  * fastx_quality_stats: all-reduce (SUM) of the u64 hist[cycle][5][109] partials           -> `allreduce_hist`
-  * fastx_collapser: local uniques routed to owner = std::hash mod world (all-to-all), owners merge, the
-    (hash, first, count, key) rows of all owners are gathered on every rank for the single ordering pass
-                                                                                               -> `route_to_owners`, `gather_rows`
-
-Everything here is device-agnostic tensor plumbing (NCCL on GPUs, gloo in the CPU tests); the kernels stay behind
-the C ABI (fastx_toolkit_b200._lib).
+  * `owner_of`, `route_to_owners`, `gather_rows`, `allreduce_hist`: a device-agnostic MODEL of the same exchange on
+    torch.distributed tensors.  It runs on CPU with gloo, which is what tests/test_dist_gloo.py uses to check the
+    partition / merge logic at world sizes 2 and 3 without a GPU; the GPU path does not call it.
 """
 import torch
 import torch.distributed as dist
+
+
+def native_comm(local_device):
+    """fxg_comm over all ranks of the torch.distributed job: rank 0 makes the NCCL unique id, a broadcast (any backend)
+    hands it to the others, every rank joins with fxg_comm_init_rank.  Returns fastx_toolkit_b200.Comm."""
+    from . import _lib
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    box = [_lib.Comm.unique_id() if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(box, src=0)
+    return _lib.Comm.rank(local_device, world, rank, box[0])
 
 
 def shard_bounds(n, world):

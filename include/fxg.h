@@ -176,15 +176,69 @@ int64_t     fxg_collapse_launches(const fxg_collapser *c);
 int         fxg_collapse_order_dev(int device, const uint64_t *hash_dev, const uint64_t *first_dev, const uint64_t *count_dev,
                                    int64_t n_unique, uint32_t *perm_dev);
 
-/* ---- the one native collective: all-reduce of the quality-stats histograms ------------------------
- * One process driving several GPUs (the drop-in tools with FASTX_GPUS=N): ncclCommInitAll over `devices`, then an
- * in-place ncclSum/ncclUint64 all-reduce of one buffer per device.  NCCL is dlopen()ed at the first call.
- * (Multi-process jobs — torchrun — all-reduce the same buffers with their own communicator.) */
+/* ---- the native collectives ------------------------------------------------------------------------
+ * A communicator drives the GPUs THIS PROCESS owns: every GPU of the box for the drop-in tools (fxg_comm_init_all:
+ * ncclCommInitAll over `devices`), or one GPU per process for torchrun / mpirun style jobs (fxg_comm_init_rank: rank 0
+ * makes the 128-byte id with fxg_comm_unique_id() and whatever launched the job hands it to the other ranks).  NCCL is
+ * dlopen()ed at the first call.  Collectives are enqueued on the communicator's own streams (after a device-wide wait
+ * for earlier work), or on streams adopted from the caller (fxg_comm_set_stream, then plain stream order applies);
+ * fxg_comm_sync() waits for them.
+ *   fxg_comm_allreduce_u64  the fastx_quality_stats reduction: in-place ncclSum of one u64 histogram per local GPU
+ *                           (src/fastx_quality_stats/fastx_quality_stats.c:166-216 accumulates ONE table; G GPUs hold G partials)
+ *   fxg_comm_allgather      small fixed-size all-gather (count matrices)
+ *   fxg_comm_alltoallv      the collapser's owner exchange: grouped ncclSend/ncclRecv with per-peer counts/offsets
+ *                           (elements of elem_bytes bytes; arrays indexed [local GPU * nranks + peer], host memory)
+ *   fxg_comm_gatherv        variable-size gather to one rank (cnt/off: nranks entries, elements)                          */
+#define FXG_COMM_ID_BYTES 128
 typedef struct fxg_comm fxg_comm;
 int         fxg_comm_init_all(int ndev, const int *devices, fxg_comm **out);
+int         fxg_comm_unique_id(void *id_out /* FXG_COMM_ID_BYTES */);
+int         fxg_comm_init_rank(int device, int nranks, int rank, const void *id, fxg_comm **out);
+int         fxg_comm_nranks(const fxg_comm *c);
+int         fxg_comm_nlocal(const fxg_comm *c);
+int         fxg_comm_rank(const fxg_comm *c, int local_index);
+int         fxg_comm_device(const fxg_comm *c, int local_index);
+int         fxg_comm_set_stream(fxg_comm *c, int local_index, void *cuda_stream, int adopt);
+int         fxg_comm_sync(fxg_comm *c);
 int         fxg_comm_allreduce_u64(fxg_comm *c, uint64_t *const *bufs_dev, size_t count);
+int         fxg_comm_allgather(fxg_comm *c, const void *const *send_dev, void *const *recv_dev, size_t bytes);
+int         fxg_comm_alltoallv(fxg_comm *c, const void *const *send_dev, const int64_t *send_off, const int64_t *send_cnt,
+                               void *const *recv_dev, const int64_t *recv_off, const int64_t *recv_cnt, size_t elem_bytes);
+int         fxg_comm_gatherv(fxg_comm *c, const void *const *send_dev, const int64_t *cnt, const int64_t *off, void *root_recv_dev,
+                             int root, size_t elem_bytes);
+int64_t     fxg_comm_bytes_sent(const fxg_comm *c);      /* payload bytes this process sent to OTHER ranks              */
+int64_t     fxg_comm_collectives(const fxg_comm *c);     /* NCCL groups issued                                            */
 void        fxg_comm_free(fxg_comm *c);
 const char *fxg_comm_error(const fxg_comm *c);
+
+/* ---- a8/a9 across GPUs: the collapser's global count map (src/fastx_collapser/fastx_collapser.cpp:112-114) partitioned by
+ * owner = std::hash(sequence) mod nranks, then the reference's output order (:116-122) computed once on the root GPU.
+ * run(): batches[i] = DEVICE slabs on the communicator's i-th local GPU (seq only; len == NULL: uniform_len), global read
+ * index of row r = index_base[i] + r, weight_dev (or weight_dev[i]) NULL = 1 per read.  Phases: K-ROUTE (hash, owner, send
+ * slabs) -> exchange of key rows + 16-byte {first, weight, len} records -> K-DEDUP on the owners -> gather of the uniques'
+ * (hash, first, count) to the root -> K-ORDER.  Key rows never leave their owner: fetch_local() returns an owner's uniques
+ * in its table order, fetch_order() (root's process) says which (owner, index) is printed at every rank of the output.    */
+typedef struct {
+    int64_t n_unique;          /* uniques in the whole job                                                              */
+    int64_t first_bad_read;    /* smallest global index of a read the reader would reject, -1 = none                    */
+    int64_t n_reads_local;     /* reads this process put in                                                             */
+    int64_t rows_received;     /* rows this process's GPUs own after the exchange                                       */
+    int64_t n_unique_local;    /* uniques this process's GPUs own                                                       */
+    int64_t bytes_sent;        /* payload bytes sent to other ranks (NVLink)                                            */
+    float   ms[5];             /* route, exchange, dedup, gather, order — CUDA events on the root's (else first) local GPU */
+    float   reserved;
+} fxg_dcollapse_report;
+typedef struct fxg_dcollapse fxg_dcollapse;
+int         fxg_dcollapse_new(fxg_comm *comm, int32_t stride, fxg_dcollapse **out);
+void        fxg_dcollapse_free(fxg_dcollapse *d);
+int         fxg_dcollapse_run(fxg_dcollapse *d, const fxg_batch *batches, const int64_t *index_base, const int32_t *const *weight_dev,
+                              int root, fxg_dcollapse_report *rep);
+int         fxg_dcollapse_fetch_local(fxg_dcollapse *d, int local_index, uint8_t *out_seq, int32_t *out_len, uint64_t *out_count,
+                                      int64_t *out_first, uint64_t *out_hash);
+int         fxg_dcollapse_fetch_order(fxg_dcollapse *d, int32_t *perm_owner_host, uint32_t *perm_index_host, int64_t *ordered_first_host,
+                                      uint64_t *ordered_count_host);
+const char *fxg_dcollapse_error(const fxg_dcollapse *d);
+int64_t     fxg_dcollapse_launches(const fxg_dcollapse *d);
 
 /* ---- (f-2) three more loop bodies on the same slabs ------------------------------------------------------------------
  * fxg_validate_*: the reader's checks alone (fastx.c:45-54,118-135,361-362) — all fastx_trimmer needs, its body being

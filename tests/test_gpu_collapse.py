@@ -171,3 +171,128 @@ def test_collapse_sharded_like_multi_gpu(ctx):
     assert U == len(ecnt)
     assert np.array_equal(ff.cpu().numpy()[p], efirst)
     assert np.array_equal(cc.cpu().numpy()[p].astype(np.uint64), ecnt)
+
+
+def test_dcollapse_one_rank_native_exchange(ctx):
+    """fxg_dcollapse_* (the multi-GPU collapser) on a communicator of ONE GPU: every phase runs — K-ROUTE, the NCCL
+    send/recv exchange (to itself), owner dedup, triple gather, K-ORDER — and the result must be the reference's."""
+    import fastx_toolkit_b200 as F
+    for n, L, kind in ((300000, 50, H.DUPS), (50000, 150, H.DUPS), (777, 36, H.WITH_N)):
+        seq, _ = H.synth_slab(H.SEED_BASE + 4, n, L, kind)
+        stride = seq.shape[1]
+        dseq = dev(seq)
+        comm = F.Comm.all([0])
+        assert comm.nranks == 1 and comm.nlocal == 1
+        dc = F.DCollapser(comm, stride)
+        for _ in range(2):                 # a second run reuses the buffers
+            rep = dc.run([F.Batch(dseq.data_ptr(), None, None, L, stride, n)], [0])
+        U = rep.n_unique
+        efirst, ecnt = H.o_collapse(seq, None, L, stride)
+        assert U == len(ecnt) == rep.n_unique_local and rep.first_bad_read == -1 and rep.rows_received == n
+        po, pi = np.empty(U, np.int32), np.empty(U, np.uint32)
+        of, oc = np.empty(U, np.int64), np.empty(U, np.uint64)
+        dc.fetch_order(po, pi, of, oc)
+        assert np.array_equal(of, efirst) and np.array_equal(oc, ecnt) and not po.any()
+        rows, lens = np.zeros((U, stride), np.uint8), np.zeros(U, np.int32)
+        cnt, first = np.zeros(U, np.uint64), np.zeros(U, np.int64)
+        dc.fetch_local(0, rows, lens, cnt, first, None)
+        assert np.array_equal(first[pi], efirst) and np.array_equal(cnt[pi], ecnt) and (lens == L).all()
+        assert np.array_equal(rows[pi][:, :L], seq[efirst][:, :L])
+        assert comm.collectives() >= 7 and dc.launches() > 0
+        dc.close(); comm.close()
+    # a bad read is reported with its global index; ragged lengths and weights travel in the 16-byte records
+    seq, _ = H.synth_slab(H.SEED_BASE + 6, 4000, 30, H.WITH_N)
+    rng = np.random.default_rng(5)
+    lens = rng.integers(1, 31, size=4000).astype(np.int32)
+    seq[np.arange(seq.shape[1])[None, :] >= lens[:, None]] = 0
+    seq[2000:3000] = seq[:1000]; lens[2000:3000] = lens[:1000]
+    w = rng.integers(1, 9, size=4000).astype(np.int32)
+    comm = F.Comm.all([0]); dc = F.DCollapser(comm, seq.shape[1])
+    dseq, dlens, dw = dev(seq), dev(lens), dev(w)
+    rep = dc.run([F.Batch(dseq.data_ptr(), None, dlens.data_ptr(), 0, seq.shape[1], 4000)], [1000], [dw])
+    U = rep.n_unique
+    rows, ol, cnt, first = np.zeros((U, seq.shape[1]), np.uint8), np.zeros(U, np.int32), np.zeros(U, np.uint64), np.zeros(U, np.int64)
+    dc.fetch_local(0, rows, ol, cnt, first, None)
+    keys = {}
+    for i in range(4000):
+        k = seq[i, :lens[i]].tobytes()
+        c, fm = keys.get(k, (0, 1 << 62))
+        keys[k] = (c + int(w[i]), min(fm, 1000 + i))
+    assert {rows[k, :ol[k]].tobytes(): (int(cnt[k]), int(first[k])) for k in range(U)} == keys
+    seq[1234, 0] = ord("x")
+    dseq = dev(seq)
+    rep = dc.run([F.Batch(dseq.data_ptr(), None, dlens.data_ptr(), 0, seq.shape[1], 4000)], [1000])
+    assert rep.first_bad_read == 1000 + 1234
+    dc.close(); comm.close()
+
+
+def test_collapse_24m_reads_full_order_vs_oracle(ctx):
+    """BASELINE config (e) shape, scaled to what the oracle finishes in a minute: 24 M x 50 bp, ~16 M uniques — the map
+    grows through bucket counts 5 967 347, 12 117 689 and 24 607 243 (three rehash epochs beyond the 2 M-read test) and the
+    FULL ordered output must equal the reference's (src/fastx_collapser/fastx_collapser.cpp:112-122)."""
+    import fastx_toolkit_b200 as F
+    n, L, stride = int(os.environ.get("FXG_COLLAPSE_N", 24_000_000)), 50, 64
+    dseq = torch.empty((n, stride), dtype=torch.uint8, device="cuda")
+    dq = torch.empty((n, stride), dtype=torch.uint8, device="cuda")
+    ctx.synth_dev(dseq, dq, n, L, stride, H.SEED_BASE + 4, H.DUPS, 33)
+    ctx.sync()
+    del dq
+    col = F.Collapser(0, n, stride)
+    col.add(F.Batch(dseq.data_ptr(), None, None, L, stride, n))
+    U = col.finish(True)
+    assert U > 12_117_689 and col.first_bad == -1
+    ocnt, ofirst = np.zeros(U, np.uint64), np.zeros(U, np.int64)
+    col.fetch(None, None, ocnt, ofirst, None)
+    col.close()
+    seq = dseq.cpu().numpy()
+    del dseq
+    efirst, ecnt = H.o_collapse(seq, None, L, stride)
+    assert U == len(ecnt) and int(ocnt.sum()) == n
+    assert np.array_equal(ocnt, ecnt)
+    assert np.array_equal(ofirst, efirst), "output order differs from the reference's unordered_map order"
+
+
+def test_collapse_config_e_200m_properties(ctx):
+    """BASELINE config (e) at full size on one GPU: 200 M x 50 bp, ~40 % repeats.  Checked without the oracle: the counts sum
+    to n, the number of uniques equals an independent host recount from the generator (reads that are not repeats + distinct
+    pool members hit), the order is count-descending and the first indices are exactly the reads that start a key."""
+    import fastx_toolkit_b200 as F
+    n, L, stride = int(os.environ.get("FXG_FULL_COLLAPSE_N", 200_000_000)), 50, 64
+    free = torch.cuda.mem_get_info()[0]
+    if free < n * 64 * 2.6 + (8 << 30):
+        pytest.skip("not enough device memory")
+    seed = H.SEED_BASE + 4
+    dseq = torch.empty((n, stride), dtype=torch.uint8, device="cuda")
+    dq = torch.empty((n, stride), dtype=torch.uint8, device="cuda")
+    ctx.synth_dev(dseq, dq, n, L, stride, seed, H.DUPS, 33)
+    ctx.sync()
+    del dq
+    torch.cuda.empty_cache()
+    col = F.Collapser(0, n, stride)
+    col.add(F.Batch(dseq.data_ptr(), None, None, L, stride, n))
+    U = col.finish(True)
+    ocnt, ofirst = np.zeros(U, np.uint64), np.zeros(U, np.int64)
+    col.fetch(None, None, ocnt, ofirst, None)
+    col.close()
+    assert int(ocnt.sum()) == n
+    assert (ocnt[:-1] >= ocnt[1:]).all()
+    assert len(np.unique(ofirst)) == U and ofirst.min() == 0 and ofirst.max() < n
+    # host recount from the generator (include/fxg_synth.h fxg_synth_read_key)
+    nondup, pids = 0, []
+    with np.errstate(over="ignore"):
+        for a in range(0, n, 10_000_000):
+            idx = np.arange(a, min(a + 10_000_000, n), dtype=np.uint64)
+            g = H.sm64(np.uint64(seed) ^ np.uint64(0x5bd1e995c0ffee) ^ H.sm64(idx))
+            dup = (g % np.uint64(100)) < np.uint64(40)
+            u = (g >> np.uint64(8)) & np.uint64(0xFFFFFF)
+            pid = (((u * u) >> np.uint64(24)) * np.uint64(n // 8 + 1)) >> np.uint64(24)
+            nondup += int((~dup).sum())
+            pids.append(np.unique(pid[dup]))
+            # a read that is not a repeat starts its own key: its index must be one of the first indices
+    distinct = len(np.unique(np.concatenate(pids)))
+    assert U == nondup + distinct, (U, nondup, distinct)
+    # spot check: the keys of the 3 most frequent and 3 of the singletons really are read `first`'s bytes, with that count
+    top = dseq[torch.from_numpy(ofirst[:3]).cuda()].cpu().numpy()
+    for k in range(3):
+        same = (dseq[:, :L] == torch.from_numpy(top[k, :L]).cuda()).all(dim=1)
+        assert int(same.sum().item()) == int(ocnt[k]) and int(torch.nonzero(same)[0].item()) == int(ofirst[k])

@@ -280,3 +280,70 @@ def test_clip_generations_agree(ctx, monkeypatch):
     monkeypatch.delenv("FXG_CLIP_V")
     gpu_clip(ctx, seq, qual, None, None, L, b"AGATCGGAAGAGC", dict(min_length=20))
     gpu_clip(ctx, seq, None, None, None, L, b"AGATCGGAAGAGC", dict(min_length=20, discard_unknown=0))     # FASTA
+
+
+def test_clip_config_c_100m(ctx):
+    """BASELINE config (c) at full size: 100 M x 150 bp, 30 % of the reads carry the adapter, fastx_clipper -a AGATCGGAAGAGC -l 20.
+    Prefix and tail equal the oracle; every read lands in exactly one class; lengths stay in range."""
+    import fastx_toolkit_b200 as F
+    n = int(os.environ.get("FXG_FULL_N", 100_000_000))
+    L, stride = 150, 160
+    free = torch.cuda.mem_get_info()[0]
+    if free < (n * (stride * 2 + 16)) * 1.05:
+        n = int(free / 1.05 / (stride * 2 + 16)) // 1024 * 1024
+    dseq = torch.empty((n, stride), dtype=torch.uint8, device="cuda")
+    dqual = torch.empty((n, stride), dtype=torch.uint8, device="cuda")
+    ctx.synth_dev(dseq, dqual, n, L, stride, H.SEED_BASE + 2, H.ADAPTER, 33)
+    kw = dict(min_length=20, keep_delta=0, discard_non_clipped=0, discard_clipped=0, discard_unknown=1, min_adapter_len=0)
+    o = F.ClipOpts(adapter=b"AGATCGGAAGAGC", **kw)
+    d_len = torch.empty(n, dtype=torch.int32, device="cuda")
+    d_cls = torch.empty(n, dtype=torch.uint8, device="cuda")
+    ctx.report_reset()
+    ctx.clip_dev(ctx.batch(dseq, dqual, n, stride, L), None, 33, o, d_len, d_cls, None)
+    rep = ctx.sync()
+    assert rep.first_bad_read == -1 and rep.n_in == n
+    assert rep.n_out + sum(rep.aux[c] for c in range(1, 6)) == n
+    hist = torch.bincount(d_cls.to(torch.int64), minlength=6).cpu().numpy()
+    assert hist[0] == rep.n_out and all(hist[c] == rep.aux[c] for c in range(1, 6))
+    kept = d_len[d_cls == 0]
+    assert int(kept.min().item()) >= 20 and int(kept.max().item()) <= L and bool((d_len[d_cls != 0] == -1).all().item())
+    assert 0.25 * n < n - int((d_len == L).sum().item()) < 0.8 * n          # the lenient rules clip many adapter-free tails too
+    oo = H.FxoClipOpts(**kw)
+    for first, m in ((0, 100000), (n - 20000, 20000)):
+        seq, _ = H.synth_slab(H.SEED_BASE + 2, m, L, H.ADAPTER, first=first)
+        e_len, e_cls, _ = H.o_clip(seq, None, None, L, stride, b"AGATCGGAAGAGC", oo)
+        assert np.array_equal(d_cls[first:first + m].cpu().numpy(), e_cls)
+        assert np.array_equal(d_len[first:first + m].cpu().numpy(), np.where(e_cls == 0, e_len, -1))
+
+
+def test_stats_config_d_share_100m(ctx):
+    """BASELINE config (d), one GPU's worth and more: fastx_quality_stats over 100 M x 150 bp.  hist.sum() == n*L, every cycle
+    holds n bases, the histogram of a 500 K-read prefix equals the oracle, and the whole equals the sum of its two halves
+    (the additivity the multi-GPU all-reduce relies on)."""
+    n = int(os.environ.get("FXG_FULL_N", 100_000_000))
+    L, stride = 150, 160
+    free = torch.cuda.mem_get_info()[0]
+    if free < (n * stride * 2) * 1.05:
+        n = int(free / 1.05 / (stride * 2)) // 1024 * 1024
+    dseq = torch.empty((n, stride), dtype=torch.uint8, device="cuda")
+    dqual = torch.empty((n, stride), dtype=torch.uint8, device="cuda")
+    ctx.synth_dev(dseq, dqual, n, L, stride, H.SEED_BASE + 3, H.WITH_N, 33)
+    whole = torch.zeros((L, 5, 109), dtype=torch.int64, device="cuda")
+    ctx.report_reset()
+    ctx.stats_accum_dev(ctx.batch(dseq, dqual, n, stride, L), 33, whole, L)
+    rep = ctx.sync()
+    assert rep.first_bad_read == -1
+    assert int(whole.sum().item()) == n * L and bool((whole.sum(dim=(1, 2)) == n).all().item())
+    h = n // 2 + 12345
+    halves = torch.zeros((L, 5, 109), dtype=torch.int64, device="cuda")
+    ctx.stats_accum_dev(ctx.batch(dseq, dqual, h, stride, L), 33, halves, L)
+    ctx.stats_accum_dev(ctx.batch(dseq[h:], dqual[h:], n - h, stride, L), 33, halves, L, None, h)
+    ctx.sync()
+    assert torch.equal(whole, halves)
+    m = 500000
+    pre = torch.zeros((L, 5, 109), dtype=torch.int64, device="cuda")
+    ctx.stats_accum_dev(ctx.batch(dseq, dqual, m, stride, L), 33, pre, L)
+    ctx.sync()
+    seq, qual = H.synth_slab(H.SEED_BASE + 3, m, L, H.WITH_N)
+    eh, _ = H.o_stats_hist(seq, qual, None, L, stride, 33, L)
+    assert np.array_equal(pre.cpu().numpy().astype(np.uint64), eh)

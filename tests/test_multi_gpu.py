@@ -22,6 +22,17 @@ def test_two_rank_nccl_stats_allreduce_and_collapser_exchange():
     assert b"collapser U=" in r.stdout and b"MISMATCH" not in r.stdout
 
 
+def test_single_process_two_gpus_native_collectives():
+    """one process driving 2 GPUs (the drop-in tools' style): fxg_comm_init_all + fxg_comm_allreduce_u64 + fxg_dcollapse_*"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, MG_N="300000")
+    r = subprocess.run([sys.executable, os.path.join(H.ROOT, "scripts", "multi_gpu_check.py"), "--single", "2"],
+                       env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
+    assert r.returncode == 0, r.stdout.decode()[-2000:]
+    assert b"collapser U=" in r.stdout and b"MISMATCH" not in r.stdout
+
+
 def test_native_nccl_allreduce_and_multi_gpu_stats_tool(tmp_path):
     """fxg_comm_allreduce_u64 (NCCL from C, one process driving 2 GPUs) and fastx_quality_stats with FASTX_GPUS=2."""
     if torch.cuda.device_count() < 2:
