@@ -28,8 +28,8 @@ class BarcodeTable(C.Structure):
 
 
 class Stage(C.Structure):
-    """struct fxg_stage (op: 0 trim, 1 filter, 2 clip)"""
-    _fields_ = [("op", C.c_int32), ("a0", C.c_int32), ("a1", C.c_int32), ("clip", C.c_void_p)]
+    """struct fxg_stage (op: 0 trim, 1 filter, 2 clip, 3 collapse)"""
+    _fields_ = [("op", C.c_int32), ("a0", C.c_int32), ("a1", C.c_int32), ("clip", C.c_void_p), ("collapser", C.c_void_p)]
 
 
 class ClipOpts(C.Structure):
@@ -151,6 +151,7 @@ def lib():
         "fxg_collapse_new": (i32, [i32, i64, C.c_int32, C.POINTER(vp)]),
         "fxg_collapse_free": (None, [vp]),
         "fxg_collapse_add": (i32, [vp, BP, vp, vp, i64]),
+        "fxg_collapse_add_next": (i32, [vp, BP]),
         "fxg_collapse_finish": (i32, [vp, i32, C.POINTER(i64), C.POINTER(i64)]),
         "fxg_collapse_fetch": (i32, [vp, vp, vp, vp, vp, vp]),
         "fxg_collapse_error": (C.c_char_p, [vp]),

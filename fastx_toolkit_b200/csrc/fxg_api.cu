@@ -500,6 +500,23 @@ static int stats_enqueue(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint64_
     long rfit3 = ((long)MAX_DYN_SMEM - 98432L) / 24 / (4L * b->stride);
     if (rfit3 > S2_TILE_READS) rfit3 = S2_TILE_READS;
     const bool fast3 = ver == 3 && b->qual && !weight && rfit3 >= 4 && t_ring != 0 && q_offset - 15 <= 64 && b->n / rfit3 < (1ll << 31);
+    // FXG_STATS_V=4: lane-per-read kernel (fxg_stats4.cu)
+    long rfit4 = ((long)MAX_DYN_SMEM - (long)S4_HIST_BYTES - S4_DUMMY_BYTES) / S4_WARPS / (2L * b->stride);
+    if (rfit4 > S4_TILE_READS) rfit4 = S4_TILE_READS;
+    const bool fast4 = ver == 4 && b->qual && !weight && rfit4 >= 8 && t_ring != 0 && q_offset - 15 <= 64 && b->n / rfit4 < (1ll << 31);
+    if (fast4) {
+        p.tile_reads = (int)rfit4; p.stages = 1;
+        const uint32_t smem = (uint32_t)((size_t)S4_HIST_BYTES + S4_DUMMY_BYTES + (size_t)S4_WARPS * 2 * b->stride * rfit4);
+        const int64_t ntiles = (b->n + rfit4 - 1) / rfit4;
+        int64_t grid = ctx->sm_count;
+        const int64_t need = (ntiles + S4_WARPS - 1) / S4_WARPS;
+        if (grid > need) grid = need;
+        for (int w0 = 0; w0 < words; w0 += ST_MAXW) {
+            p.w0 = w0; p.nw = (words - w0 < ST_MAXW) ? (words - w0) : ST_MAXW;
+            CK(ctx, launch_stats4(p, (int)grid, smem, st));
+            ctx->launches++;
+        }
+    } else
     if (fast3) {
         p.tile_reads = (int)rfit3; p.stages = 2;
         const uint32_t smem = (uint32_t)(98432u + (size_t)24 * 4 * b->stride * rfit3);
@@ -801,14 +818,15 @@ extern "C" int fxg_pipeline_dev(fxg_ctx *ctx, const fxg_batch *b, int q_offset, 
     if (b->n >= (1ll << 31)) return arg_error(ctx, "pipeline: more than 2^31 reads in one batch");
     for (int k = 0; k < n_stages; k++) {
         if (stages[k].op == FXG_STAGE_CLIP) {
-            // FXG_PIPE_STALE=1 (EXPERIMENTAL, not yet run on a GPU): build the aligner's stale-buffer rows with a scan
-            const char *es = getenv("FXG_PIPE_STALE");
-            const bool stale_ok = es && es[0] == '1' && b->stride <= 160;
-            if ((k != 0 || b->len) && !stale_ok) {
-                snprintf(ctx->err, sizeof(ctx->err), "pipeline: the clipper must be stage 0 on a batch of one read length (stale-buffer semantics)");
+            // after another stage (or on a ragged batch) the aligner sees mixed lengths: its stale-buffer rows come from one
+            // scan over the survivors (fxg_pipeline.cu launch_stale_rows), whose row operator holds at most 160 bases
+            if ((k != 0 || b->len) && b->stride > 160) {
+                snprintf(ctx->err, sizeof(ctx->err), "pipeline: the clipper on mixed read lengths supports strides up to 160");
                 return FXG_ERR_UNSUPPORTED;
             }
             if ((rc = check_clip_opts(ctx, stages[k].clip))) return rc;
+        } else if (stages[k].op == FXG_STAGE_COLLAPSE) {
+            if (k != n_stages - 1 || !stages[k].collapser) return arg_error(ctx, "pipeline: the collapser must be the last stage and needs a fxg_collapser");
         } else if (stages[k].op == FXG_STAGE_FILTER) {
             if (stages[k].a1 < 0 || stages[k].a1 > 100) return arg_error(ctx, "min_percent must be 0..100");
         } else if (stages[k].op != FXG_STAGE_TRIM) return arg_error(ctx, "pipeline: unknown stage");
@@ -841,6 +859,19 @@ extern "C" int fxg_pipeline_dev(fxg_ctx *ctx, const fxg_batch *b, int q_offset, 
     for (int k = 0; k < n_stages && cur_n > 0; k++) {
         const fxg_stage &sg = stages[k];
         cur.n = cur_n;
+        if (sg.op == FXG_STAGE_COLLAPSE) {
+            // the survivors (already compacted, in input order) enter the count map exactly as the next process of the pipe
+            // would read them (fastx_collapser.cpp:112-114); their lengths also go back to final_len
+            cudaError_t e = launch_pipe_keep_all(cur_n, cur.len, cur.uniform_len, cur_idx, final_len, ctx->sm_count, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "pipeline collapse stage: %s", cudaGetErrorString(e)); rc = FXG_ERR_CUDA; break; }
+            ctx->launches++;
+            fxg_batch kb = cur;
+            kb.qual = NULL;
+            rc = fxg_collapse_add_next(sg.collapser, &kb);
+            if (rc) snprintf(ctx->err, sizeof(ctx->err), "pipeline collapse stage: %s", fxg_collapse_error(sg.collapser));
+            break;
+        }
         const bool bytes = sg.op == FXG_STAGE_FILTER;
         if (sg.op == FXG_STAGE_TRIM) rc = scan_enqueue(ctx, MODE_TRIM, &cur, q_offset, sg.a0, sg.a1, 0, d_dec, 0, st);
         else if (sg.op == FXG_STAGE_FILTER) rc = scan_enqueue(ctx, MODE_FILTER, &cur, q_offset, sg.a0, 0, sg.a1, d_dec, 0, st);

@@ -423,6 +423,11 @@ extern "C" int fxg_collapse_add(fxg_collapser *c, const fxg_batch *b, const int3
     return FXG_OK;
 }
 
+extern "C" int fxg_collapse_add_next(fxg_collapser *c, const fxg_batch *b)
+{
+    return c ? fxg_collapse_add(c, b, NULL, NULL, c->rows) : FXG_ERR_ARG;
+}
+
 // Compact the table; with order != 0 also compute the reference's output order.
 extern "C" int fxg_collapse_finish(fxg_collapser *c, int order, int64_t *n_unique, int64_t *first_bad_read)
 {

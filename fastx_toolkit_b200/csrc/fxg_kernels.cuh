@@ -86,6 +86,14 @@ constexpr int S2_HIST_BYTES = 4 * ST_QWIN * S2_PITCH;   // 256 bins: 163 840 byt
 constexpr int S2_DUMMY_BYTES = 128;               // 32 scratch counters behind the histogram (masked-off increments land here)
 constexpr int S2_TILE_READS = 8;                  // reads per warp tile (4 lanes per read)
 
+// third layout (k_stats4, fxg_stats4.cu): lane = read; a bin owns 96 words: 64 words of u16 pairs for cycles 0..127 (word
+// 32*(wi>>1) + 8k + c, half wi&1, for window word w = 4c + wi and byte k) + 32 full words for cycles 128..159 (64 + 4(w-32) + k)
+constexpr int S4_PITCH = 96 * 4;                  // bytes per bin; 96 = 0 (mod 32): the bank of a counter never depends on the data
+constexpr int S4_HIST_BYTES = 4 * ST_QWIN * S4_PITCH;   // 256 bins: 98 304 bytes
+constexpr int S4_DUMMY_BYTES = 128;               // one scratch counter per lane (masked-off increments land here)
+constexpr int S4_WARPS = 12;                      // 12 x 10 KB tiles (150 bp) beside the histogram
+constexpr int S4_TILE_READS = 32;
+
 struct StatsParams {
     const uint8_t *seq;
     const uint8_t *qual;      // NULL: FASTA (simple kernel only)
@@ -162,6 +170,8 @@ cudaError_t launch_pipe_gather(const uint8_t *src_seq, const uint8_t *src_qual, 
                                uint8_t *dst_qual, int32_t *dst_len, int32_t *dst_idx, int sm_count, cudaStream_t st);
 cudaError_t launch_stale_rows(const uint8_t *seq, const int32_t *len, int stride, int64_t n, uint8_t *out_seq, int32_t *out_width, void *scratch,
                               size_t scratch_bytes, size_t *need, int sm_count, cudaStream_t st);   // experimental
+cudaError_t launch_pipe_keep_all(int64_t n, const int32_t *cur_len, int uniform_len, const int32_t *cur_idx, int32_t *final_len, int sm_count,
+                                 cudaStream_t st);
 cudaError_t launch_pipe_scatter(int64_t n, const int32_t *flags, const int32_t *new_len, const int32_t *cur_len, int uniform_len, const int32_t *cur_idx,
                                 int32_t *final_len, int sm_count, cudaStream_t st);
 cudaError_t launch_stats3(const StatsParams &p, int grid, uint32_t smem_bytes, cudaStream_t st);   // experimental (fxg_stats3.cu)
@@ -171,6 +181,7 @@ cudaError_t stats_set_smem_attrs();
 cudaError_t launch_extra(int op, const uint8_t *seq, const uint8_t *qual, const int32_t *len, int uniform_len, int stride, int64_t n,
                          int q_offset, int thr_q, int mask_char, uint8_t *out_seq, uint8_t *flags, int64_t index_base,
                          unsigned long long *counters, int sm_count, cudaStream_t st);
+cudaError_t launch_stats4(const StatsParams &p, int grid, uint32_t smem_bytes, cudaStream_t st);
 cudaError_t launch_hash(const uint8_t *seq, const int32_t *len, int uniform_len, int stride, int64_t n, uint64_t *out, cudaStream_t st);
 
 cudaError_t launch_scan(int mode, bool has_seq, const TilePlan &plan, const ScanParams &p, cudaStream_t st);

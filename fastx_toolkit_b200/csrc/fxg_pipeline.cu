@@ -6,9 +6,9 @@
 // sees exactly the records the next process of the pipe would read (fastx.c:440-473 writes, fastx.c:314-404 re-reads).
 // All three tools only ever shorten a read from its 3' end, so a record is fully described by (original index, length).
 //
-// Limits of this version: the clipper may only be the FIRST stage and only on batches of one read length — after a
-// trimming stage the reference's aligner works on mixed lengths with its stale-buffer semantics,
-// which needs a scan over the reads that is not written yet (the target is pinned: tests/test_pipeline_oracle.py).
+// The clipper after a trimming stage (or on a ragged batch) works on mixed lengths with the reference aligner's
+// stale-buffer semantics: its rows come from one scan over the survivors (launch_stale_rows below).
+// A fastx_collapser stage may end the chain: the survivors are added to a fxg_collapser in input order.
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
 #include <thrust/iterator/transform_iterator.h>
@@ -54,6 +54,13 @@ __global__ void __launch_bounds__(256) k_pipe_scatter(int64_t n, const int32_t *
         if (flags[i]) final_len[cur_idx ? cur_idx[i] : i] = new_len ? new_len[i] : (cur_len ? cur_len[i] : uniform_len);
 }
 
+// a collapser stage keeps every read it is given: final_len = current length
+__global__ void __launch_bounds__(256) k_pipe_keep_all(int64_t n, const int32_t *cur_len, int uniform_len, const int32_t *cur_idx, int32_t *final_len)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        final_len[cur_idx ? cur_idx[i] : i] = cur_len ? cur_len[i] : uniform_len;
+}
+
 static unsigned pgrid(int64_t n, int sm) { int64_t b = (n + 255) / 256; if (b > (int64_t)sm * 16) b = (int64_t)sm * 16; if (b < 1) b = 1; return (unsigned)b; }
 
 size_t pipe_scan_tmp_bytes(int64_t n)
@@ -81,6 +88,13 @@ cudaError_t launch_pipe_gather(const uint8_t *src_seq, const uint8_t *src_qual, 
     return cudaGetLastError();
 }
 
+cudaError_t launch_pipe_keep_all(int64_t n, const int32_t *cur_len, int uniform_len, const int32_t *cur_idx, int32_t *final_len, int sm_count,
+                                 cudaStream_t st)
+{
+    k_pipe_keep_all<<<pgrid(n, sm_count), 256, 0, st>>>(n, cur_len, uniform_len, cur_idx, final_len);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_pipe_scatter(int64_t n, const int32_t *flags, const int32_t *new_len, const int32_t *cur_len, int uniform_len, const int32_t *cur_idx,
                                 int32_t *final_len, int sm_count, cudaStream_t st)
 {
@@ -91,7 +105,7 @@ cudaError_t launch_pipe_scatter(int64_t n, const int32_t *flags, const int32_t *
 }  // namespace fxg
 
 // ------------------------------------------------------------------------------------------------------------------
-// EXPERIMENTAL (FXG_PIPE_STALE=1; not yet run on a GPU): the rows the reference's aligner sees for MIXED-length reads
+// The rows the reference's aligner sees for MIXED-length reads
 // (SURVEY Appendix D.1), needed when the clipper is not the first stage.  Its query buffer only grows and keeps stale
 // bytes, so row i = the buffer after reads 0..i: read i's bases, a NUL, then whatever longer earlier reads left behind,
 // up to the running maximum length.  "Overwrite a prefix" is closed under composition and associative

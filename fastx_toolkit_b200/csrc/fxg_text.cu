@@ -101,6 +101,13 @@ __global__ void __launch_bounds__(256) k_recs(const uint8_t *text, const uint32_
         else if (ln[1] == 0) an = AN_EMPTY_SEQ;
         else if (ln[3] != ln[1]) an = AN_QUAL_LEN;               // numeric quality (or a broken record): host path
         else if (ln[0] >= 24998u || ln[1] >= 24998u || ln[2] >= 24998u) an = AN_LONG_LINE;
+        else {
+            // chomp() cuts a line at its FIRST CR (src/libfastx/chomp.c:34-44): a CR inside a name line changes what the
+            // reference writes back, so such a record goes to the host parser (sequence / quality lines: a CR is an illegal
+            // character there and the validation of the op kernels reports it)
+            for (uint32_t i = 0; i < ln[0]; i++) if (text[st[0] + i] == '\r') an = AN_BAD_RECORD;
+            for (uint32_t i = 0; i < ln[2]; i++) if (text[st[2] + i] == '\r') an = AN_BAD_RECORD;
+        }
         if (an != AN_NONE) atomicMin(anomaly, ((unsigned long long)r << 8) | (unsigned long long)an);
         seq_len[r] = (int32_t)ln[1];
         if ((int)ln[1] > local_max && an == AN_NONE) local_max = (int)ln[1];

@@ -218,7 +218,10 @@ static int next_line(fxh_reader *r, char **start, size_t *n)
     else if (r->eof) raw = r->len - r->pos;        /* last line without a newline */
     else return -1;
     size_t l = nl ? raw - 1 : raw;
-    if (l > 0 && s[l - 1] == '\r') l--;            /* chomp(): CR/LF (src/libfastx/chomp.c:34-44) */
+    {   /* chomp(): the line ends at its FIRST CR or LF (src/libfastx/chomp.c:34-44), an interior CR included */
+        const char *cr = (const char *)memchr(s, '\r', l);
+        if (cr) l = (size_t)(cr - s);
+    }
     if (l >= FXH_MAX_LINE - 1)
         errx(1, "line %llu is longer than %d characters (the reference's fgets() buffer); not supported",
              (unsigned long long)(r->line_no + 1), FXH_MAX_LINE - 2);
@@ -337,7 +340,7 @@ fxh_batch *fxh_reader_next(fxh_reader *r, int64_t max_reads)
             break;
         }
         if (!r->fastq && (n1 == 0 || l1[0] != '>')) {
-            if (all_bases(l1, n1))
+            if (n1 > 0 && all_bases(l1, n1))     /* a blank line is no nucleotide string (fastx.c:338-346 tests the first character) */
                 PEND(r, "Invalid input: This looks like a multi-line FASTA file.\nLine %llu contains a nucleotides string instead of a '>' prefix.\n"
                         "FASTX-Toolkit can't handle multi-line FASTA files.\nPlease use the FASTA-Formatter tool to convert this file into a single-line FASTA.\n",
                      (unsigned long long)ln1);

@@ -302,10 +302,10 @@ static void clip_text_path(fxg_ctx *ctx, fxh_reader *rd, fxh_writer *wr, const f
         fxh_write_raw(wr, ob, (size_t)rep.out_bytes, rep.n_out_records);
         *count_input += (unsigned int)rep.n_records;
         for (int k = 0; k < 6; k++) cnt[k] += (unsigned int)rep.clip_class[k];
-        {   /* sequence line of the last consumed record: 3 newlines back from the end of the record */
-            size_t e = (size_t)rep.consumed_bytes - 1;          /* the record's final newline */
+        {   /* sequence line of the last consumed record: 2 newlines back from the end of the record */
+            size_t e = (size_t)rep.consumed_bytes - 1;          /* the record's final newline (end of line 4) */
             int nl = 0;
-            while (e > 0 && nl < 3) { e--; if (p[e] == '\n') nl++; }     /* e = newline ending line 2 */
+            while (e > 0 && nl < 2) { e--; if (p[e] == '\n') nl++; }     /* e = newline ending line 2 (line 3's, then line 2's) */
             size_t s2 = e;
             while (s2 > 0 && p[s2 - 1] != '\n') s2--;
             fxh_reader_seed_shadow(rd, p + s2, rep.max_len);

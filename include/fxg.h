@@ -166,6 +166,7 @@ typedef struct fxg_collapser fxg_collapser;
 int         fxg_collapse_new(int device, int64_t max_reads, int32_t stride, fxg_collapser **out);
 void        fxg_collapse_free(fxg_collapser *c);
 int         fxg_collapse_add(fxg_collapser *c, const fxg_batch *b, const int32_t *weight, const int64_t *first, int64_t index_base);
+int         fxg_collapse_add_next(fxg_collapser *c, const fxg_batch *b);   /* add(): weight 1, first = rows added so far + i */
 int         fxg_collapse_finish(fxg_collapser *c, int order, int64_t *n_unique, int64_t *first_bad_read);
 int         fxg_collapse_fetch(fxg_collapser *c, uint8_t *out_seq, int32_t *out_len, uint64_t *out_count, int64_t *out_first,
                                uint64_t *out_hash);
@@ -279,19 +280,24 @@ typedef struct {
 int fxg_barcode_dev (fxg_ctx *ctx, const fxg_batch *fragments, const fxg_barcode_table *t, int32_t *best_dev);
 int fxg_barcode_host(fxg_ctx *ctx, const fxg_batch *fragments, const fxg_barcode_table *t, int32_t *best_host, fxg_report *report);
 
-/* ---- (f-3) fused pipelines, first version (parity-checked on B200 against the composed oracle) ----------
- * The map-type tools chained on the device, e.g. fastx_clipper | fastq_quality_trimmer | fastq_quality_filter: every
- * stage runs the tool's own kernel on the survivors of the stage before (compacted in HBM, exactly the records the next
- * process of a shell pipe would read).  All three tools only shorten reads at the 3' end, so the result is one length
- * per ORIGINAL read: final_len[i] = length after the last stage, -1 = dropped by some stage.
- * FXG_STAGE_CLIP may only be stage 0 and needs a batch of one read length (len == NULL): after a trimming stage the
- * reference's aligner depends on the order of mixed-length reads -> FXG_ERR_UNSUPPORTED.
+/* ---- (f-3) fused pipelines (parity-checked on B200 against the composed oracle and the reference shell pipe) ----------
+ * The tools chained on the device, e.g. fastq_quality_trimmer | fastx_clipper | fastq_quality_filter | fastx_collapser:
+ * every stage runs the tool's own kernel on the survivors of the stage before (compacted in HBM, exactly the records the
+ * next process of a shell pipe would read).  The map-type tools only shorten reads at the 3' end, so their result is one
+ * length per ORIGINAL read: final_len[i] = length after the last stage, -1 = dropped by some stage.
+ * FXG_STAGE_CLIP on mixed lengths (after a trimming stage, or on a ragged batch) reproduces the reference aligner's
+ * grow-only query buffer (src/libfastx/sequence_alignment.cpp:131-153) with one scan over the
+ * survivors; that path needs stride <= 160.  The buffer's history starts with the batch: one call = one input stream
+ * (a second call does not see the first call's reads, exactly like a second run of the shell pipe).
+ * FXG_STAGE_COLLAPSE must be the last stage: the survivors are added, in input order, to stage.collapser
+ * (fxg_collapse_new; finish/fetch it afterwards); several calls may feed one collapser.
  * Blocking (one small device-to-host read per stage); report.first_bad_read refers to the input batch. */
-enum { FXG_STAGE_TRIM = 0, FXG_STAGE_FILTER = 1, FXG_STAGE_CLIP = 2 };
+enum { FXG_STAGE_TRIM = 0, FXG_STAGE_FILTER = 1, FXG_STAGE_CLIP = 2, FXG_STAGE_COLLAPSE = 3 };
 typedef struct {
     int32_t op;                   /* FXG_STAGE_*                                                            */
     int32_t a0, a1;               /* TRIM: -t, -l    FILTER: -q, -p                                         */
     const fxg_clip_opts *clip;    /* CLIP                                                                   */
+    fxg_collapser *collapser;     /* COLLAPSE                                                               */
 } fxg_stage;
 int fxg_pipeline_dev(fxg_ctx *ctx, const fxg_batch *b, int q_offset, const fxg_stage *stages, int n_stages, int32_t *final_len_dev,
                      int64_t *n_survivors);

@@ -15,8 +15,15 @@ def pytest_configure(config):
 
 def pytest_sessionstart(session):
     """Build what the tests load (libfxg.so, bin/ tools, the oracle) when a fresh checkout has not been built yet."""
+    import shutil
     import subprocess
-    need = [os.path.join(ROOT, "fastx_toolkit_b200", "libfxg.so"), os.path.join(ROOT, "bin", "fastx_b200"),
-            os.path.join(ROOT, "oracle", "libfastx_oracle.so")]
+    if not os.path.exists(os.path.join(ROOT, "oracle", "libfastx_oracle.so")):
+        subprocess.call(["make", "-C", ROOT, "oracle"], stdout=subprocess.DEVNULL)          # gcc only
+    need = [os.path.join(ROOT, "fastx_toolkit_b200", "libfxg.so"), os.path.join(ROOT, "bin", "fastx_b200")]
     if not all(os.path.exists(p) for p in need):
-        subprocess.check_call(["make", "-C", ROOT, "lib", "tools", "oracle"], stdout=subprocess.DEVNULL)
+        # without nvcc the CUDA library cannot be built: the tests that need it fail on their own, the CPU-only ones still run
+        if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
+            try:
+                subprocess.check_call(["make", "-C", ROOT, "lib", "tools"], stdout=subprocess.DEVNULL)
+            except subprocess.CalledProcessError as e:
+                print("conftest: building libfxg.so / bin failed (%s); GPU-library tests will fail" % e, file=sys.stderr)

@@ -61,16 +61,12 @@ def test_pipeline_matches_composed_oracle():
         got = final.cpu().numpy()
         assert np.array_equal(got, exp), (len(stages), int((got != exp).sum()))
         assert alive == int((exp >= 0).sum())
-    # the clipper after another stage is refused (stale-buffer semantics are not implemented on the device)
-    with pytest.raises(F.FxgError):
-        ctx.pipeline_dev(ctx.batch(dseq, dqual, n, stride, L), 33, [F.Stage(0, 20, 20, None), F.Stage(2, 0, 0, C.addressof(clip))],
-                         torch.empty(n, dtype=torch.int32, device="cuda"))
     ctx.close()
 
 
-@pytest.mark.skipif(os.environ.get("FXG_PIPE_STALE") != "1", reason="experimental: the device-side stale-buffer scan has not run on a GPU yet (set FXG_PIPE_STALE=1)")
-def test_pipeline_clipper_after_trimmer_experimental():
-    """trim | clip: the clipper on mixed lengths, stale-buffer rows from the prefix-overwrite scan (fxg_pipeline.cu)"""
+def test_pipeline_clipper_on_mixed_lengths():
+    """trim | clip and a ragged batch straight into the clipper: mixed lengths, the reference aligner's stale-buffer rows
+     built on the device by the prefix-overwrite scan (fxg_pipeline.cu launch_stale_rows)"""
     import ctypes as C
     import fastx_toolkit_b200 as F
     ctx = F.Context(0)
@@ -84,4 +80,54 @@ def test_pipeline_clipper_after_trimmer_experimental():
     exp = oracle_final_len(seq, qual, np.full(n, L, np.int32),
                            [lambda s, q, l: stage_trim(s, q, l, 25, 30), lambda s, q, l: stage_clip(s, q, l, 15, discard_unknown=0)])
     assert np.array_equal(final.cpu().numpy(), exp) and alive == int((exp >= 0).sum())
+    # ragged input, clipper first, then two more stages
+    s2, q2 = seq.copy(), qual.copy()
+    lens = H.ragged(s2, q2, np.random.default_rng(3), min_len=8)
+    final = torch.full((n,), 12345, dtype=torch.int32, device="cuda")
+    alive = ctx.pipeline_dev(ctx.batch(torch.from_numpy(s2).cuda(), torch.from_numpy(q2).cuda(), n, stride, 0, torch.from_numpy(lens).cuda()), 33,
+                             [F.Stage(2, 0, 0, C.addressof(clip)), F.Stage(1, 20, 80, None), F.Stage(0, 22, 12, None)], final)
+    exp = oracle_final_len(s2, q2, lens, [lambda s, q, l: stage_clip(s, q, l, 15, discard_unknown=0), lambda s, q, l: stage_filter(s, q, l, 20, 80),
+                                          lambda s, q, l: stage_trim(s, q, l, 22, 12)])
+    assert np.array_equal(final.cpu().numpy(), exp) and alive == int((exp >= 0).sum())
+    ctx.close()
+
+
+def collapser_text(col, u):
+    stride = col.stride
+    oseq, olen, ocnt = np.zeros((u, stride), np.uint8), np.zeros(u, np.int32), np.zeros(u, np.uint64)
+    col.fetch(oseq, olen, ocnt, None, None)
+    return b"".join(b">%d-%d\n" % (k + 1, int(ocnt[k])) + oseq[k, :olen[k]].tobytes() + b"\n" for k in range(u))
+
+
+@pytest.mark.parametrize("name", ["clip_trim_filter_collapse", "trim_clip_collapse"])
+def test_pipeline_with_collapser_equals_reference_shell_pipe(name):
+    """the whole chain on the device, the collapser as last stage: the FASTA it yields must be the bytes the reference tools
+    produce in a shell pipe (digests in tests/golden/pipeline.json, made from the reference binaries; the same composition
+    is replayed against the live binaries by tests/test_pipeline_oracle.py)"""
+    import ctypes as C
+    import hashlib
+    import json
+    import fastx_toolkit_b200 as F
+    from test_pipeline_oracle import GOLD, oracle_pipeline
+    ctx = F.Context(0)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    seq, qual, L = synth_input()
+    n, stride = seq.shape
+    col = F.Collapser(0, n, stride)
+    if name == "clip_trim_filter_collapse":
+        clip = F.ClipOpts(adapter=ADAPTER, min_length=20, keep_delta=0, discard_non_clipped=0, discard_clipped=0, discard_unknown=1, min_adapter_len=0)
+        stages = [F.Stage(2, 0, 0, C.addressof(clip), None), F.Stage(0, 20, 20, None, None), F.Stage(1, 20, 90, None, None), F.Stage(3, 0, 0, None, col.h)]
+    else:
+        clip = F.ClipOpts(adapter=ADAPTER, min_length=15, keep_delta=0, discard_non_clipped=0, discard_clipped=0, discard_unknown=0, min_adapter_len=0)
+        stages = [F.Stage(0, 25, 30, None, None), F.Stage(2, 0, 0, C.addressof(clip), None), F.Stage(3, 0, 0, None, col.h)]
+    final = torch.full((n,), 12345, dtype=torch.int32, device="cuda")
+    # two calls feeding one collapser would be two input streams for the clipper's history: one call, as one shell pipe
+    alive = ctx.pipeline_dev(ctx.batch(torch.from_numpy(seq).cuda(), torch.from_numpy(qual).cuda(), n, stride, L), 33, stages, final)
+    u = col.finish(True)
+    text = collapser_text(col, u)
+    col.close()
+    gold = json.load(open(GOLD))[name]
+    assert u == gold["unique_sequences"] and alive == int((final >= 0).sum().item())
+    assert hashlib.sha256(text).hexdigest() == gold["sha256"]
+    assert text == oracle_pipeline(name)
     ctx.close()

@@ -89,6 +89,11 @@ def test_structurally_broken_inputs_fail_like_the_reference(harness, tmp_path):
         variant("quallong.fq", set_line(4 * 3000 + 3, b"I" * 60)),
         variant("numeric_bad.fq", set_line(4 * 10 + 3, b"40 40 x 40")),
         variant("numeric_range.fq", set_line(4 * 10 + 3, b" ".join([b"40"] * 49 + [b"120"]))),
+        # chomp() ends a line at its FIRST carriage return (chomp.c:34-44)
+        variant("cr_in_name.fq", set_line(4 * 4000, b"@r40\r00 tail")),
+        variant("cr_in_name2.fq", set_line(4 * 4000 + 2, b"+r40\r00")),
+        variant("cr_in_seq.fq", set_line(4 * 2500 + 1, b"ACGTACGT\rCGT" + b"A" * 38)),
+        variant("cr_in_qual.fq", set_line(4 * 2500 + 3, b"I" * 20 + b"\r" + b"I" * 29)),
     ]
     empty = str(tmp_path / "empty.fq")
     open(empty, "wb").write(b"")
@@ -96,6 +101,8 @@ def test_structurally_broken_inputs_fail_like_the_reference(harness, tmp_path):
     open(junk, "wb").write(b"hello\nworld\n")
     fa_bad = str(tmp_path / "bad.fa")
     open(fa_bad, "wb").write(b">a\nACGT\nACGT\n>b\nAC\n")      # a second sequence line where an identifier is expected
+    fa_blank = str(tmp_path / "blank.fa")
+    open(fa_blank, "wb").write(b">a\nACGT\n\n>b\nACGT\n")     # a blank line is not a nucleotide string: "expecting FASTA prefix"
     for env in ({}, {"FASTX_BATCH_READS": "1000"}):
-        for p in cases + [empty, junk, fa_bad, str(tmp_path / "missing.fq")]:
+        for p in cases + [empty, junk, fa_bad, fa_blank, str(tmp_path / "missing.fq")]:
             same(harness, ["-i", p], env=env)

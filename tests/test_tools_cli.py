@@ -123,6 +123,14 @@ def test_trim_filter_revcomp_stats_binaries(tmp_path, L, kind, ragged, crlf):
         assert_same("fastq_quality_trimmer", ["-t", "20"], stdin=open(fq, "rb").read())   # stdin -> stdout
     finally:
         os.environ.pop("FASTX_BATCH_READS", None)
+    # FASTA: a blank line where a '>' is expected is "expecting FASTA prefix", not the multi-line FASTA message
+    fa = str(tmp_path / "blank.fa")
+    open(fa, "wb").write(b">a\nACGT\n\n>b\nACGT\n")
+    assert_same("fastx_reverse_complement", ["-i", fa])
+    assert_same("fastx_collapser", ["-i", fa])
+    ml = str(tmp_path / "multiline.fa")
+    open(ml, "wb").write(b">a\nACGT\nACGT\n>b\nACGT\n")
+    assert_same("fastx_reverse_complement", ["-i", ml])
 
 
 @gpu
@@ -182,6 +190,36 @@ def test_clipper_text_path_and_fallback_transition(tmp_path):
         finally:
             for k in env:
                 os.environ.pop(k, None)
+
+
+@gpu
+@needs_ref
+def test_clipper_fallback_right_after_a_text_chunk_sees_the_stale_bases(tmp_path):
+    """the GPU text chunk ends exactly where the read length drops: the record path that takes over starts with a SHORT read
+    and must find, behind its end, the bases of the last long read (the reference aligner's grow-only query buffer) — here
+    an adapter, so with -C the short reads are dropped as 'clipped' exactly as the reference drops them"""
+    rng = np.random.default_rng(77)
+    ad = b"AGATCGGAAGAGC"
+    n1, L = 300, 100
+    first = b""
+    for k in range(n1):
+        seq = bytes(rng.choice(list(b"ACGT"), size=L).astype(np.uint8))
+        if k == n1 - 1:
+            seq = seq[:60] + ad + seq[60 + len(ad):]
+        first += b"@r%d\n%s\n+\n%s\n" % (k, seq, b"I" * L)
+    rest = b""
+    for k in range(200):
+        Ls = int(rng.integers(20, 50))
+        rest += b"@s%d\n%s\n+\n%s\n" % (k, bytes(rng.choice(list(b"ACGT"), size=Ls).astype(np.uint8)), b"I" * Ls)
+    assert len(first) >= 16384
+    fq = str(tmp_path / "switch.fq")
+    open(fq, "wb").write(first + rest)
+    os.environ.update(FASTX_CHUNK_BYTES=str(len(first)), FASTX_WINDOW_BYTES=str(4 * len(first)))
+    try:
+        for o in (["-C", "-v"], ["-c", "-v"], ["-v"], ["-n", "-l", "5", "-v"]):
+            assert_same("fastx_clipper", ["-a", ad.decode()] + o + ["-i", fq])
+    finally:
+        os.environ.pop("FASTX_CHUNK_BYTES"); os.environ.pop("FASTX_WINDOW_BYTES")
 
 
 @gpu
@@ -288,6 +326,12 @@ def test_broken_inputs_fail_like_the_reference(tmp_path):
         variant("qualshort.fq", set_line(4 * 8000 + 3, b"I" * 30)),
         variant("two_errors.fq", lambda ls: (ls.__setitem__(4 * 6000 + 3, b"I" * 49 + b"\x01"), ls.__setitem__(4 * 2000 + 1, b"N" * 49 + b"U"))),
         variant("base_and_trunc.fq", lambda ls: (ls.__setitem__(4 * 11000 + 1, b"ACGU" + b"A" * 46), ls.__delitem__(slice(4 * 11000 + 3, None)))),
+        # chomp() ends a line at its FIRST carriage return (chomp.c:34-44): inside a name the rest is dropped, inside the
+        # sequence / quality line the record is short
+        variant("cr_in_name.fq", set_line(4 * 4000, b"@r40\r00 tail")),
+        variant("cr_in_name2.fq", set_line(4 * 4000 + 2, b"+r40\r00")),
+        variant("cr_in_seq.fq", set_line(4 * 9500 + 1, b"ACGTACGT\rCGT" + b"A" * 38)),
+        variant("cr_in_qual.fq", set_line(4 * 9500 + 3, b"I" * 20 + b"\r" + b"I" * 29)),
     ]
     os.environ["FASTX_BATCH_READS"] = "2500"
     try:
