@@ -43,7 +43,7 @@ class TextReport(C.Structure):
     """struct fxg_text_report"""
     _fields_ = [("n_records", C.c_int64), ("n_out_records", C.c_int64), ("consumed_bytes", C.c_int64), ("out_bytes", C.c_int64),
                 ("max_len", C.c_int32), ("anomaly", C.c_int32), ("anomaly_record", C.c_int64),
-                ("min_len", C.c_int32), ("reserved", C.c_int32), ("clip_class", C.c_int64 * 6)]
+                ("min_len", C.c_int32), ("reserved", C.c_int32), ("clip_class", C.c_int64 * 6), ("n_reads", C.c_int64), ("n_out_reads", C.c_int64)]
 
 
 class DCollapseReport(C.Structure):
@@ -146,6 +146,10 @@ def lib():
         "fxg_text_run_host": (i32, [vp, i32, vp, sz, i32, i32, i32, vp, C.POINTER(TextReport)]),
         "fxg_text_clip_host": (i32, [vp, vp, sz, i32, C.POINTER(ClipOpts), i32, i32, vp, C.POINTER(TextReport)]),
         "fxg_text_stats_host": (i32, [vp, vp, sz, i32, vp, C.c_int32, C.POINTER(TextReport)]),
+        "fxg_text_set_format": (i32, [vp, i32]),
+        "fxg_text_collapse_host": (i32, [vp, vp, sz, i32, vp, i64, C.POINTER(TextReport)]),
+        "fxg_text_numeric_chunks": (i64, [vp]),
+        "fxg_text_fasta_chunks": (i64, [vp]),
         "fxg_text_error": (C.c_char_p, [vp]),
         "fxg_text_launches": (i64, [vp]),
         "fxg_collapse_new": (i32, [i32, i64, C.c_int32, C.POINTER(vp)]),
@@ -156,6 +160,7 @@ def lib():
         "fxg_collapse_fetch": (i32, [vp, vp, vp, vp, vp, vp]),
         "fxg_collapse_error": (C.c_char_p, [vp]),
         "fxg_collapse_launches": (i64, [vp]),
+        "fxg_collapse_stride": (C.c_int32, [vp]),
         "fxg_collapse_order_dev": (i32, [i32, vp, vp, vp, i64, vp]),
     }
     for name, (res, args) in sig.items():
@@ -348,6 +353,36 @@ class TextPipe:
         if rc != FXG_OK:
             raise FxgError(rc, self.L.fxg_text_error(self.h).decode())
         return out[: rep.out_bytes].tobytes(), rep
+
+    def set_format(self, fasta):
+        rc = self.L.fxg_text_set_format(self.h, 1 if fasta else 0)
+        if rc != FXG_OK:
+            raise FxgError(rc, "fxg_text_set_format")
+
+    def collapse(self, text, q_offset, collapser, first_base=-1):
+        """fxg_text_collapse_host: add the chunk's reads to a Collapser.  Returns TextReport."""
+        import numpy as np
+        src = np.frombuffer(text, np.uint8) if isinstance(text, (bytes, bytearray)) else text
+        rep = TextReport()
+        rc = self.L.fxg_text_collapse_host(self.h, src.ctypes.data, src.size, q_offset, collapser.h, first_base, C.byref(rep))
+        if rc != FXG_OK:
+            raise FxgError(rc, self.L.fxg_text_error(self.h).decode())
+        return rep
+
+    def stats(self, text, q_offset, hist_dev, max_cycles):
+        import numpy as np
+        src = np.frombuffer(text, np.uint8) if isinstance(text, (bytes, bytearray)) else text
+        rep = TextReport()
+        rc = self.L.fxg_text_stats_host(self.h, src.ctypes.data, src.size, q_offset, _ptr(hist_dev), max_cycles, C.byref(rep))
+        if rc != FXG_OK:
+            raise FxgError(rc, self.L.fxg_text_error(self.h).decode())
+        return rep
+
+    def numeric_chunks(self):
+        return int(self.L.fxg_text_numeric_chunks(self.h))
+
+    def fasta_chunks(self):
+        return int(self.L.fxg_text_fasta_chunks(self.h))
 
     def clip(self, text, q_offset, opts, show_adapter_only=0, expect_len=0):
         """fxg_text_clip_host: fastx_clipper on a chunk of equal-length reads.  Returns (output bytes, TextReport)."""

@@ -505,7 +505,8 @@ static int stats_enqueue(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint64_
     if (rfit4 > S4_TILE_READS) rfit4 = S4_TILE_READS;
     const bool fast4 = ver == 4 && b->qual && !weight && rfit4 >= 8 && t_ring != 0 && q_offset - 15 <= 64 && b->n / rfit4 < (1ll << 31);
     if (fast4) {
-        p.tile_reads = (int)rfit4; p.stages = 1;
+        p.tile_reads = (int)rfit4;
+        { const char *ep = getenv("FXG_STATS_PAIR"); p.stages = (ep && atoi(ep) == 1) ? 1 : 2; }      // 2: warp pairs share a tile buffer
         const uint32_t smem = (uint32_t)((size_t)S4_HIST_BYTES + S4_DUMMY_BYTES + (size_t)S4_WARPS * 2 * b->stride * rfit4);
         const int64_t ntiles = (b->n + rfit4 - 1) / rfit4;
         int64_t grid = ctx->sm_count;
@@ -662,12 +663,13 @@ extern "C" int fxg_internal_clip_on_stream(fxg_ctx *ctx, const fxg_batch *b, int
     CK(ctx, cudaSetDevice(ctx->device));
     return clip_enqueue(ctx, b, NULL, q_offset, o, out_len, out_class, NULL, 0, (cudaStream_t)stream);
 }
-extern "C" int fxg_internal_stats_on_stream(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint64_t *hist, int32_t max_cycles, void *stream)
+extern "C" int fxg_internal_stats_on_stream(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint64_t *hist, int32_t max_cycles,
+                                            const int32_t *weight_dev, void *stream)
 {
     int rc = check_batch(ctx, b, true, false, q_offset);
     if (rc) return rc;
     CK(ctx, cudaSetDevice(ctx->device));
-    return stats_enqueue(ctx, b, q_offset, hist, max_cycles, NULL, 0, (cudaStream_t)stream);
+    return stats_enqueue(ctx, b, q_offset, hist, max_cycles, weight_dev, 0, (cudaStream_t)stream);
 }
 
 // ---- K-HASH (std::hash<std::string> of every read; collapser routing key) ----------------------------------

@@ -135,6 +135,33 @@ __global__ void __launch_bounds__(256) k_fill_len(int32_t *p, int32_t v, int64_t
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) p[t] = v;
 }
 
+// rows from one stride to another (the table grows its stride when a longer read arrives; shorter batches are padded)
+__global__ void __launch_bounds__(256) k_copy_rows(const uint8_t *src, int src_stride, uint8_t *dst, int dst_stride, int64_t n)
+{
+    const int chunks = (src_stride < dst_stride ? src_stride : dst_stride) >> 4;
+    const int64_t total = n * chunks;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t / chunks;
+        const int c = (int)(t - i * chunks);
+        reinterpret_cast<uint4 *>(dst + (size_t)i * dst_stride)[c] = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)i * src_stride) + c);
+    }
+}
+// move every occupied slot of the old table into a larger one (keys are distinct: first empty slot on the probe path)
+__global__ void __launch_bounds__(256) k_rehash(const unsigned long long *slots, const unsigned long long *count, const unsigned long long *firsts,
+                                                const uint64_t *hash, int64_t nslots, unsigned long long *nslots_new_slots, uint64_t mask_new,
+                                                unsigned long long *count_new, unsigned long long *firsts_new)
+{
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nslots; t += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long cur = slots[t];
+        if (cur == 0ull) continue;
+        const uint64_t h = hash[(cur & 0xFFFFFFFFull) - 1ull];
+        uint64_t slot = h & mask_new;
+        while (atomicCAS(&nslots_new_slots[slot], 0ull, cur) != 0ull) slot = (slot + 1) & mask_new;
+        count_new[slot] = count[t];
+        firsts_new[slot] = firsts[t];
+    }
+}
+
 // compact the occupied slots into dense arrays (order irrelevant: everything is sorted afterwards)
 __global__ void __launch_bounds__(256) k_compact(const unsigned long long *slots, const unsigned long long *count,
                                                  const unsigned long long *firsts, const uint64_t *hash, int64_t nslots,
@@ -340,6 +367,7 @@ struct fxg_collapser {
 
 extern "C" const char *fxg_collapse_error(const fxg_collapser *c) { return c ? c->err : "no collapser"; }
 extern "C" int64_t fxg_collapse_launches(const fxg_collapser *c) { return c ? c->launches : 0; }
+extern "C" int32_t fxg_collapse_stride(const fxg_collapser *c) { return c ? c->stride : 0; }
 
 #define CKO(c, call)                                                                               \
     do {                                                                                           \
@@ -362,7 +390,7 @@ extern "C" void fxg_collapse_free(fxg_collapser *c)
 
 extern "C" int fxg_collapse_new(int device, int64_t max_reads, int32_t stride, fxg_collapser **out)
 {
-    if (!out || max_reads <= 0 || max_reads >= 0xFFFFFFF0ll || stride <= 0 || (stride & 15)) return FXG_ERR_ARG;
+    if (!out || max_reads <= 0 || max_reads >= 0xFFFFFFF0ll || stride <= 0 || (stride & 15)) return FXG_ERR_ARG;   // both grow on demand
     *out = NULL;
     if (cudaSetDevice(device) != cudaSuccess) return FXG_ERR_CUDA;
     fxg_collapser *c = (fxg_collapser *)calloc(1, sizeof(fxg_collapser));
@@ -389,15 +417,75 @@ extern "C" int fxg_collapse_new(int device, int64_t max_reads, int32_t stride, f
     return FXG_OK;
 }
 
+// Room for `rows` rows of `stride` bytes: the row store is re-allocated (and re-strided), the table rebuilt at twice the
+// size when it would get more than half full.  A streaming caller does not know the number of reads, or the longest one,
+// when it creates the table.
+static int collapse_reserve(fxg_collapser *c, int64_t rows, int32_t stride)
+{
+    if (rows <= c->cap && stride <= c->stride) return FXG_OK;
+    if (rows >= 0xFFFFFFF0ll) { snprintf(c->err, sizeof(c->err), "collapser: more than 2^32 rows"); return FXG_ERR_UNSUPPORTED; }
+    int64_t ncap = c->cap;
+    while (ncap < rows) ncap = ncap * 2 > 0xFFFFFFEFll ? 0xFFFFFFEFll : ncap * 2;
+    const int32_t nstride = stride > c->stride ? stride : c->stride;
+    if (ncap != c->cap || nstride != c->stride) {
+        uint8_t *nk = NULL; int32_t *nl = NULL; uint64_t *nh = NULL;
+        CKO(c, cudaMalloc(&nk, (size_t)ncap * nstride)); CKO(c, cudaMalloc(&nl, (size_t)ncap * 4)); CKO(c, cudaMalloc(&nh, (size_t)ncap * 8));
+        if (c->rows > 0) {
+            if (nstride == c->stride) CKO(c, cudaMemcpyAsync(nk, c->keys, (size_t)c->rows * nstride, cudaMemcpyDeviceToDevice, c->st));
+            else { k_copy_rows<<<grid_for((uint64_t)c->rows * (c->stride >> 4)), 256, 0, c->st>>>(c->keys, c->stride, nk, nstride, c->rows); c->launches++; }
+            CKO(c, cudaMemcpyAsync(nl, c->len, (size_t)c->rows * 4, cudaMemcpyDeviceToDevice, c->st));
+            CKO(c, cudaMemcpyAsync(nh, c->hash, (size_t)c->rows * 8, cudaMemcpyDeviceToDevice, c->st));
+        }
+        CKO(c, cudaStreamSynchronize(c->st));
+        cudaFree(c->keys); cudaFree(c->len); cudaFree(c->hash);
+        c->keys = nk; c->len = nl; c->hash = nh; c->cap = ncap; c->stride = nstride;
+    }
+    uint64_t ns = c->nslots;
+    while (ns < (uint64_t)ncap * 2) ns <<= 1;
+    if (ns != c->nslots) {
+        unsigned long long *s2 = NULL, *c2 = NULL, *f2 = NULL;
+        CKO(c, cudaMalloc(&s2, ns * 8)); CKO(c, cudaMalloc(&c2, ns * 8)); CKO(c, cudaMalloc(&f2, ns * 8));
+        CKO(c, cudaMemsetAsync(s2, 0, ns * 8, c->st)); CKO(c, cudaMemsetAsync(c2, 0, ns * 8, c->st)); CKO(c, cudaMemsetAsync(f2, 0xFF, ns * 8, c->st));
+        k_rehash<<<grid_for(c->nslots), 256, 0, c->st>>>(c->slots, c->count, c->firsts, c->hash, (int64_t)c->nslots, s2, ns - 1, c2, f2);
+        c->launches++;
+        CKO(c, cudaStreamSynchronize(c->st));
+        cudaFree(c->slots); cudaFree(c->count); cudaFree(c->firsts);
+        c->slots = s2; c->count = c2; c->firsts = f2; c->nslots = ns;
+    }
+    return FXG_OK;
+}
+
 // Append rows (device or host memory — cudaMemcpyDefault) and insert them.  weight/first: see fxg.h.
 extern "C" int fxg_collapse_add(fxg_collapser *c, const fxg_batch *b, const int32_t *weight, const int64_t *first, int64_t index_base)
 {
-    if (!c || !b || !b->seq || b->n < 0 || b->stride != c->stride) return FXG_ERR_ARG;
-    if (c->rows + b->n > c->cap) { snprintf(c->err, sizeof(c->err), "collapser capacity %lld rows exceeded", (long long)c->cap); return FXG_ERR_ARG; }
+    if (!c || !b || !b->seq || b->n < 0 || b->stride <= 0 || (b->stride & 15)) return FXG_ERR_ARG;
     if (b->n == 0) return FXG_OK;
     CKO(c, cudaSetDevice(c->device));
+    { int rc = collapse_reserve(c, c->rows + b->n, b->stride); if (rc) return rc; }
     const int64_t row0 = c->rows;
     const size_t S = (size_t)c->stride;
+    if (b->stride != c->stride) {
+        // a batch of shorter rows: staged on the device, then copied row by row into the table's stride
+        uint8_t *tmp = NULL; int32_t *d_w = NULL; int64_t *d_f = NULL;
+        CKO(c, cudaMalloc(&tmp, (size_t)b->n * b->stride));
+        CKO(c, cudaMemcpyAsync(tmp, b->seq, (size_t)b->n * b->stride, cudaMemcpyDefault, c->st));
+        k_copy_rows<<<grid_for((uint64_t)b->n * (b->stride >> 4)), 256, 0, c->st>>>(tmp, b->stride, c->keys + (size_t)row0 * S, c->stride, b->n);
+        if (weight) { CKO(c, cudaMalloc(&d_w, (size_t)b->n * 4)); CKO(c, cudaMemcpyAsync(d_w, weight, (size_t)b->n * 4, cudaMemcpyDefault, c->st)); }
+        if (first) { CKO(c, cudaMalloc(&d_f, (size_t)b->n * 8)); CKO(c, cudaMemcpyAsync(d_f, first, (size_t)b->n * 8, cudaMemcpyDefault, c->st)); }
+        if (b->len) CKO(c, cudaMemcpyAsync(c->len + row0, b->len, (size_t)b->n * 4, cudaMemcpyDefault, c->st));
+        else k_fill_len<<<grid_for((uint64_t)b->n), 256, 0, c->st>>>(c->len + row0, b->uniform_len, b->n);
+        DedupParams p;
+        p.keys = c->keys; p.len = c->len; p.meta = NULL; p.stride = c->stride; p.row0 = row0; p.n = b->n;
+        p.weight = d_w; p.first = d_f; p.index_base = index_base;
+        p.hash = c->hash; p.slots = c->slots; p.mask = c->nslots - 1; p.count = c->count; p.firsts = c->firsts; p.counters = c->d_counters;
+        k_hash_dedup<<<grid_for((uint64_t)b->n), 256, 0, c->st>>>(p);
+        CKO(c, cudaGetLastError());
+        c->launches += 3;
+        CKO(c, cudaStreamSynchronize(c->st));
+        cudaFree(tmp); cudaFree(d_w); cudaFree(d_f);
+        c->rows += b->n;
+        return FXG_OK;
+    }
     // stream the rows in chunks so that H2D copies overlap the insert kernel of the previous chunk
     const int64_t chunk = (64ll << 20) / (int64_t)S;
     int32_t *d_w = NULL; int64_t *d_f = NULL;
@@ -426,6 +514,23 @@ extern "C" int fxg_collapse_add(fxg_collapser *c, const fxg_batch *b, const int3
 extern "C" int fxg_collapse_add_next(fxg_collapser *c, const fxg_batch *b)
 {
     return c ? fxg_collapse_add(c, b, NULL, NULL, c->rows) : FXG_ERR_ARG;
+}
+
+// add_next() that also says whether THIS batch held a read the reader would reject (row index inside the batch, -1 = none):
+// the GPU text path hands such a chunk back to the host parser, which words the reference's message
+// first_base: first-occurrence index of the batch's row 0 (< 0: the number of rows added so far)
+extern "C" int fxg_collapse_add_checked(fxg_collapser *c, const fxg_batch *b, const int32_t *weight, int64_t first_base, int64_t *first_bad_row)
+{
+    if (!c || !first_bad_row) return FXG_ERR_ARG;
+    const int64_t base = first_base >= 0 ? first_base : c->rows;
+    unsigned long long before = 0, after = 0;
+    CKO(c, cudaSetDevice(c->device));
+    CKO(c, cudaMemcpy(&before, c->d_counters + CNT_FIRST_BAD, 8, cudaMemcpyDeviceToHost));
+    int rc = fxg_collapse_add(c, b, weight, NULL, base);
+    if (rc) return rc;
+    CKO(c, cudaMemcpy(&after, c->d_counters + CNT_FIRST_BAD, 8, cudaMemcpyDeviceToHost));
+    *first_bad_row = (after != before && after != ~0ull && (int64_t)after >= base) ? (int64_t)after - base : -1;
+    return FXG_OK;
 }
 
 // Compact the table; with order != 0 also compute the reference's output order.

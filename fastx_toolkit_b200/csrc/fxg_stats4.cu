@@ -52,6 +52,21 @@ __device__ __forceinline__ void s4_red(uint32_t addr, uint32_t inc)
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(inc) : "memory");
 }
 
+// increment only when `on` (a predicated RED: lanes that are off touch no bank at all)
+__device__ __forceinline__ void s4_red_if(uint32_t addr, uint32_t inc, bool on)
+{
+    asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %2, 0;\n @p red.shared.add.u32 [%0], %1;\n}" ::"r"(addr), "r"(inc), "r"((uint32_t)on) : "memory");
+}
+// increment only when k < vb (the byte lies inside the read)
+__device__ __forceinline__ void s4_red_lt(uint32_t addr, uint32_t inc, int k, int vb)
+{
+    asm volatile("{\n .reg .pred p;\n setp.lt.s32 p, %2, %3;\n @p red.shared.add.u32 [%0], %1;\n}" ::"r"(addr), "r"(inc), "r"(k), "r"(vb) : "memory");
+}
+__device__ __forceinline__ void s4_mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // byte address (relative to the histogram) and increment of the shared counter of (bin, window word w, byte k)
 __device__ __forceinline__ uint32_t s4_counter(uint32_t bin, int w, int k, uint32_t &inc)
 {
@@ -117,37 +132,39 @@ __device__ __forceinline__ void s4_emit_a(uint32_t comb, const uint32_t (&ksel)[
 }
 // the same with bytes past the end of the read steered to a scratch counter (vb = valid bytes of the word, may be <= 0)
 template <int WI>
-__device__ __forceinline__ void s4_emit_a_masked(uint32_t comb, int vb, const uint32_t (&ksel)[4], const uint32_t (&cb)[4], uint32_t dummy)
+__device__ __forceinline__ void s4_emit_a_masked(uint32_t comb, int vb, const uint32_t (&ksel)[4], const uint32_t (&cb)[4])
 {
     constexpr uint32_t IMM = 128u * (uint32_t)(WI >> 1), INC = (WI & 1) ? 0x10000u : 1u;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const uint32_t addr = prmt_raw(comb, 0u, ksel[i]) * (uint32_t)S4_PITCH + cb[i] + IMM;
-        s4_red((int)(ksel[i] & 3u) < vb ? addr : dummy, INC);
-    }
+    for (int i = 0; i < 4; i++)
+        s4_red_lt(prmt_raw(comb, 0u, ksel[i]) * (uint32_t)S4_PITCH + cb[i] + IMM, INC, (int)(ksel[i] & 3u), vb);
 }
 
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 1) k_stats4(const __grid_constant__ StatsParams P)
+// TILES tile buffers per CTA, PAIR warps per buffer (PAIR = 2: the two warps of a pair read the same 32 reads and split the
+// chunk steps between them — twice the warps to hide latency behind, for the same shared memory)
+template <int TILES, int PAIR>
+__global__ void __launch_bounds__(TILES * PAIR * 32, 1) k_stats4(const __grid_constant__ StatsParams P)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    constexpr int NTHREADS = WARPS * 32;
-    __shared__ __align__(8) uint64_t full_bar[WARPS];
+    constexpr int NTHREADS = TILES * PAIR * 32;
+    __shared__ __align__(8) uint64_t full_bar[TILES], empty_bar[TILES];
 
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int S = P.stride, R = P.tile_reads;                          // R <= 32 reads per warp tile, one per lane
+    const int tid = threadIdx.x, lane = tid & 31, w = (tid >> 5) / PAIR, half = (tid >> 5) % PAIR;
+    const int S = P.stride, R = P.tile_reads;                          // R <= 32 reads per tile, one per lane
     const uint32_t slab_bytes = (uint32_t)R * (uint32_t)S;
     uint8_t *wbase = smem + S4_HIST_BYTES + S4_DUMMY_BYTES + (size_t)w * (2u * slab_bytes);
-    uint64_t *bar = &full_bar[w];
+    uint64_t *bar = &full_bar[w], *ebar = &empty_bar[w];
     const uint32_t ntiles = (uint32_t)((P.n + R - 1) / R);            // host guarantees n / R < 2^31
-    const uint32_t gw = blockIdx.x * WARPS + w, GW = gridDim.x * WARPS;
-    const uint32_t gw0 = blockIdx.x * WARPS;                           // the CTA's first warp has the most tiles
+    const uint32_t gw = blockIdx.x * TILES + w, GW = gridDim.x * TILES;
+    const uint32_t gw0 = blockIdx.x * TILES;                           // the CTA's first tile slot has the most tiles
     const uint32_t rounds = gw0 < ntiles ? (ntiles - gw0 + GW - 1) / GW : 0u;
+    constexpr int T0 = 8 / PAIR;                                       // chunk / word steps per warp
 
     for (uint32_t i = tid * 16; i < (uint32_t)(S4_HIST_BYTES + S4_DUMMY_BYTES); i += NTHREADS * 16)
         *reinterpret_cast<uint4 *>(smem + i) = make_uint4(0, 0, 0, 0);
-    if (lane == 0) {
+    if (lane == 0 && half == 0) {
         mbar_init(bar, 1);
+        mbar_init(ebar, PAIR);
         mbar_fence_init();
     }
     __syncthreads();
@@ -161,12 +178,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_stats4(const __grid_constant_
         bulk_g2s(wbase + slab_bytes, gq, bytes, bar);
         gs += gstep; gq += gstep;
     };
-    if (lane == 0 && gw < ntiles) issue(gw);
+    if (lane == 0 && half == 0 && gw < ntiles) issue(gw);
 
     const uint32_t hs_addr = smem_u32(smem);
-    const uint32_t dummy = hs_addr + (uint32_t)S4_HIST_BYTES + 4u * (uint32_t)lane;
     Stats4K K;
-    const uint32_t zero = (uint32_t)((unsigned long long)P.n >> 62);       // 0, but only known at run time
+    // 0, but read from (zeroed) shared memory: per thread and opaque, so the three constants live in ordinary registers — as
+    // uniform values or immediates they are copied into one in front of every PRMT that uses them
+    const uint32_t zero = s4_lds32(hs_addr + (uint32_t)S4_HIST_BYTES + 4u * (uint32_t)lane);
     K.vlut_lo = VLUT_LO + zero; K.n6_lo = S4_N6_LO + zero; K.neg_lo4 = zero - P.qk.lo4;
     const int passoff = 4 * P.w0, ncols = 4 * P.nw;              // this pass covers cycles [passoff, passoff + ncols), ncols <= 160
 
@@ -176,6 +194,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_stats4(const __grid_constant_
     const int r_l = odd_pitch ? ((2 * i8 + (q8 & 1)) & 7) : i8;
     const int kb_l = odd_pitch ? (2 * (q8 >> 1) + (i8 >> 2)) : q8;
     uint32_t ksel[4], kcol[4], kselb[4], kcolb[4];
+    int kb4[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const uint32_t k = (uint32_t)((i + kb_l) & 3);
@@ -184,6 +203,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_stats4(const __grid_constant_
         const uint32_t kb = (uint32_t)((i + lane) & 3);
         kselb[i] = 0x4440u + kb;
         kcolb[i] = hs_addr + 4u * (64u + kb);                    // + 16W per word
+        kb4[i] = (int)kb;
     }
     const int wb0 = lane >> 2;
     const uint32_t srow = smem_u32(wbase) + (uint32_t)(lane < R ? lane : 0) * (uint32_t)S + (uint32_t)passoff;
@@ -191,7 +211,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_stats4(const __grid_constant_
     const int ulen = P.uniform_len;
     const bool ragged = P.len != nullptr;
     const uint32_t lo4 = P.qk.lo4;
-    uint32_t parity = 0;
+    uint32_t parity = 0, eparity = 0;
+    const int tbeg = half * T0;
 
     for (uint32_t round = 0; round < rounds; round++) {
         const uint32_t tile = gw + round * GW;
@@ -211,7 +232,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_stats4(const __grid_constant_
             // ---- A region: words 0..31 ----
             if (__all_sync(0xFFFFFFFFu, Lp >= 128)) {
 #pragma unroll 2
-                for (int t = 0; t < 8; t++) {
+                for (int t = tbeg; t < tbeg + T0; t++) {
                     const uint32_t c = (uint32_t)((t + r_l) & 7);
                     const uint4 s4 = s4_lds128(srow + 16u * c), q4 = s4_lds128(qrow + 16u * c);
                     uint32_t cb[4];
@@ -234,7 +255,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_stats4(const __grid_constant_
                 // some read of the tile ends inside the A region: every word carries its count of valid bytes
                 const int tmax = (__reduce_max_sync(0xFFFFFFFFu, Lp) + 15) >> 4;     // chunks any lane still needs (warp uniform)
                 if (tmax > 0) {
-                    for (int t = 0; t < 8; t++) {
+                    for (int t = tbeg; t < tbeg + T0; t++) {
                         const uint32_t c = (uint32_t)((t + r_l) & 7);
                         const int vbc = Lp - 16 * (int)c;                            // valid bytes from this chunk on
                         if (!__any_sync(0xFFFFFFFFu, vbc > 0)) continue;
@@ -254,7 +275,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_stats4(const __grid_constant_
 #define S4_MASKED_WORD(WI)                                                                                           \
     do {                                                                                                             \
         const int vb_ = vbc - 4 * WI;                                                                                \
-        if (tst[WI] == 0u) s4_emit_a_masked<WI>(comb[WI], vb_, ksel, cb, dummy);                                     \
+        if (tst[WI] == 0u) s4_emit_a_masked<WI>(comb[WI], vb_, ksel, cb);                                     \
         else if (vb_ > 0) bad |= s4_slow_word(P, sws[WI], qws[WI], w4 + WI, vb_ < 4 ? vb_ : 4, hs_addr);             \
     } while (0)
                         S4_MASKED_WORD(0); S4_MASKED_WORD(1); S4_MASKED_WORD(2); S4_MASKED_WORD(3);
@@ -265,10 +286,29 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_stats4(const __grid_constant_
             // ---- B region: words 32..39 (the read's last bases included) ----
             {
                 const int LpB = Lp - 128;
-                if (__any_sync(0xFFFFFFFFu, LpB > 0)) {
+                const bool b_full4 = __all_sync(0xFFFFFFFFu, LpB >= 16);      // every read holds words 32..35 complete
+                if (b_full4) {
+                    // words 32..35 without masks: lane l visits word (l>>2 + a) & 3 — two lanes per counter (same address:
+                    // two wavefronts per RED), a fraction of the masked steps' instructions
+#pragma unroll
+                    for (int a = half * (4 / PAIR); a < (half + 1) * (4 / PAIR); a++) {
+                        const uint32_t W = (uint32_t)((wb0 + a) & 3);
+                        const uint32_t sw = s4_lds32(srow + 128u + 4u * W), qw = s4_lds32(qrow + 128u + 4u * W);
+                        uint32_t comb;
+                        if (s4_decode(K, sw, qw, comb) == 0u) {
+#pragma unroll
+                            for (int b = 0; b < 4; b++) s4_red(prmt_raw(comb, 0u, kselb[b]) * (uint32_t)S4_PITCH + kcolb[b] + 16u * W, 1u);
+                        } else {
+                            bad |= s4_slow_word(P, sw, qw, 32 + (int)W, 4, hs_addr);
+                        }
+                    }
+                }
+                // the rest (words 36..39 after the full block, else 32..39): every byte carries its validity
+                const int wlo = b_full4 ? 4 : 0, wn = b_full4 ? 4 : 8;       // wn words starting at 32 + wlo
+                if (__any_sync(0xFFFFFFFFu, LpB > 4 * wlo)) {
 #pragma unroll 2
-                    for (int a = 0; a < 8; a++) {
-                        const uint32_t W = (uint32_t)((wb0 + a) & 7);
+                    for (int a = half * (wn / PAIR); a < (half + 1) * (wn / PAIR); a++) {
+                        const uint32_t W = (uint32_t)(wlo + ((wb0 + a) & (wn - 1)));
                         const int vb = LpB - 4 * (int)W;
                         uint32_t sw = 0, qw = 0;
                         if (vb > 0) { sw = s4_lds32(srow + 128u + 4u * W); qw = s4_lds32(qrow + 128u + 4u * W); }
@@ -277,10 +317,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_stats4(const __grid_constant_
                         const uint32_t tst = s4_decode(K, (sw & m) | (0x41414141u & ~m), (qw & m) | (lo4 & ~m), comb);
                         if (tst == 0u) {
 #pragma unroll
-                            for (int b = 0; b < 4; b++) {
-                                const uint32_t addr = prmt_raw(comb, 0u, kselb[b]) * (uint32_t)S4_PITCH + kcolb[b] + 16u * W;
-                                s4_red((int)(kselb[b] & 3u) < vb ? addr : dummy, 1u);
-                            }
+                            for (int b = 0; b < 4; b++)
+                                s4_red_lt(prmt_raw(comb, 0u, kselb[b]) * (uint32_t)S4_PITCH + kcolb[b] + 16u * W, 1u, kb4[b], vb);
                         } else if (vb > 0) {
                             bad |= s4_slow_word(P, sw, qw, 32 + (int)W, vb < 4 ? vb : 4, hs_addr);
                         }
@@ -290,10 +328,19 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_stats4(const __grid_constant_
             if ((bad != 0 || lenbad) && active) atomicMin(&P.counters[CNT_FIRST_BAD], (unsigned long long)(P.index_base + g));
 
             __syncwarp();
-            if (lane == 0 && tile + GW < ntiles) issue(tile + GW);
+            if (PAIR == 1) {
+                if (lane == 0 && tile + GW < ntiles) issue(tile + GW);
+            } else if (lane == 0) {
+                s4_mbar_arrive(ebar);                                  // this warp is done with the buffer
+                if (half == 0 && tile + GW < ntiles) {                 // the pair's first warp refills it when both are
+                    mbar_wait(ebar, eparity);
+                    issue(tile + GW);
+                }
+                eparity ^= 1u;
+            }
         }
         // a u16 half of the A region holds at most one increment per read: flush before 65 535 reads went through this CTA
-        if ((round + 1u) % (uint32_t)(65535 / NTHREADS) == 0u || round + 1u == rounds) {
+        if ((round + 1u) % (uint32_t)(65535 / (TILES * 32)) == 0u || round + 1u == rounds) {
             __syncthreads();
             for (int i = tid; i < S4_HIST_BYTES / 4; i += NTHREADS) {
                 uint32_t *cell = reinterpret_cast<uint32_t *>(smem) + i;
@@ -318,8 +365,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_stats4(const __grid_constant_
 
 cudaError_t launch_stats4(const StatsParams &p, int grid, uint32_t smem_bytes, cudaStream_t st)
 {
-    cudaFuncSetAttribute(k_stats4<S4_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
-    k_stats4<S4_WARPS><<<grid, S4_WARPS * 32, smem_bytes, st>>>(p);
+    if (p.stages == 2) {          // warp pairs
+        cudaFuncSetAttribute(k_stats4<S4_WARPS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+        k_stats4<S4_WARPS, 2><<<grid, S4_WARPS * 64, smem_bytes, st>>>(p);
+    } else {
+        cudaFuncSetAttribute(k_stats4<S4_WARPS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+        k_stats4<S4_WARPS, 1><<<grid, S4_WARPS * 32, smem_bytes, st>>>(p);
+    }
     return cudaGetLastError();
 }
 

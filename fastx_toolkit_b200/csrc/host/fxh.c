@@ -15,6 +15,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/stat.h>
+#include <sys/uio.h>
 #include <sys/types.h>
 #include <sys/wait.h>
 #include <time.h>
@@ -439,6 +440,41 @@ void fxh_reader_consume(fxh_reader *r, size_t bytes, int64_t records)
     r->next_index += records;
 }
 
+/* ---- hooks for the streaming engine (fxh_stream.c) ---- */
+int fxh_reader_fd(const fxh_reader *r) { return r->fd; }
+
+/* the unparsed bytes the reader holds (they stay where they are until fxh_reader_restart) and whether the input ended there */
+void fxh_reader_detach(fxh_reader *r, char **p, size_t *len, int *eof)
+{
+    *p = r->buf + r->pos;
+    *len = r->len - r->pos;
+    *eof = r->eof;
+}
+
+/* records the engine consumed on the reader's behalf */
+void fxh_reader_account(fxh_reader *r, int64_t records, int64_t reads, int lines_per_record)
+{
+    r->line_no += (uint64_t)lines_per_record * (uint64_t)records;
+    r->n_seq += (size_t)records;
+    r->n_reads += (size_t)reads;
+    r->next_index += records;
+}
+
+/* the reader continues with these bytes (in order), then with whatever its file descriptor still delivers */
+void fxh_reader_restart(fxh_reader *r, const struct iovec *iov, int niov, int eof)
+{
+    size_t total = 0;
+    for (int i = 0; i < niov; i++) total += iov[i].iov_len;
+    size_t cap = r->cap;
+    while (cap < 2 * total + 4096) cap *= 2;
+    char *nb = (char *)malloc(cap + 1);
+    if (!nb) err(1, "out of memory (input buffer)");
+    size_t off = 0;
+    for (int i = 0; i < niov; i++) { memcpy(nb + off, iov[i].iov_base, iov[i].iov_len); off += iov[i].iov_len; }
+    free(r->buf);
+    r->buf = nb; r->cap = cap; r->len = total; r->pos = 0; r->eof = eof;
+}
+
 void fxh_reader_pin(fxh_reader *r)
 {
     if (r->cap >= ((size_t)32 << 20)) (void)fxg_host_register(r->buf, r->cap + 1);   /* small inputs: not worth page-locking */
@@ -678,6 +714,15 @@ void fxh_write_raw(fxh_writer *w, const char *text, size_t bytes, int64_t record
     pthread_mutex_unlock(&w->aw_mu);
     w->n_seq += (size_t)records;
     w->n_reads += (size_t)records;
+}
+
+/* formatted text, written before the call returns (the streaming engine's own thread is the background here) */
+void fxh_writer_write_now(fxh_writer *w, const char *text, size_t bytes, int64_t records, int64_t reads)
+{
+    writer_flush(w);
+    write_all(w->fd, text, bytes);
+    w->n_seq += (size_t)records;
+    w->n_reads += (size_t)reads;
 }
 
 void fxh_writer_close(fxh_writer *w)

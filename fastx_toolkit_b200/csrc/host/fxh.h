@@ -17,6 +17,7 @@
 #include <stddef.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <sys/uio.h>
 
 #include "fxg.h"
 
@@ -77,6 +78,12 @@ void        fxh_reader_seed_shadow(fxh_reader *r, const char *last_seq, int len)
 int         fxh_text_path_enabled(void);                                   /* FASTX_TEXT_PATH=0 disables it            */
 size_t      fxh_text_chunk_bytes(void);                                    /* FASTX_CHUNK_BYTES (default 64 MB)        */
 
+/* ---- hooks for the streaming engine (fxh_stream.c), which reads the file descriptor itself while it runs ---- */
+int         fxh_reader_fd(const fxh_reader *r);
+void        fxh_reader_detach(fxh_reader *r, char **p, size_t *len, int *eof);
+void        fxh_reader_account(fxh_reader *r, int64_t records, int64_t reads, int lines_per_record);
+void        fxh_reader_restart(fxh_reader *r, const struct iovec *iov, int niov, int eof);
+
 /* ---- writer ---- */
 typedef struct fxh_writer fxh_writer;
 fxh_writer *fxh_writer_open(const char *filename, int fastq, int compress);
@@ -87,6 +94,7 @@ void        fxh_write_record(fxh_writer *w, const fxh_batch *b, int64_t i, const
 void        fxh_write_record_named(fxh_writer *w, const fxh_batch *b, int64_t i, const uint8_t *seq_row, const uint8_t *qual_row,
                                    int32_t out_len, const char *name, int32_t name_len);
 void        fxh_write_raw(fxh_writer *w, const char *text, size_t bytes, int64_t records);   /* already formatted */
+void        fxh_writer_write_now(fxh_writer *w, const char *text, size_t bytes, int64_t records, int64_t reads);
 void        fxh_writer_close(fxh_writer *w);
 size_t      fxh_num_output_sequences(const fxh_writer *w);
 size_t      fxh_num_output_reads(const fxh_writer *w);

@@ -19,6 +19,7 @@
 #include <unistd.h>
 
 #include "fxh.h"
+#include "fxh_stream.h"
 #include "fxh_usage.h"
 
 static void *pinned(size_t bytes)
@@ -38,52 +39,21 @@ static void *pbuf_get(pbuf *b, size_t bytes)
 
 static int batch_q(const fxh_batch *b) { return b->numeric_qual ? 33 : fxh_q_offset(); }
 
-/* GPU text path (fxg_text_*): whole chunks of raw FASTQ go to the GPU, which parses, packs, runs op and emits the
- * output text; the host only moves blocks.  It stops at the first chunk holding anything it does not reproduce
- * bit-exactly by construction (numeric qualities, broken structure, illegal bytes) and leaves the reader positioned
- * at that chunk, so the record-by-record host path that follows produces the reference's output and message. */
-static void text_fast_path(fxg_ctx *ctx, fxh_reader *rd, fxh_writer *wr, int op, int a0, int a1)
+/* GPU text path (fxg_text_*) driven by the streaming engine (fxh_stream.c): whole chunks of raw FASTQ / FASTA text go to
+ * the GPUs (FASTX_GPUS of them), which parse, pack, run the op and emit the output text; the host only moves blocks, with
+ * read(2), the copies, the kernels and write(2) overlapped.  The engine stops at the first chunk holding anything the GPU
+ * path does not reproduce bit-exactly by construction (broken structure, illegal bytes, mixed quality encodings) and
+ * leaves the reader positioned there, so the record-by-record host path that follows produces the reference's output
+ * and message. */
+static int first_gpu(void) { return getenv("FASTX_GPU") ? atoi(getenv("FASTX_GPU")) : 0; }
+
+static void text_fast_path(fxh_reader *rd, fxh_writer *wr, int op, int a0, int a1)
 {
-    if (!fxh_text_path_enabled() || !fxh_reader_is_fastq(rd)) return;
-    char *p;
-    size_t len = fxh_reader_raw(rd, &p);
-    if (len == 0) return;
-    size_t cap = fxh_text_chunk_bytes();       /* chunk size: small enough to overlap, large enough for PCIe */
-    if (fxh_reader_at_eof(rd) && len + 4096 < cap) cap = len + 4096;
-    fxg_text *tx = NULL;
-    const int dev = getenv("FASTX_GPU") ? atoi(getenv("FASTX_GPU")) : 0;
-    if (fxg_text_new(ctx, dev, cap, &tx) != FXG_OK) return;            /* not enough memory: host path */
-    const size_t ocap = cap + cap / 4 + 64;
-    char *out = (char *)pinned(2 * ocap);       /* two output blocks: one is being written while the next is filled */
-    int which = 0;
-    const int timing = getenv("FASTX_TIMING") != NULL;
-    double t_read = 0, t_gpu = 0, t_write = 0, t0 = fxh_now(), ta, tb;
-    fxh_reader_pin(rd);
-    const double t_pin = fxh_now() - t0;
-    for (;;) {
-        ta = fxh_now();
-        len = fxh_reader_raw(rd, &p);
-        tb = fxh_now(); t_read += tb - ta;
-        if (len == 0) break;
-        if (len > cap) len = cap;
-        fxg_text_report rep;
-        char *o = out + (size_t)which * ocap;
-        int rc = fxg_text_run_host(tx, op, p, len, fxh_q_offset(), a0, a1, o, &rep);
-        ta = fxh_now(); t_gpu += ta - tb;
-        if (rc != FXG_OK) errx(1, "fxg_text_run_host failed: %s (%s)", fxg_strerror(rc), fxg_text_error(tx));
-        if (rep.anomaly != 0 || rep.n_records == 0) break;             /* let the host parser look at this chunk */
-        fxh_write_raw(wr, o, (size_t)rep.out_bytes, rep.n_out_records);
-        fxh_reader_consume(rd, (size_t)rep.consumed_bytes, rep.n_records);
-        t_write += fxh_now() - ta;
-        which ^= 1;
-    }
-    ta = fxh_now();
-    fxh_write_raw(wr, out, 0, 0);               /* drain the background write before the blocks are released */
-    t_write += fxh_now() - ta;
-    if (timing) fprintf(stderr, "[timing] text path: pin %.3f s, read/refill %.3f s, H2D+GPU+D2H %.3f s, waiting for write(2) %.3f s, total %.3f s\n",
-                        t_pin, t_read, t_gpu, t_write, fxh_now() - t0);
-    fxg_free_pinned(out);
-    fxg_text_free(tx);
+    fxs_job job;
+    memset(&job, 0, sizeof job);
+    job.op = op; job.a0 = a0; job.a1 = a1;
+    job.ngpu = fxh_gpu_count(); job.first_dev = first_gpu();
+    (void)fxs_run(&job, rd, wr);
 }
 
 /* ================================================================================ fastq_quality_trimmer */
@@ -119,7 +89,7 @@ static int main_trimmer(int argc, char **argv)
     if (getenv("FASTX_TIMING")) fprintf(stderr, "[timing] open+first read %.3f s, GPU context %.3f s\n", t_opened - t_start, fxh_now() - t_opened);
     pbuf out = { 0, 0 };
     fxh_batch *b;
-    text_fast_path(ctx, rd, wr, 0, tr_min_quality, tr_min_length);
+    text_fast_path(rd, wr, FXS_TRIM, tr_min_quality, tr_min_length);
     while ((b = fxh_reader_next(rd, fxh_batch_reads())) != NULL) {
         int32_t *out_len = (int32_t *)pbuf_get(&out, (size_t)b->n * sizeof(int32_t));
         fxg_batch gb = fxh_as_fxg_batch(b, 1);
@@ -176,7 +146,7 @@ static int main_filter(int argc, char **argv)
     fxg_ctx *ctx = fxh_gpu_open();
     pbuf out = { 0, 0 };
     fxh_batch *b;
-    text_fast_path(ctx, rd, wr, 1, fl_min_quality, fl_min_percent);
+    text_fast_path(rd, wr, FXS_FILTER, fl_min_quality, fl_min_percent);
     while ((b = fxh_reader_next(rd, fxh_batch_reads())) != NULL) {
         uint8_t *keep = (uint8_t *)pbuf_get(&out, (size_t)b->n);
         fxg_batch gb = fxh_as_fxg_batch(b, 1);
@@ -212,7 +182,7 @@ static int main_revcomp(int argc, char **argv)
     fxg_ctx *ctx = fxh_gpu_open();
     pbuf os = { 0, 0 }, oq = { 0, 0 };
     fxh_batch *b;
-    text_fast_path(ctx, rd, wr, 2, 0, 0);          /* FASTQ only; FASTA goes through the host parser */
+    text_fast_path(rd, wr, FXS_REVCOMP, 0, 0);
     while ((b = fxh_reader_next(rd, fxh_batch_reads())) != NULL) {
         const size_t bytes = (size_t)b->n * b->stride;
         uint8_t *oseq = (uint8_t *)pbuf_get(&os, bytes), *oqual = fastq ? (uint8_t *)pbuf_get(&oq, bytes) : NULL;
@@ -271,51 +241,18 @@ static int cl_args(int oi, int optc, char *oa)
     return 1;
 }
 
-/* GPU text path for the clipper: chunks whose reads all have one length (the usual sequencer output).  The first
- * chunk with another length, a malformed record or an illegal byte goes — with everything after it — to the record
- * path below, whose packer is told what the aligner's query buffer would hold at that point. */
-static void clip_text_path(fxg_ctx *ctx, fxh_reader *rd, fxh_writer *wr, const fxg_clip_opts *o, unsigned int *count_input, unsigned int *cnt)
+/* fastx_clipper on the GPU text path: chunks whose reads all have one and the same length (the usual raw-reads case).
+ * The first chunk with another length hands over to the record path, whose packer reproduces the reference aligner's
+ * stale query buffer — the engine seeds it with the last read it consumed. */
+static void clip_text_path(fxh_reader *rd, fxh_writer *wr, const fxg_clip_opts *o, unsigned int *count_input, unsigned int *cnt)
 {
-    if (!fxh_text_path_enabled() || !fxh_reader_is_fastq(rd)) return;
-    char *p;
-    size_t len = fxh_reader_raw(rd, &p);
-    if (len == 0) return;
-    size_t cap = fxh_text_chunk_bytes();
-    if (fxh_reader_at_eof(rd) && len + 4096 < cap) cap = len + 4096;
-    fxg_text *tx = NULL;
-    const int dev = getenv("FASTX_GPU") ? atoi(getenv("FASTX_GPU")) : 0;
-    if (fxg_text_new(ctx, dev, cap, &tx) != FXG_OK) return;
-    const size_t ocap = cap + cap / 4 + 64;
-    char *out = (char *)pinned(2 * ocap);
-    int which = 0, expect_len = 0;
-    fxh_reader_pin(rd);
-    for (;;) {
-        len = fxh_reader_raw(rd, &p);
-        if (len == 0) break;
-        if (len > cap) len = cap;
-        fxg_text_report rep;
-        char *ob = out + (size_t)which * ocap;
-        int rc = fxg_text_clip_host(tx, p, len, fxh_q_offset(), o, cl_show_adapter_only, expect_len, ob, &rep);
-        if (rc != FXG_OK) errx(1, "fxg_text_clip_host failed: %s (%s)", fxg_strerror(rc), fxg_text_error(tx));
-        if (rep.anomaly != 0 || rep.n_records == 0) break;
-        expect_len = rep.max_len;
-        fxh_write_raw(wr, ob, (size_t)rep.out_bytes, rep.n_out_records);
-        *count_input += (unsigned int)rep.n_records;
-        for (int k = 0; k < 6; k++) cnt[k] += (unsigned int)rep.clip_class[k];
-        {   /* sequence line of the last consumed record: 2 newlines back from the end of the record */
-            size_t e = (size_t)rep.consumed_bytes - 1;          /* the record's final newline (end of line 4) */
-            int nl = 0;
-            while (e > 0 && nl < 2) { e--; if (p[e] == '\n') nl++; }     /* e = newline ending line 2 (line 3's, then line 2's) */
-            size_t s2 = e;
-            while (s2 > 0 && p[s2 - 1] != '\n') s2--;
-            fxh_reader_seed_shadow(rd, p + s2, rep.max_len);
-        }
-        fxh_reader_consume(rd, (size_t)rep.consumed_bytes, rep.n_records);
-        which ^= 1;
-    }
-    fxh_write_raw(wr, out, 0, 0);
-    fxg_free_pinned(out);
-    fxg_text_free(tx);
+    fxs_job job;
+    memset(&job, 0, sizeof job);
+    job.op = FXS_CLIP; job.a0 = cl_show_adapter_only; job.clip = o;
+    job.ngpu = fxh_gpu_count(); job.first_dev = first_gpu();
+    (void)fxs_run(&job, rd, wr);
+    *count_input += (unsigned int)job.records;
+    for (int k = 0; k < 6; k++) cnt[k] += job.clip_class[k];
 }
 
 static int main_clipper(int argc, char **argv)
@@ -334,7 +271,7 @@ static int main_clipper(int argc, char **argv)
     unsigned int count_input = 0, cnt[6] = { 0, 0, 0, 0, 0, 0 };
     pbuf ol = { 0, 0 }, oc = { 0, 0 };
     fxh_batch *b;
-    clip_text_path(ctx, rd, wr, &o, &count_input, cnt);
+    clip_text_path(rd, wr, &o, &count_input, cnt);
     while ((b = fxh_reader_next(rd, fxh_batch_reads())) != NULL) {
         int32_t *out_len = (int32_t *)pbuf_get(&ol, (size_t)b->n * sizeof(int32_t));
         uint8_t *out_cls = (uint8_t *)pbuf_get(&oc, (size_t)b->n);
@@ -385,67 +322,33 @@ static int main_collapser(int argc, char **argv)
         if (!out) errx(1, "Failed to create output file (%s)", fxh_output_filename());
     }
     fxg_ctx *ctx = fxh_gpu_open();
-    /* the whole input has to be resident before anything can be printed: keep the bases compactly on the host */
-    uint8_t *bases = NULL; size_t bases_len = 0, bases_cap = 0;
-    int32_t *lens = NULL, *weights = NULL; int64_t n = 0, cap = 0;
-    int maxlen = 0;
-    pbuf keep = { 0, 0 };
+    /* the count map lives on the GPU from the first read on (fastx_collapser.cpp:112-114); it grows as the input arrives */
+    fxg_collapser *col = NULL;
+    int rc = fxg_collapse_new(first_gpu(), 1 << 20, 64, &col);
+    if (rc != FXG_OK) errx(1, "fxg_collapse_new failed: %s", fxg_strerror(rc));
+    fxs_job job;
+    memset(&job, 0, sizeof job);
+    job.op = FXS_COLLAPSE; job.ngpu = 1; job.first_dev = first_gpu(); job.collapser = col;
+    (void)fxs_run(&job, rd, NULL);
+    /* whatever the GPU text path handed back: record by record, validated as the reader validates (K-VALIDATE) */
+    int64_t host_rows = 0;
     fxh_batch *b;
     while ((b = fxh_reader_next(rd, fxh_batch_reads())) != NULL) {
-        int64_t lim = b->n;
-        if (fastq) {   /* FASTQ input: the reader also validates the qualities (K-VALIDATE fused in the filter kernel) */
-            fxg_batch gb = fxh_as_fxg_batch(b, 1);
-            fxg_report rep;
-            fxh_gpu_check(ctx, fxg_filter_host(ctx, &gb, batch_q(b), -100, 100, (uint8_t *)pbuf_get(&keep, (size_t)b->n), &rep), "fxg_filter_host");
-            if (rep.first_bad_read >= 0) fxh_die_bad_record(rd, b, rep.first_bad_read);
-        }
-        if (n + lim > cap) {
-            cap = (n + lim) * 2;
-            lens = (int32_t *)realloc(lens, (size_t)cap * sizeof(int32_t));
-            weights = (int32_t *)realloc(weights, (size_t)cap * sizeof(int32_t));
-            if (!lens || !weights) err(1, "out of memory");
-        }
-        for (int64_t i = 0; i < lim; i++) {
-            const int L = b->len[i];
-            if (bases_len + (size_t)L > bases_cap) {
-                bases_cap = (bases_len + (size_t)L) * 2 + (1u << 20);
-                bases = (uint8_t *)realloc(bases, bases_cap);
-                if (!bases) err(1, "out of memory");
-            }
-            memcpy(bases + bases_len, b->seq + (size_t)i * b->stride, (size_t)L);
-            bases_len += (size_t)L;
-            lens[n] = L; weights[n] = b->weight[i];
-            if (L > maxlen) maxlen = L;
-            n++;
-        }
-    }
-    const int stride = (maxlen + 15) & ~15;
-    fxg_collapser *col = NULL;
-    int rc = fxg_collapse_new(getenv("FASTX_GPU") ? atoi(getenv("FASTX_GPU")) : 0, n > 0 ? n : 1, stride > 0 ? stride : 16, &col);
-    if (rc != FXG_OK) errx(1, "fxg_collapse_new failed: %s", fxg_strerror(rc));
-    {   /* re-pack into fixed-stride rows, a pinned chunk at a time */
-        const int64_t chunk = 1 << 20;
-        uint8_t *rows = (uint8_t *)pinned((size_t)chunk * (size_t)(stride > 0 ? stride : 16));
-        size_t off = 0;
-        for (int64_t r0 = 0; r0 < n; r0 += chunk) {
-            const int64_t nr = (n - r0 < chunk) ? (n - r0) : chunk;
-            for (int64_t i = 0; i < nr; i++) { memcpy(rows + (size_t)i * stride, bases + off, (size_t)lens[r0 + i]); off += (size_t)lens[r0 + i]; }
-            fxg_batch gb = { rows, NULL, lens + r0, 0, stride, nr };
-            rc = fxg_collapse_add(col, &gb, weights + r0, NULL, r0);
-            if (rc != FXG_OK) errx(1, "fxg_collapse_add failed: %s (%s)", fxg_strerror(rc), fxg_collapse_error(col));
-        }
-        fxg_free_pinned(rows);
+        fxg_batch gb = fxh_as_fxg_batch(b, fastq);
+        fxg_report rep;
+        fxh_gpu_check(ctx, fxg_validate_host(ctx, &gb, batch_q(b), &rep), "fxg_validate_host");
+        if (rep.first_bad_read >= 0) fxh_die_bad_record(rd, b, rep.first_bad_read);
+        gb.qual = NULL;
+        rc = fxg_collapse_add(col, &gb, b->weight, NULL, ((job.chunks + 1) << 32) + host_rows);
+        if (rc != FXG_OK) errx(1, "fxg_collapse_add failed: %s (%s)", fxg_strerror(rc), fxg_collapse_error(col));
+        host_rows += b->n;
     }
     int64_t U = 0, bad = -1;
     rc = fxg_collapse_finish(col, 1, &U, &bad);
     if (rc != FXG_OK) errx(1, "fxg_collapse_finish failed: %s (%s)", fxg_strerror(rc), fxg_collapse_error(col));
-    if (bad >= 0) {   /* an illegal base: line numbers are implied by the record index (the structure was verified) */
-        size_t off = 0;
-        for (int64_t i = 0; i < bad; i++) off += (size_t)lens[i];
-        errx(1, "found invalid nucleotide sequence (%.*s) on line %lld\n", lens[bad], (const char *)bases + off,
-             (long long)(bad * (fastq ? 4 : 2) + 2));
-    }
-    uint8_t *useq = (uint8_t *)malloc((size_t)(U > 0 ? U : 1) * (size_t)(stride > 0 ? stride : 16));
+    if (bad >= 0) errx(1, "internal error: the count map rejected a read the validation had accepted (index %lld)", (long long)bad);
+    const int32_t stride = fxg_collapse_stride(col);
+    uint8_t *useq = (uint8_t *)malloc((size_t)(U > 0 ? U : 1) * (size_t)stride);
     int32_t *ulen = (int32_t *)malloc((size_t)(U > 0 ? U : 1) * sizeof(int32_t));
     uint64_t *ucnt = (uint64_t *)malloc((size_t)(U > 0 ? U : 1) * sizeof(uint64_t));
     if (!useq || !ulen || !ucnt) err(1, "out of memory");
@@ -568,7 +471,7 @@ static int main_stats(int argc, char **argv)
      * (fxg_comm_allreduce_u64) merges them before printing — the only collective this tool needs. */
     const int ngpu = fxh_gpu_count();
     const int dev0 = getenv("FASTX_GPU") ? atoi(getenv("FASTX_GPU")) : 0;
-    fxg_ctx *ctxs[64]; uint64_t *hists[64]; fxg_text *txs[64]; int devs[64];
+    fxg_ctx *ctxs[64]; uint64_t *hists[64]; int devs[64];
     const int max_cycles = FXH_MAX_LINE;
     const size_t hist_bytes = (size_t)max_cycles * 5 * FXG_QBINS * sizeof(uint64_t);
     for (int g = 0; g < ngpu; g++) {
@@ -578,36 +481,17 @@ static int main_stats(int argc, char **argv)
         if (!hists[g]) errx(1, "cannot allocate the histogram on GPU %d: %s", devs[g], fxg_last_error(ctxs[g]));
         fxh_gpu_check(ctxs[g], fxg_memset_dev(ctxs[g], hists[g], 0, hist_bytes), "fxg_memset_dev");
         fxh_gpu_check(ctxs[g], fxg_sync(ctxs[g]), "fxg_sync");
-        txs[g] = NULL;
     }
     fxg_ctx *ctx = ctxs[0];
     uint64_t *d_hist = hists[0];
     int maxlen = 0, turn = 0;
     fxh_batch *b;
-    if (fastq && fxh_text_path_enabled()) {        /* GPU text path: parse + pack + accumulate on the device */
-        char *p;
-        size_t len = fxh_reader_raw(rd, &p);
-        size_t cap = fxh_text_chunk_bytes();
-        if (fxh_reader_at_eof(rd) && len + 4096 < cap) cap = len + 4096;
-        int ok = len > 0;
-        for (int g = 0; ok && g < ngpu; g++) ok = fxg_text_new(ctxs[g], devs[g], cap, &txs[g]) == FXG_OK;
-        if (ok) {
-            fxh_reader_pin(rd);
-            for (;;) {
-                len = fxh_reader_raw(rd, &p);
-                if (len == 0) break;
-                if (len > cap) len = cap;
-                fxg_text_report rep;
-                const int g = turn % ngpu;
-                int rc = fxg_text_stats_host(txs[g], p, len, fxh_q_offset(), hists[g], max_cycles, &rep);
-                if (rc != FXG_OK) errx(1, "fxg_text_stats_host failed: %s (%s)", fxg_strerror(rc), fxg_text_error(txs[g]));
-                if (rep.anomaly != 0 || rep.n_records == 0) break;   /* numeric qualities / broken input: host parser from here */
-                if (rep.max_len > maxlen) maxlen = rep.max_len;
-                fxh_reader_consume(rd, (size_t)rep.consumed_bytes, rep.n_records);
-                turn++;
-            }
-        }
-        for (int g = 0; g < ngpu; g++) if (txs[g]) fxg_text_free(txs[g]);
+    {   /* GPU text path: parse + pack + accumulate on the devices, chunks to whichever GPU is free */
+        fxs_job job;
+        memset(&job, 0, sizeof job);
+        job.op = FXS_STATS; job.ngpu = ngpu; job.first_dev = dev0; job.hist_dev = hists; job.max_cycles = max_cycles;
+        (void)fxs_run(&job, rd, NULL);
+        if (job.max_len > maxlen) maxlen = job.max_len;
     }
     while ((b = fxh_reader_next(rd, fxh_batch_reads())) != NULL) {
         fxg_batch gb = fxh_as_fxg_batch(b, fastq);

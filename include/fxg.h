@@ -163,6 +163,8 @@ int fxg_hash_dev(fxg_ctx *ctx, const fxg_batch *b, uint64_t *hash_dev);
  * wins).  finish(order=1) computes the reference's output order (count descending, ties in reverse
  * std::unordered_map iteration order); fetch() copies the uniques out in that order. */
 typedef struct fxg_collapser fxg_collapser;
+/* max_reads and stride are starting sizes: add() grows the row store (and its stride, when a batch with longer rows
+ * arrives) and rebuilds the table when it would get more than half full. */
 int         fxg_collapse_new(int device, int64_t max_reads, int32_t stride, fxg_collapser **out);
 void        fxg_collapse_free(fxg_collapser *c);
 int         fxg_collapse_add(fxg_collapser *c, const fxg_batch *b, const int32_t *weight, const int64_t *first, int64_t index_base);
@@ -172,6 +174,7 @@ int         fxg_collapse_fetch(fxg_collapser *c, uint8_t *out_seq, int32_t *out_
                                uint64_t *out_hash);
 const char *fxg_collapse_error(const fxg_collapser *c);
 int64_t     fxg_collapse_launches(const fxg_collapser *c);
+int32_t     fxg_collapse_stride(const fxg_collapser *c);      /* row pitch of fetch()'s out_seq (may have grown)  */
 /* K-ORDER alone: perm_dev[k] = index of the unique printed at rank k, from (hash, first, count) triples that
  * may have been gathered from several GPUs (device pointers on `device`). */
 int         fxg_collapse_order_dev(int device, const uint64_t *hash_dev, const uint64_t *first_dev, const uint64_t *count_dev,
@@ -310,8 +313,9 @@ int fxg_pipeline_dev(fxg_ctx *ctx, const fxg_batch *b, int q_offset, const fxg_s
  * the surviving records as text (fastx.c:440-473) into out_host (capacity >= 1.25 x max_chunk_bytes).
  * fxg_text_stats_host() does the same up to the slabs and accumulates the quality-stats histogram (fxg_stats_accum_*)
  * into hist_dev instead of emitting text.  Anything it cannot reproduce bit-exactly
- * by construction (broken structure, numeric qualities, illegal bytes, over-long lines) is reported as
- * anomaly != 0 with nothing emitted, so the caller can re-read that chunk with the host parser. */
+ * by construction (broken structure, a chunk mixing ASCII and numeric quality lines, malformed numbers, illegal bytes,
+ * over-long lines) is reported as anomaly != 0 with nothing emitted, so the caller can re-read that chunk with the host
+ * parser. */
 typedef struct {
     int64_t n_records;        /* complete records found in the chunk                          */
     int64_t n_out_records;    /* records emitted                                              */
@@ -323,6 +327,8 @@ typedef struct {
     int32_t min_len;          /* shortest read                                                */
     int32_t reserved;
     int64_t clip_class[6];    /* fxg_text_clip_host: reads per FXG_CLIP_* class               */
+    int64_t n_reads;          /* sum of get_reads_count() over the records (FASTA "N-COUNT" ids; = n_records for FASTQ) */
+    int64_t n_out_reads;      /* the same over the emitted records                            */
 } fxg_text_report;
 #define FXG_TEXT_PREFIX     1
 #define FXG_TEXT_EMPTY_SEQ  2
@@ -341,8 +347,21 @@ int         fxg_text_clip_host(fxg_text *t, const char *text_host, size_t bytes,
                                int show_adapter_only, int expect_len, char *out_host, fxg_text_report *rep);
 int         fxg_text_stats_host(fxg_text *t, const char *text_host, size_t bytes, int q_offset, uint64_t *hist_dev,
                                 int32_t max_cycles, fxg_text_report *rep);
+/* Record format of the input text: 0 = 4-line FASTQ (default), 1 = 2-line FASTA (fastx.c:348-352; ops 2 = reverse
+ * complement, clip, stats, collapse; the read weights are get_reads_count() of the identifiers, fastx.c:475-497).
+ * FASTQ chunks whose records all carry NUMERIC quality lines (fastx.c:137-167,382-390) are parsed on the GPU too and
+ * written back in numeric form (fastx.c:421-438); a chunk that mixes the two forms is an anomaly (host parser). */
+int         fxg_text_set_format(fxg_text *t, int fasta);
+/* fastx_collapser: the reads of the chunk (FASTA or FASTQ; FASTQ records are validated as the reader validates them) are
+ * added to `col` (fxg_collapse_new; finish / fetch it when the input is exhausted).  first_base = first-occurrence index
+ * of the chunk's record 0 (any values that grow with the input order, e.g. chunk number << 32, so chunks may be added
+ * in any order); < 0: the number of rows added so far. */
+int         fxg_text_collapse_host(fxg_text *t, const char *text_host, size_t bytes, int q_offset, fxg_collapser *col, int64_t first_base,
+                                   fxg_text_report *rep);
 const char *fxg_text_error(const fxg_text *t);
 int64_t     fxg_text_launches(const fxg_text *t);
+int64_t     fxg_text_numeric_chunks(const fxg_text *t);   /* chunks that went through the numeric-quality form of the path */
+int64_t     fxg_text_fasta_chunks(const fxg_text *t);     /* chunks that went through the FASTA form of the path          */
 
 #ifdef __cplusplus
 }

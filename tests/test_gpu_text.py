@@ -98,7 +98,7 @@ def test_text_path_flags_anomalies(ctx):
         edit(ls)
         return tp.run(0, b"\n".join(ls) + b"\n", 33, 20, 20)[1]
 
-    rep = run(lambda ls: ls.__setitem__(4 * 1234 + 3, b"40 " * 59 + b"40"))        # numeric quality line
+    rep = run(lambda ls: ls.__setitem__(4 * 1234 + 3, b"40 " * 59 + b"40"))        # ONE numeric quality line in an ASCII chunk
     assert (rep.anomaly, rep.anomaly_record) == (3, 1234)
     rep = run(lambda ls: ls.__setitem__(4 * 77, b"r77"))                             # no '@'
     assert (rep.anomaly, rep.anomaly_record) == (1, 77)
@@ -156,3 +156,150 @@ def test_text_path_clipper(ctx):
     rep = tp.clip(fastq_bytes(s2, qual, None, L), 33, o, 0, 0)[1]
     assert (rep.anomaly, rep.anomaly_record) == (5, 321)
     tp.close()
+
+
+def numeric_fastq(seq, qual, lens, L, q_offset=33, style=0):
+    """4-line records with NUMERIC quality lines (fastx.c:137-167): style 1 writes signs / leading zeros / tabs the way strtol
+    accepts them; the reference prints plain %d back"""
+    out = []
+    for i in range(seq.shape[0]):
+        l = int(lens[i]) if lens is not None else L
+        vals = [int(v) - q_offset for v in qual[i, :l]]
+        if style == 0:
+            ql = b" ".join(b"%d" % v for v in vals)
+        else:
+            ql = b"".join((b" " if k else b"") + (b"\t" if k % 7 == 3 else b"") + (b"+%d" % v if (v >= 0 and k % 5 == 0) else b"%03d" % v if (v >= 0 and k % 11 == 1) else b"%d" % v)
+                          for k, v in enumerate(vals))
+        out.append(b"@n%d\n" % i + seq[i, :l].tobytes() + b"\n+n%d\n" % i + ql + b"\n")
+    return b"".join(out)
+
+
+def test_text_path_numeric_qualities(ctx):
+    """records with numeric quality lines are parsed (K-NUMQ), processed and written back in numeric form on the GPU"""
+    import tempfile, os
+    import fastx_toolkit_b200 as F
+    n, L = 12000, 60
+    seq, qual = H.synth_slab(H.SEED_BASE + 15, n, L, H.WITH_N)
+    rng = np.random.default_rng(8)
+    qual[:, :L] = (rng.integers(-15, 94, size=(n, L)) + 33).astype(np.uint8)          # the whole legal range, negatives included
+    lens = H.ragged(seq, qual, rng, min_len=2)
+    lens[lens == 1] = 2
+    for style in (0, 1):
+        text = numeric_fastq(seq, qual, lens, L, 33, style)
+        p = tempfile.mktemp(suffix=".fq")
+        open(p, "wb").write(text)
+        recs = H.read_fastx(p)
+        os.unlink(p)
+        tp = F.TextPipe(ctx, len(text) + 4096)
+        for op, a0, a1 in ((0, 20, 10), (1, 10, 60), (0, -5, 3)):
+            got, rep = tp.run(op, text, 64, a0, a1)           # -Q is irrelevant for numeric records
+            if op == 0:
+                out, bad = H.o_trim(seq, qual, lens, 0, seq.shape[1], 33, a0, a1)
+            else:
+                keep, bad = H.o_filter(seq, qual, lens, 0, seq.shape[1], 33, a0, a1)
+                out = np.where(keep != 0, lens, -1)
+            exp = emit(recs, out, 33)
+            assert rep.anomaly == 0 and rep.n_records == n and bad == -1
+            assert rep.n_out_records == int((out >= 0).sum()) and got == exp, (style, op)
+        got, rep = tp.run(2, text, 33, 0, 0)
+        eseq, equal = H.o_revcomp(seq, qual, lens, 0, seq.shape[1])
+        exp = numeric_fastq(eseq, equal, lens, L, 33, 0)
+        assert rep.anomaly == 0 and got == exp
+        assert tp.numeric_chunks() == 4 and tp.fasta_chunks() == 0
+        tp.close()
+    # malformed numbers, a value out of range, a missing value, trailing blank: the host parser words the message
+    lines = numeric_fastq(seq[:3000], qual[:3000], lens[:3000], L).split(b"\n")[:-1]
+    tp = F.TextPipe(ctx, 4 << 20)
+    nb = int(lens[1500])
+    for bad_line in (b"40 40 x 40", b" ".join([b"40"] * (nb - 1) + [b"94"]), b" ".join([b"40"] * (nb - 1) + [b"-16"]), b" ".join([b"40"] * (nb - 1)),
+                     b" ".join([b"40"] * nb) + b" ", b" ".join([b"40"] * (nb + 1))):
+        if len(bad_line) == nb:
+            continue                      # same length as the sequence: an ASCII quality line by the reader's rule
+        ls = list(lines)
+        ls[4 * 1500 + 3] = bad_line
+        rep = tp.run(0, b"\n".join(ls) + b"\n", 33, 20, 20)[1]
+        assert rep.anomaly != 0 and rep.anomaly_record == 1500, bad_line
+    tp.close()
+
+
+def fasta_bytes(seq, lens, L, names=None):
+    return b"".join(b">" + (names[i] if names else b"s%d" % i) + b"\n" + seq[i, :(int(lens[i]) if lens is not None else L)].tobytes() + b"\n"
+                    for i in range(seq.shape[0]))
+
+
+def test_text_path_fasta_and_collapser(ctx):
+    """2-line FASTA records on the GPU text path: reverse complement, quality stats (weights from "N-COUNT" identifiers) and the
+    collapser fed straight from text (FASTA and FASTQ)"""
+    import fastx_toolkit_b200 as F
+    n, L = 30000, 50
+    seq, qual = H.synth_slab(H.SEED_BASE + 4, n, L, H.DUPS)
+    rng = np.random.default_rng(3)
+    lens = H.ragged(seq, qual, rng, min_len=1)
+    names = [b"%d-%d" % (i, rng.integers(1, 40)) if i % 3 else b"plain%d" % i for i in range(n)]
+    weights = np.array([int(nm.split(b"-")[1]) if b"-" in nm else 1 for nm in names], np.int32)
+    text = fasta_bytes(seq, lens, L, names)
+    tp = F.TextPipe(ctx, len(text) + 4096)
+    tp.set_format(True)
+    got, rep = tp.run(2, text, 33, 0, 0)
+    eseq, _ = H.o_revcomp(seq, qual, lens, 0, seq.shape[1])
+    assert rep.anomaly == 0 and rep.n_records == n and rep.n_reads == int(weights.sum()) == rep.n_out_reads
+    assert got == fasta_bytes(eseq, lens, L, names)
+    # quality stats of FASTA: only counts, weighted by the collapsed-read counts
+    hist = torch.zeros((L, 5, 109), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    rep = tp.stats(text, 33, hist, L)
+    assert rep.anomaly == 0
+    exp = np.zeros((L, 5), np.int64)
+    code = {ord("A"): 0, ord("C"): 1, ord("G"): 2, ord("T"): 3, ord("N"): 4}
+    for i in range(n):
+        for c in range(int(lens[i])):
+            exp[c, code[int(seq[i, c])]] += int(weights[i])
+    assert np.array_equal(hist.sum(dim=2).cpu().numpy(), exp)
+    # the collapser: counts are the identifiers' read counts; order is the reference's
+    col = F.Collapser(0, n, seq.shape[1])
+    half = text[: text.index(b">", len(text) // 2)]
+    r1 = tp.collapse(half, 33, col)
+    r2 = tp.collapse(text[len(half):], 33, col)
+    assert r1.anomaly == 0 and r2.anomaly == 0 and r1.n_records + r2.n_records == n
+    u = col.finish(True)
+    oseq, olen, ocnt, ofirst = np.zeros((u, seq.shape[1]), np.uint8), np.zeros(u, np.int32), np.zeros(u, np.uint64), np.zeros(u, np.int64)
+    col.fetch(oseq, olen, ocnt, ofirst, None)
+    col.close()
+    O = H.oracle()
+    oc = O.fxo_collapser_new()
+    import ctypes as C
+    for i in range(n):
+        row = np.ascontiguousarray(seq[i])
+        O.fxo_collapser_add(oc, H._p(row, H.u8p), int(lens[i]), int(weights[i]))
+    eu = O.fxo_collapser_unique(oc)
+    efirst, ecnt = np.empty(eu, np.int64), np.empty(eu, np.uint64)
+    O.fxo_collapser_order(oc, H._p(efirst, H.i64p), H._p(ecnt, H.u64p))
+    O.fxo_collapser_free(oc)
+    assert u == eu and np.array_equal(ocnt, ecnt) and np.array_equal(ofirst, efirst)
+    assert all(oseq[k, :olen[k]].tobytes() == seq[efirst[k], :lens[efirst[k]]].tobytes() for k in (0, 1, u // 2, u - 1))
+    assert tp.fasta_chunks() == 4
+    # a FASTA chunk with a problem is handed back
+    bad = text.replace(b">plain0\n", b"plain0\n", 1)
+    assert tp.run(2, bad, 33, 0, 0)[1].anomaly == 1
+    s2 = seq.copy(); s2[777, 0] = ord("x")
+    col = F.Collapser(0, n, seq.shape[1])
+    rep = tp.collapse(fasta_bytes(s2, lens, L, names), 33, col)
+    assert (rep.anomaly, rep.anomaly_record) == (5, 777)
+    col.close()
+    tp.close()
+    # FASTQ into the collapser: qualities are validated as the reader validates them
+    fq = fastq_bytes(seq, qual, lens, L)
+    tq = F.TextPipe(ctx, len(fq) + 4096)
+    col = F.Collapser(0, n, seq.shape[1])
+    assert tq.collapse(fq, 33, col).anomaly == 0
+    u2 = col.finish(True)
+    efirst2, ecnt2 = H.o_collapse(seq, lens, 0, seq.shape[1])
+    c2, f2 = np.zeros(u2, np.uint64), np.zeros(u2, np.int64)
+    col.fetch(None, None, c2, f2, None)
+    assert u2 == len(ecnt2) and np.array_equal(c2, ecnt2) and np.array_equal(f2, efirst2)
+    col.close()
+    q2 = qual.copy(); q2[4321, 0] = 7
+    col = F.Collapser(0, n, seq.shape[1])
+    rep = tq.collapse(fastq_bytes(seq, q2, lens, L), 33, col)
+    assert (rep.anomaly, rep.anomaly_record) == (5, 4321)
+    col.close(); tq.close()
