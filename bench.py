@@ -305,6 +305,42 @@ def leg_collapse(args, ctx, comm, stream, rank, world, barrier, max_over_ranks, 
             "timing": "CUDA events on the communicator's (= launch) stream around K blocking fxg_dcollapse_run calls, max over ranks"}
 
 
+def file_to_file(args, chunk, chunk_reads, world):
+    """bin/fastq_quality_trimmer -t 20 -l 20 -Q33 file -> file on tmpfs (the input is page-cache resident by construction): the
+    whole tool, process start and CUDA context creation included, with 1 GPU and with all `world` GPUs (FASTX_GPUS)."""
+    tool = os.path.join(ROOT, "bin", "fastq_quality_trimmer")
+    d = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
+    tmp = tempfile.mkdtemp(prefix="fxg_f2f_", dir=d)
+    try:
+        reps = max(1, args.f2f_reads // chunk_reads)
+        fin, fout = os.path.join(tmp, "in.fq"), os.path.join(tmp, "out.fq")
+        with open(fin, "wb") as f:
+            for _ in range(reps):
+                f.write(chunk)
+        res = {"reads": reps * chunk_reads, "input_bytes": reps * len(chunk), "filesystem": d,
+               "command": "bin/fastq_quality_trimmer -Q33 -t 20 -l 20 -i in.fq -o out.fq (wall clock of the whole process)"}
+        ref_out = None
+        for g in sorted({1, world}):
+            best = None
+            for _ in range(2):
+                env = dict(os.environ, FASTX_GPUS=str(g), FASTX_GPU="0")
+                t0 = time.perf_counter()
+                r = subprocess.run([tool, "-Q", str(Q), "-t", str(T), "-l", str(MINLEN), "-i", fin, "-o", fout], env=env, stderr=subprocess.PIPE)
+                dt = time.perf_counter() - t0
+                if r.returncode != 0:
+                    raise RuntimeError("file->file run failed: %s" % r.stderr.decode()[-300:])
+                best = dt if best is None else min(best, dt)
+            size = os.path.getsize(fout)
+            if ref_out is None:
+                ref_out = size
+            assert size == ref_out, "the output size changes with the number of GPUs"
+            res["gpus_%d" % g] = {"seconds": best, "value": reps * chunk_reads / best / 1e6, "unit": UNIT, "output_bytes": size}
+        # the first chunk's worth of output must be the bytes the library path produced for that chunk
+        return res
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -320,8 +356,13 @@ def main():
     ap.add_argument("--collapse-reads", type=int, default=25_000_000, help="reads per GPU in the collapser leg (config (e): 200 M / 8)")
     ap.add_argument("--parity-reads", type=int, default=100_000, help="reads per GPU in the oracle parity checks (outside every timed region)")
     ap.add_argument("--no-legs", action="store_true", help="skip the quality_stats / collapser legs")
+    ap.add_argument("--no-f2f", action="store_true", help="skip the file -> file run of the drop-in binary")
+    ap.add_argument("--e2e-only", action="store_true", help="diagnostics: small HBM batch, no legs, no file -> file, no CPU baseline — just the e2e numbers")
+    ap.add_argument("--f2f-reads", type=int, default=10_000_000, help="reads in the file -> file input (tmpfs)")
     args = ap.parse_args()
 
+    if args.e2e_only:
+        args.reads = min(args.reads, 2_000_000); args.no_legs = True; args.no_f2f = True; args.no_cpu_baseline = True
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -461,35 +502,46 @@ def main():
     import threading
     import numpy as np
     chunk_reads = int(os.environ.get("FXG_BENCH_CHUNK_READS", "250000"))     # tuning knobs for the e2e leg only
+    NROT = int(os.environ.get("FXG_BENCH_ROTATE", "4"))                       # distinct input chunks per rank, sent in rotation
     exe = os.path.join(ROOT, "bin", "fxg_synth")
     if not os.path.exists(exe):
         subprocess.check_call(["make", "-C", ROOT, "tools"], stdout=subprocess.DEVNULL)
-    chunk = subprocess.run([exe, "-n", str(chunk_reads), "-l", str(L), "-s", str(SEED), "-f", str(rank * chunk_reads)],
-                           stdout=subprocess.PIPE, check=True).stdout
-    cb = len(chunk)
+    chunks, host_ins = [], []
+    for j in range(NROT):
+        cj = subprocess.run([exe, "-n", str(chunk_reads), "-l", str(L), "-s", str(SEED), "-f", str((rank * NROT + j) * chunk_reads)],
+                            stdout=subprocess.PIPE, check=True).stdout
+        hj = torch.empty(len(cj), dtype=torch.uint8).pin_memory()
+        hj.numpy()[:] = np.frombuffer(cj, np.uint8)
+        chunks.append(cj); host_ins.append(hj)
+    chunk = chunks[0]
+    cb = max(len(c) for c in chunks)
     nchunks = max(1, args.e2e_reads // chunk_reads)
-    host_in = torch.empty(cb, dtype=torch.uint8).pin_memory()
-    host_in.numpy()[:] = np.frombuffer(chunk, np.uint8)
     W = int(os.environ.get("FXG_BENCH_WORKERS", "3"))
     workers = []
     for _ in range(W):
         wctx = F.Context(local_rank)
         workers.append((wctx, F.TextPipe(wctx, cb + 4096), torch.empty(cb + cb // 4 + 64, dtype=torch.uint8).pin_memory()))
     Lib = F.lib()
-    stat = {"out_bytes": 0, "launches": 0}
+    stat = {"in_bytes": 0, "out_bytes": 0}
+    stat_lock = threading.Lock()
 
-    def text_worker(w, count):
+    def text_worker(w, first_chunk, count):
         wctx, tp, wout = workers[w]
         rep = F.TextReport()
-        for _ in range(count):
-            rc = Lib.fxg_text_run_host(tp.h, 0, host_in.data_ptr(), cb, Q, T, MINLEN, wout.data_ptr(), C.byref(rep))
+        ib = ob = 0
+        for k in range(count):
+            hin = host_ins[(first_chunk + k) % NROT]
+            rc = Lib.fxg_text_run_host(tp.h, 0, hin.data_ptr(), hin.numel(), Q, T, MINLEN, wout.data_ptr(), C.byref(rep))
             if rc != 0 or rep.anomaly != 0 or rep.n_records != chunk_reads:
                 raise RuntimeError("text path failed: rc=%d anomaly=%d" % (rc, rep.anomaly))
-        stat["out_bytes"] = int(rep.out_bytes)
+            ib += hin.numel(); ob += int(rep.out_bytes)
+        with stat_lock:
+            stat["in_bytes"] += ib; stat["out_bytes"] += ob
 
     def text_pass():
         per = [nchunks // W + (1 if w < nchunks % W else 0) for w in range(W)]
-        th = [threading.Thread(target=text_worker, args=(w, per[w])) for w in range(W)]
+        starts = [sum(per[:w]) for w in range(W)]
+        th = [threading.Thread(target=text_worker, args=(w, starts[w], per[w])) for w in range(W)]
         [t.start() for t in th]
         [t.join() for t in th]
 
@@ -499,15 +551,21 @@ def main():
     first = out[: chunk_reads].cpu().numpy() if rank == 0 else None
     barrier()
     l0 = sum(int(Lib.fxg_text_launches(w[1].h)) + w[0].launches() for w in workers)
+    stat["in_bytes"] = stat["out_bytes"] = 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
         text_pass()
     torch.cuda.synchronize()
-    dt = max_over_ranks(time.perf_counter() - t0)
+    dt_local = time.perf_counter() - t0
+    dt = max_over_ranks(dt_local)
     launches_e2e = sum(int(Lib.fxg_text_launches(w[1].h)) + w[0].launches() for w in workers) - l0
     e2e_value = world * nchunks * chunk_reads * args.steps / dt / 1e6
+    e2e_h2d_step, e2e_d2h_step = stat["in_bytes"] // args.steps, stat["out_bytes"] // args.steps
+    pcie = {"h2d_GBps_this_gpu": stat["in_bytes"] / dt_local / 1e9, "d2h_GBps_this_gpu": stat["out_bytes"] / dt_local / 1e9}
     if rank == 0:
-        got = workers[0][2].numpy()[: stat["out_bytes"]].tobytes().split(b"\n")
+        rep0 = F.TextReport()
+        Lib.fxg_text_run_host(workers[0][1].h, 0, host_ins[0].data_ptr(), host_ins[0].numel(), Q, T, MINLEN, workers[0][2].data_ptr(), C.byref(rep0))
+        got = workers[0][2].numpy()[: int(rep0.out_bytes)].tobytes().split(b"\n")
         src = chunk.split(b"\n")
         k = 0
         for i in range(chunk_reads):
@@ -515,6 +573,19 @@ def main():
                 assert got[4 * k] == src[4 * i] and got[4 * k + 1] == src[4 * i + 1][: first[i]] and got[4 * k + 3] == src[4 * i + 3][: first[i]], "text path output differs"
                 k += 1
         assert len(got) == 4 * k + 1
+    for w in workers:
+        w[1].close(); w[0].close()
+    del workers, host_ins
+
+    # ---------------- file -> file: the drop-in binary itself (BASELINE.md regime iii) on a page-cache-resident file ----------------
+    f2f = None
+    if not args.no_f2f:
+        del dseq, dqual, out, batch
+        torch.cuda.empty_cache()
+        barrier()
+        if rank == 0:
+            f2f = file_to_file(args, chunk, chunk_reads, world)
+        barrier()
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -532,7 +603,9 @@ def main():
                      "traffic": n * NCU_TRAFFIC_BYTES_PER_READ, "traffic_source": "ncu --set full capture of the same kernel (profiles/r01_ncu_trim_full.txt), bytes/read x reads per launch",
                      "kernel": "fxg::k_scan_w<G=1,TRIM,HAS_SEQ> (warp-private TMA ring, lane per read)", "algorithmic_bytes_per_read": ALGO_BYTES_PER_READ,
                      "kernel_ms": kernel_ms, "peak_source": peak_src},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * nchunks * cb, "d2h_bytes_per_step": world * nchunks * stat["out_bytes"],
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * e2e_h2d_step, "d2h_bytes_per_step": world * e2e_d2h_step,
+                "pcie_rank0": pcie, "input_rotation": "%d distinct chunks of %d reads per GPU (%.0f MB, larger than the host L3) sent in rotation" % (NROT, chunk_reads, NROT * cb / 1e6),
+                "file_to_file": f2f,
                 "reads_per_step_per_gpu": nchunks * chunk_reads,
                 "api": "fxg_text_run_host: FASTQ text in pinned host memory -> H2D -> parse/pack/K-TRIM/emit on the GPU -> D2H -> trimmed FASTQ text "
                        "in host memory; %d worker threads per GPU, chunks of %d reads" % (W, chunk_reads),

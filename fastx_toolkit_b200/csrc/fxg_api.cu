@@ -690,6 +690,25 @@ static int extra_enqueue(fxg_ctx *ctx, int op, const fxg_batch *b, int q_offset,
                          uint8_t *flags, int64_t index_base, cudaStream_t st)
 {
     if (b->n == 0) return FXG_OK;
+    if (b->qual && (op == 0 || op == 2 || op == 3) && !getenv("FXG_EXTRA_PLAIN")) {
+        // FASTQ batches of short reads: the same warp-private TMA tile ring as K-TRIM (fxg_kernels.cu k_scan_w), with the op's
+        // per-word work in place of the quality compare
+        TilePlan plan;
+        int rc = make_plan(ctx, b, 2, 0, &plan);
+        if (rc) return rc;
+        if (plan.warp_ring) {
+            ScanParams p;
+            memset(&p, 0, sizeof(p));
+            p.seq = b->seq; p.qual = b->qual; p.len = b->len; p.uniform_len = b->uniform_len; p.stride = b->stride; p.n = b->n;
+            p.tile_reads = plan.tile_reads; p.stages = plan.stages; p.rot_shift = plan.rot_shift;
+            p.qk = make_qualk(q_offset, 0);
+            p.out = flags; p.index_base = index_base; p.counters = ctx->d_counters;
+            CK(ctx, launch_scan(op == 0 ? MODE_VALIDATE : op == 3 ? MODE_HASN : MODE_ARTIFACT, true, plan, p, st));
+            ctx->launches++;
+            ctx->report.n_in += b->n;
+            return FXG_OK;
+        }
+    }
     CK(ctx, launch_extra(op, b->seq, b->qual, b->len, b->uniform_len, b->stride, b->n, q_offset, thr_q, mask_char, out_seq, flags,
                          index_base, ctx->d_counters, ctx->sm_count, st));
     ctx->launches += (op == 1 || op == 3) ? 2 : 1;

@@ -168,10 +168,18 @@ __global__ void __launch_bounds__(256) k_compact(const unsigned long long *slots
                                                  unsigned long long *n_out, uint32_t *u_rep, uint64_t *u_hash,
                                                  uint64_t *u_first, uint64_t *u_count)
 {
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nslots; t += (int64_t)gridDim.x * blockDim.x) {
-        const unsigned long long cur = slots[t];
+    // one position counter for the whole table: a warp takes its block of positions with ONE atomic (ballot + popc)
+    const int lane = threadIdx.x & 31;
+    for (int64_t t0 = (int64_t)blockIdx.x * blockDim.x; t0 < nslots; t0 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t t = t0 + threadIdx.x;
+        const unsigned long long cur = t < nslots ? slots[t] : 0ull;
+        const unsigned occ = __ballot_sync(0xffffffffu, cur != 0ull);
+        if (occ == 0u) continue;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(n_out, (unsigned long long)__popc(occ));
+        base = __shfl_sync(0xffffffffu, base, 0);
         if (cur == 0ull) continue;
-        const unsigned long long pos = atomicAdd(n_out, 1ull);
+        const unsigned long long pos = base + (unsigned long long)__popc(occ & ((1u << lane) - 1u));
         const uint32_t rep = (uint32_t)(cur & 0xFFFFFFFFull) - 1u;
         u_rep[pos] = rep;
         u_hash[pos] = hash[rep];
@@ -362,6 +370,8 @@ struct fxg_collapser {
     uint32_t *u_rep, *perm;
     uint64_t *u_hash, *u_first, *u_count;
     int64_t launches;
+    uint64_t max_first;           // upper bound of every first-occurrence index seen (0 = unknown: explicit `first` arrays)
+    int first_unknown;
     char err[256];
 };
 
@@ -462,6 +472,8 @@ extern "C" int fxg_collapse_add(fxg_collapser *c, const fxg_batch *b, const int3
     if (b->n == 0) return FXG_OK;
     CKO(c, cudaSetDevice(c->device));
     { int rc = collapse_reserve(c, c->rows + b->n, b->stride); if (rc) return rc; }
+    if (first || index_base < 0) c->first_unknown = 1;
+    else if ((uint64_t)(index_base + b->n) > c->max_first) c->max_first = (uint64_t)(index_base + b->n);
     const int64_t row0 = c->rows;
     const size_t S = (size_t)c->stride;
     if (b->stride != c->stride) {
@@ -560,7 +572,7 @@ extern "C" int fxg_collapse_finish(fxg_collapser *c, int order, int64_t *n_uniqu
     if (n_unique) *n_unique = c->U;
     if (order && U > 0) {
         CKO(c, cudaMalloc(&c->perm, (size_t)U * 4));
-        int rc = fxg_order_impl(c->u_hash, c->u_first, c->u_count, (uint32_t)U, c->perm, 0, c->st, c->err, sizeof(c->err), &c->launches);
+        int rc = fxg_order_impl(c->u_hash, c->u_first, c->u_count, (uint32_t)U, c->perm, c->first_unknown ? 0 : c->max_first, c->st, c->err, sizeof(c->err), &c->launches);
         if (rc) return rc;
     }
     return FXG_OK;

@@ -333,8 +333,8 @@ extern "C" int fxg_dcollapse_run(fxg_dcollapse *d, const fxg_batch *batches, con
         CKD(d, ensure(&l->u_first, (size_t)ucap * 8)); CKD(d, ensure(&l->u_count, (size_t)ucap * 8));
         CKD(d, cudaMemsetAsync(l->slots.p, 0, ns * 8, st)); CKD(d, cudaMemsetAsync(l->count.p, 0, ns * 8, st));
         CKD(d, cudaMemsetAsync(l->firsts.p, 0xFF, ns * 8, st));
-        unsigned long long *cnt = (unsigned long long *)l->small.p;      // [0] = uniques, [1] = first bad read (CNT_FIRST_BAD)
-        const unsigned long long init[2] = { 0ull, ~0ull };
+        unsigned long long *cnt = (unsigned long long *)l->small.p;      // [0] = uniques, [1] = first bad read (CNT_FIRST_BAD), [2] = bound of the first indices put in here
+        const unsigned long long init[3] = { 0ull, ~0ull, (unsigned long long)(index_base[i] + batches[i].n) };
         CKD(d, cudaMemcpyAsync(cnt, init, sizeof init, cudaMemcpyHostToDevice, st));
         if (l->m > 0) {
             DedupParams p;
@@ -353,19 +353,20 @@ extern "C" int fxg_dcollapse_run(fxg_dcollapse *d, const fxg_batch *batches, con
     {
         const void *snd[DC_MAX_RANKS]; void *rcv[DC_MAX_RANKS];
         for (int i = 0; i < NL; i++) { snd[i] = d->loc[i].small.p; rcv[i] = (unsigned long long *)d->loc[i].small.p + (G + 2); }
-        CKR(d, fxg_comm_allgather(c, snd, rcv, sizeof(unsigned long long) * 2));
+        CKR(d, fxg_comm_allgather(c, snd, rcv, sizeof(unsigned long long) * 3));
         for (int i = 0; i < NL; i++) {
             CKD(d, cudaSetDevice(d->loc[i].device));
-            CKD(d, cudaMemcpyAsync(d->loc[i].h_small, rcv[i], sizeof(unsigned long long) * 2 * (size_t)G, cudaMemcpyDeviceToHost, c->streams[i]));
+            CKD(d, cudaMemcpyAsync(d->loc[i].h_small, rcv[i], sizeof(unsigned long long) * 3 * (size_t)G, cudaMemcpyDeviceToHost, c->streams[i]));
         }
         CKR(d, fxg_comm_sync(c));
     }
     int64_t ucnt[DC_MAX_RANKS];
-    unsigned long long first_bad = ~0ull;
+    unsigned long long first_bad = ~0ull, max_first = 0;
     d->u_off[0] = 0;
     for (int s = 0; s < G; s++) {
-        ucnt[s] = (int64_t)d->loc[0].h_small[2 * s];
-        if (d->loc[0].h_small[2 * s + 1] < first_bad) first_bad = d->loc[0].h_small[2 * s + 1];
+        ucnt[s] = (int64_t)d->loc[0].h_small[3 * s];
+        if (d->loc[0].h_small[3 * s + 1] < first_bad) first_bad = d->loc[0].h_small[3 * s + 1];
+        if (d->loc[0].h_small[3 * s + 2] > max_first) max_first = d->loc[0].h_small[3 * s + 2];
         d->u_off[s + 1] = d->u_off[s] + ucnt[s];
     }
     d->U_total = d->u_off[G];
@@ -390,9 +391,9 @@ extern "C" int fxg_dcollapse_run(fxg_dcollapse *d, const fxg_batch *batches, con
     if (d->root_local >= 0 && d->U_total > 0) {
         Local *l = &d->loc[d->root_local];
         CKD(d, cudaSetDevice(l->device));
-        // first indices are < the largest index_base + n of the job; the callers' bases are arbitrary, so bound them by value
+        // every first index is below the largest index_base + n of the job: that bound sizes the radix passes of the first sort
         int rc = fxg_order_impl((const uint64_t *)d->g_hash.p, (const uint64_t *)d->g_first.p, (const uint64_t *)d->g_count.p, (uint32_t)d->U_total,
-                                (uint32_t *)d->g_perm.p, 0, c->streams[d->root_local], d->err, sizeof d->err, &d->launches);
+                                (uint32_t *)d->g_perm.p, (uint64_t)max_first, c->streams[d->root_local], d->err, sizeof d->err, &d->launches);
         if (rc) return rc;
     }
     for (int i = 0; i < NL; i++) { CKD(d, cudaSetDevice(d->loc[i].device)); CKD(d, cudaEventRecord(d->loc[i].ev[5], c->streams[i])); }

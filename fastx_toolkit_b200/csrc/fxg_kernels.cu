@@ -52,7 +52,34 @@ struct ScanAcc {
     int      lastc;    // trim: last 16-byte chunk holding a byte with q >= t
     uint32_t lowb;     // filter: per-byte-lane counters of bytes with q < min_q
     uint32_t low;      // filter: flushed total
+    uint32_t hasn;     // has-N: bit7 flags of 'N' bytes
+    uint32_t ba, bc, bg, bt;   // artifacts: per-byte-lane counters of A / C / G / T
+    uint32_t ca, cc, cg, ct;   // artifacts: flushed totals
 };
+
+// per-word work of the sequence-only modes (the (f-2)/(f-4) loop bodies on the same tile ring):
+//   MODE_HASN      strchr(nucleotides, 'N')                      src/fastq_to_fasta/fastq_to_fasta.c:79-82
+//   MODE_ARTIFACT  per-read counts of A, C, G, T                 src/fastx_artifacts_filter/fastx_artifacts_filter.c:56-114
+template <int MODE>
+__device__ __forceinline__ void scan_seq_word(ScanAcc &a, uint32_t x, uint32_t m)
+{
+    if (MODE == MODE_HASN) {                      // zero byte of (x ^ "NNNN"), exact for any byte value
+        const uint32_t z = x ^ 0x4E4E4E4Eu;
+        a.hasn |= ~(((z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | z) & HI & m;
+    }
+    if (MODE == MODE_ARTIFACT) {                  // legal bases are < 128: (x ^ pat) + 0x7F.. has bit7 set iff the byte differs
+        const uint32_t mh = m & HI;
+        a.ba += (~((x ^ 0x41414141u) + 0x7F7F7F7Fu) & mh) >> 7;
+        a.bc += (~((x ^ 0x43434343u) + 0x7F7F7F7Fu) & mh) >> 7;
+        a.bg += (~((x ^ 0x47474747u) + 0x7F7F7F7Fu) & mh) >> 7;
+        a.bt += (~((x ^ 0x54545454u) + 0x7F7F7F7Fu) & mh) >> 7;
+    }
+}
+__device__ __forceinline__ void scan_flush_counts(ScanAcc &a)
+{
+    a.ca += __dp4a(a.ba, ONES, 0u); a.cc += __dp4a(a.bc, ONES, 0u); a.cg += __dp4a(a.bg, ONES, 0u); a.ct += __dp4a(a.bt, ONES, 0u);
+    a.ba = a.bc = a.bg = a.bt = 0;
+}
 
 template <int MODE, bool HAS_SEQ>
 __device__ __forceinline__ void scan_chunk(ScanAcc &a, const uint4 &q, const uint4 &s, const QualK &k, int c)
@@ -63,14 +90,20 @@ __device__ __forceinline__ void scan_chunk(ScanAcc &a, const uint4 &q, const uin
     for (int w = 0; w < 4; w++) {
         const uint32_t x = qw[w], xh = x | HI;
         a.badq |= qual_bad_bits(x, xh, k);
-        const uint32_t ge = qual_ge_bits(xh, k);
-        if (MODE == MODE_TRIM) anyge |= ge;
-        else a.lowb += (~(ge >> 7)) & ONES;
+        if (MODE == MODE_TRIM || MODE == MODE_FILTER) {
+            const uint32_t ge = qual_ge_bits(xh, k);
+            if (MODE == MODE_TRIM) anyge |= ge;
+            else a.lowb += (~(ge >> 7)) & ONES;
+        }
     }
     if (MODE == MODE_TRIM) { if (anyge & HI) a.lastc = max(a.lastc, c); }
     if (HAS_SEQ) {
         a.bads |= seq_bad_bits(s.x) | seq_bad_bits(s.y);
         a.bads |= seq_bad_bits(s.z) | seq_bad_bits(s.w);
+        if (MODE == MODE_HASN || MODE == MODE_ARTIFACT) {
+            scan_seq_word<MODE>(a, s.x, 0xFFFFFFFFu); scan_seq_word<MODE>(a, s.y, 0xFFFFFFFFu);
+            scan_seq_word<MODE>(a, s.z, 0xFFFFFFFFu); scan_seq_word<MODE>(a, s.w, 0xFFFFFFFFu);
+        }
     }
 }
 
@@ -86,10 +119,15 @@ __device__ __forceinline__ void scan_tail(ScanAcc &a, const uint4 &q, const uint
         const uint32_t m = head_mask(rem - 4 * w);
         const uint32_t x = qw[w], xh = x | HI;
         a.badq |= qual_bad_bits(x, xh, k) & m;
-        const uint32_t ge = qual_ge_bits(xh, k);
-        if (MODE == MODE_TRIM) anyge |= ge & m;
-        else a.lowb += (~(ge >> 7)) & ONES & m;
-        if (HAS_SEQ) a.bads |= seq_bad_bits(sw[w]) & m;
+        if (MODE == MODE_TRIM || MODE == MODE_FILTER) {
+            const uint32_t ge = qual_ge_bits(xh, k);
+            if (MODE == MODE_TRIM) anyge |= ge & m;
+            else a.lowb += (~(ge >> 7)) & ONES & m;
+        }
+        if (HAS_SEQ) {
+            a.bads |= seq_bad_bits(sw[w]) & m;
+            if (MODE == MODE_HASN || MODE == MODE_ARTIFACT) scan_seq_word<MODE>(a, sw[w], m);
+        }
     }
     if (MODE == MODE_TRIM) { if (anyge & HI) a.lastc = max(a.lastc, c); }
 }
@@ -120,6 +158,7 @@ __device__ __forceinline__ void scan_read(ScanAcc &a, const uint8_t *qrow, const
                     a.lowb = 0; since_flush = 0;
                 }
             }
+            if (MODE == MODE_ARTIFACT) { if (++since_flush == 32) { scan_flush_counts(a); since_flush = 0; } }
         }
     } else {
 #pragma unroll 2
@@ -134,6 +173,7 @@ __device__ __forceinline__ void scan_read(ScanAcc &a, const uint8_t *qrow, const
                     a.lowb = 0; since_flush = 0;
                 }
             }
+            if (MODE == MODE_ARTIFACT) { if (++since_flush == 32) { scan_flush_counts(a); since_flush = 0; } }
         }
     }
     if (rem && (nfull & (G - 1)) == j) {
@@ -143,6 +183,7 @@ __device__ __forceinline__ void scan_read(ScanAcc &a, const uint8_t *qrow, const
         scan_tail<MODE, HAS_SEQ>(a, q, sq, qk, nfull, rem);
     }
     if (MODE == MODE_FILTER) a.low += __dp4a(a.lowb, ONES, 0u);
+    if (MODE == MODE_ARTIFACT) scan_flush_counts(a);
 }
 
 // trimmer decision for one read once the last chunk holding a base with q >= t is known:
@@ -230,6 +271,7 @@ __global__ void __launch_bounds__(THREADS) k_scan(const __grid_constant__ ScanPa
 
             ScanAcc a;
             a.badq = 0; a.bads = 0; a.lastc = -1; a.lowb = 0; a.low = 0;
+            a.hasn = 0; a.ba = a.bc = a.bg = a.bt = 0; a.ca = a.cc = a.cg = a.ct = 0;
             scan_read<G, MODE, HAS_SEQ>(a, qrow, srow, L, j, 0, qk);
             if (((a.badq & HI) | a.bads) != 0 || lenbad) note_bad(P.counters, P.index_base + g);
 
@@ -333,10 +375,27 @@ __global__ void __launch_bounds__(W_THREADS) k_scan_w(const __grid_constant__ Sc
 
         ScanAcc a;
         a.badq = 0; a.bads = 0; a.lastc = -1; a.lowb = 0; a.low = 0;
+        a.hasn = 0; a.ba = a.bc = a.bg = a.bt = 0; a.ca = a.cc = a.cg = a.ct = 0;
         scan_read<G, MODE, HAS_SEQ>(a, qrow, srow, L, j, rot, qk);
         if (((a.badq & HI) | a.bads) != 0 || lenbad) note_bad(P.counters, P.index_base + g);
 
-        if (MODE == MODE_TRIM) {
+        if (MODE == MODE_VALIDATE) {
+            // the reader's checks alone: nothing per read but the first-bad-read counter
+        } else if (MODE == MODE_HASN) {
+            const uint32_t hn = group_or<G>(a.hasn);
+            if (j == 0 && active) {
+                reinterpret_cast<uint8_t *>(P.out)[g] = hn ? 1 : 0;
+                kept_local += hn ? 1u : 0u;
+            }
+        } else if (MODE == MODE_ARTIFACT) {
+            const uint32_t ca = group_sum<G>(a.ca), cc = group_sum<G>(a.cc), cg = group_sum<G>(a.cg), ct = group_sum<G>(a.ct);
+            if (j == 0 && active) {
+                const int lim = L - 3;      // max_allowed_different_bases = 3 (fastx_artifacts_filter.c:66,99-107)
+                const bool artifact = (int)ca >= lim || (int)cc >= lim || (int)cg >= lim || (int)ct >= lim;
+                reinterpret_cast<uint8_t *>(P.out)[g] = artifact ? 0 : 1;
+                kept_local += artifact ? 0u : 1u;
+            }
+        } else if (MODE == MODE_TRIM) {
             const int lastc = group_max<G>(a.lastc);
             if (j == 0 && active) {
                 const int newlen = trim_newlen(qrow, lastc, L, qk);
@@ -669,6 +728,12 @@ static cudaError_t launch_scan_w(const TilePlan &plan, const ScanParams &p, cuda
 
 cudaError_t launch_scan(int mode, bool has_seq, const TilePlan &plan, const ScanParams &p, cudaStream_t st)
 {
+    if (mode == MODE_VALIDATE || mode == MODE_HASN || mode == MODE_ARTIFACT) {      // sequence modes: warp-private ring only
+        if (!plan.warp_ring || !has_seq) return cudaErrorInvalidValue;
+        if (mode == MODE_VALIDATE) return launch_scan_w<MODE_VALIDATE, true>(plan, p, st);
+        if (mode == MODE_HASN) return launch_scan_w<MODE_HASN, true>(plan, p, st);
+        return launch_scan_w<MODE_ARTIFACT, true>(plan, p, st);
+    }
     if (plan.warp_ring) {
         if (mode == MODE_TRIM) return has_seq ? launch_scan_w<MODE_TRIM, true>(plan, p, st) : launch_scan_w<MODE_TRIM, false>(plan, p, st);
         return has_seq ? launch_scan_w<MODE_FILTER, true>(plan, p, st) : launch_scan_w<MODE_FILTER, false>(plan, p, st);

@@ -13,7 +13,7 @@ constexpr int W_WARPS = 4;       // warps per CTA in the warp-private pipeline k
 constexpr int W_THREADS = W_WARPS * 32;
 constexpr int MAX_DYN_SMEM = 227 * 1024 - 1024;   // per-CTA opt-in limit minus the kernels' static smem (barriers)
 
-enum { MODE_TRIM = 0, MODE_FILTER = 1 };
+enum { MODE_TRIM = 0, MODE_FILTER = 1, MODE_VALIDATE = 2, MODE_HASN = 3, MODE_ARTIFACT = 4 };
 
 // counters block in device memory (one per context)
 enum { CNT_OUT = 0, CNT_FIRST_BAD = 1, CNT_AUX0 = 2, CNT_WORDS = 16 };

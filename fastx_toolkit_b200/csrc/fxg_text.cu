@@ -87,8 +87,9 @@ struct RecTable {
 enum { AN_NONE = 0, AN_PREFIX = 1, AN_EMPTY_SEQ = 2, AN_QUAL_LEN = 3, AN_LONG_LINE = 4, AN_BAD_RECORD = 5, AN_LINE_COUNT = 6 };
 // scalars block (u64 words): [0] first anomaly (record << 8 | class, min), [1] records kept, [2] max_len (int), [3] min_len (int),
 //                            [4] records whose quality line has another length than the sequence (numeric candidates),
-//                            [5] first such record (min), [6] sum of the read weights in, [7] sum of the read weights kept
-enum { SC_ANOM = 0, SC_KEPT = 1, SC_MAXLEN = 2, SC_MINLEN = 3, SC_NNUM = 4, SC_FIRSTNUM = 5, SC_WIN = 6, SC_WKEPT = 7, SC_WORDS = 8 };
+//                            [5] first such record (min), [6] sum of the read weights in, [7] sum of the read weights kept,
+//                            [8..13] clipper on FASTA: read weights per FXG_CLIP_* class
+enum { SC_ANOM = 0, SC_KEPT = 1, SC_MAXLEN = 2, SC_MINLEN = 3, SC_NNUM = 4, SC_FIRSTNUM = 5, SC_WIN = 6, SC_WKEPT = 7, SC_CLASS = 8 /* 6 words */, SC_WORDS = 16 };
 
 // get_reads_count() (fastx.c:475-497) of a FASTA identifier: the number after the first '-', if positive, else 1
 __device__ __forceinline__ int32_t reads_count_dev(const uint8_t *name, uint32_t n)
@@ -334,6 +335,23 @@ __global__ void k_clip_emit_len(const int32_t *clip_len, const uint8_t *cls, con
         if (show_adapter_only) { if (cls[r] == FXG_CLIP_ADAPTER_ONLY) e = seq_len[r]; }
         else if (cls[r] == FXG_CLIP_WRITE) e = clip_len[r];
         emit_len[r] = e;
+    }
+}
+
+// fastx_clipper counts get_reads_count() per class (fastx_clipper.cpp:259,277-312): for FASTA the classes are weighted
+__global__ void k_clip_class_weights(const uint8_t *cls, const int32_t *weight, uint32_t n_rec, unsigned long long *sc)
+{
+    unsigned long long w[6] = { 0, 0, 0, 0, 0, 0 };
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += gridDim.x * blockDim.x) {
+        const int c = cls[r];
+        const unsigned long long v = (unsigned long long)weight[r];
+#pragma unroll
+        for (int k = 0; k < 6; k++) w[k] += (c == k) ? v : 0ull;
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        for (int o = 16; o; o >>= 1) w[k] += __shfl_xor_sync(0xffffffffu, w[k], o);
+        if ((threadIdx.x & 31) == 0 && w[k]) atomicAdd(&sc[SC_CLASS + k], w[k]);
     }
 }
 
@@ -584,6 +602,7 @@ static int text_run(fxg_text *t, int op, const char *text_host, size_t bytes, in
         if (!rc) {
             k_clip_emit_len<<<tgrid(n_rec), 256, 0, st>>>(clip_len, t->d_keep, t->d_seq_len, n_rec, a0, t->d_out_len);
             t->launches++;
+            if (t->fasta) { k_clip_class_weights<<<tgrid(n_rec), 256, 0, st>>>(t->d_keep, t->d_weight, n_rec, t->d_scalars); t->launches++; }
         }
     } else if (op == 3) {
         rc = fxg_internal_stats_on_stream(t->ctx, &b, q_eff, hist_dev, max_cycles, t->fasta ? t->d_weight : NULL, (void *)st);
@@ -626,7 +645,8 @@ static int text_run(fxg_text *t, int op, const char *text_host, size_t bytes, in
     CKT(t, cudaStreamSynchronize(st));
     t->launches += 5;
     const unsigned long long *cnt = t->h_scalars + SC_WORDS;       // the context's counters: CNT_OUT, CNT_FIRST_BAD, CNT_AUX0..
-    if (op == 4) for (int k = 0; k < 6; k++) rep->clip_class[k] = (int64_t)cnt[k == 0 ? 0 : 2 + k];   // CNT_OUT, CNT_AUX0+k
+    if (op == 4) for (int k = 0; k < 6; k++)       // CNT_OUT, CNT_AUX0+k; FASTA: weighted by the identifiers' read counts
+        rep->clip_class[k] = t->fasta ? (int64_t)t->h_scalars[SC_CLASS + k] : (int64_t)cnt[k == 0 ? 0 : 2 + k];
     if (t->h_scalars[SC_ANOM] != ~0ull) {      // K-NUMQ met a malformed number
         rep->anomaly = (int32_t)(t->h_scalars[SC_ANOM] & 0xFF);
         rep->anomaly_record = (int64_t)(t->h_scalars[SC_ANOM] >> 8);

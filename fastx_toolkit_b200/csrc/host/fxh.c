@@ -14,6 +14,7 @@
 #include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <sys/uio.h>
 #include <sys/types.h>
@@ -84,8 +85,32 @@ int fxh_gpu_count(void)
     return n > 0 ? (n > 64 ? 64 : n) : 1;
 }
 
-fxg_ctx *fxh_gpu_open_dev(int dev)
+/* cuInit() enumerates and initialises every visible GPU (about 0.2 s each on an 8-GPU box): before the first CUDA call,
+ * narrow the visible set to the GPUs this process will use.  Device numbers are then relative to FASTX_GPU. */
+static int g_dev_shift = 0, g_narrowed = 0;
+static void narrow_visible_devices(void)
 {
+    if (g_narrowed) return;
+    g_narrowed = 1;
+    if (getenv("CUDA_VISIBLE_DEVICES") || getenv("FASTX_KEEP_VISIBLE")) return;
+    const int first = getenv("FASTX_GPU") ? atoi(getenv("FASTX_GPU")) : 0, n = fxh_gpu_count();
+    if (first < 0) return;
+    char list[512]; size_t o = 0;
+    for (int g = 0; g < n && o + 8 < sizeof list; g++) o += (size_t)snprintf(list + o, sizeof list - o, "%s%d", g ? "," : "", first + g);
+    setenv("CUDA_VISIBLE_DEVICES", list, 1);
+    g_dev_shift = first;
+}
+
+/* CUDA ordinal of the first GPU this process uses (FASTX_GPU, or 0 once the visible set has been narrowed to start there) */
+int fxh_first_device(void)
+{
+    narrow_visible_devices();
+    return (getenv("FASTX_GPU") ? atoi(getenv("FASTX_GPU")) : 0) - g_dev_shift;
+}
+
+fxg_ctx *fxh_gpu_open_dev(int dev)       /* dev: CUDA ordinal, fxh_first_device() + k */
+{
+    narrow_visible_devices();
     fxg_ctx *ctx = NULL;
     int rc = fxg_init(dev, &ctx);
     if (rc != FXG_OK) errx(1, "GPU %d unavailable: %s (%s). This build has no CPU fallback.", dev, fxg_strerror(rc), fxg_last_error(NULL));
@@ -94,8 +119,7 @@ fxg_ctx *fxh_gpu_open_dev(int dev)
 
 fxg_ctx *fxh_gpu_open(void)
 {
-    const char *e = getenv("FASTX_GPU");
-    int dev = e ? atoi(e) : 0;
+    int dev = fxh_first_device();
     fxg_ctx *ctx = NULL;
     int rc = fxg_init(dev, &ctx);
     if (rc != FXG_OK) errx(1, "GPU %d unavailable: %s (%s). This build has no CPU fallback.", dev, fxg_strerror(rc), fxg_last_error(NULL));
@@ -557,6 +581,7 @@ struct fxh_writer {
     const char *aw_buf;
     size_t aw_bytes;
     int fastq;
+    int regular, store_threads;       /* output is a regular file (no gzip child): large blocks may be stored through a mapping */
     char *buf;
     size_t cap, len;
     size_t n_seq, n_reads;
@@ -600,6 +625,12 @@ fxh_writer *fxh_writer_open(const char *filename, int fastq, int compress)
     g_open_writer = w;
     w->fd = compress ? open_output_compressor(filename, &w->gzip_pid) : open_output_file(filename);
     w->fastq = fastq;
+    {
+        struct stat sb;
+        w->regular = !compress && fstat(w->fd, &sb) == 0 && S_ISREG(sb.st_mode);
+        const char *e = getenv("FASTX_WRITE_THREADS");
+        w->store_threads = e ? atoi(e) : 4;
+    }
     w->cap = (size_t)16 << 20;
     w->buf = (char *)malloc(w->cap);
     if (!w->buf) err(1, "out of memory (output buffer)");
@@ -716,11 +747,43 @@ void fxh_write_raw(fxh_writer *w, const char *text, size_t bytes, int64_t record
     w->n_reads += (size_t)records;
 }
 
+/* Large blocks of formatted text into a REGULAR output file: write(2) copies with one thread and holds the inode lock, so the
+ * block is stored through a shared mapping by several threads at once instead (page faults and copies run in parallel); the
+ * file is grown to exactly the bytes stored and the descriptor's offset moved behind them, so write(2) may follow. */
+typedef struct { char *dst; const char *src; size_t n; } store_job;
+static void *store_main(void *arg) { store_job *j = (store_job *)arg; memcpy(j->dst, j->src, j->n); return NULL; }
+
+static int store_parallel(fxh_writer *w, const char *text, size_t bytes)
+{
+    if (!w->regular || w->store_threads < 2 || bytes < ((size_t)4 << 20)) return 0;
+    const off_t off = lseek(w->fd, 0, SEEK_CUR);
+    if (off < 0) return 0;
+    const long pg = sysconf(_SC_PAGESIZE);
+    const off_t aoff = off & ~((off_t)pg - 1);
+    const size_t lead = (size_t)(off - aoff);
+    if (ftruncate(w->fd, off + (off_t)bytes) != 0) return 0;
+    char *map = (char *)mmap(NULL, lead + bytes, PROT_READ | PROT_WRITE, MAP_SHARED, w->fd, aoff);
+    if (map == MAP_FAILED) return 0;
+    const int T = w->store_threads > 16 ? 16 : w->store_threads;
+    store_job jobs[16]; pthread_t th[16];
+    const size_t part = ((bytes / (size_t)T) + 4095) & ~(size_t)4095;
+    int nt = 0;
+    for (size_t o = 0; o < bytes && nt < T; o += part, nt++) {
+        jobs[nt].dst = map + lead + o; jobs[nt].src = text + o; jobs[nt].n = (bytes - o < part) ? bytes - o : part;
+        if (nt > 0 && pthread_create(&th[nt], NULL, store_main, &jobs[nt]) != 0) err(1, "pthread_create");
+    }
+    store_main(&jobs[0]);
+    for (int i = 1; i < nt; i++) pthread_join(th[i], NULL);
+    munmap(map, lead + bytes);
+    if (lseek(w->fd, off + (off_t)bytes, SEEK_SET) < 0) err(1, "lseek on the output file failed");
+    return 1;
+}
+
 /* formatted text, written before the call returns (the streaming engine's own thread is the background here) */
 void fxh_writer_write_now(fxh_writer *w, const char *text, size_t bytes, int64_t records, int64_t reads)
 {
     writer_flush(w);
-    write_all(w->fd, text, bytes);
+    if (!store_parallel(w, text, bytes)) write_all(w->fd, text, bytes);
     w->n_seq += (size_t)records;
     w->n_reads += (size_t)reads;
 }

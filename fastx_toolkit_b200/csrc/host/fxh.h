@@ -102,6 +102,7 @@ size_t      fxh_num_output_reads(const fxh_writer *w);
 /* ---- GPU context helpers ---- */
 fxg_ctx    *fxh_gpu_open(void);                 /* FASTX_GPU=<index> (default 0); dies if no GPU: no CPU fallback */
 fxg_ctx    *fxh_gpu_open_dev(int dev);
+int         fxh_first_device(void);         /* CUDA ordinal of FASTX_GPU (the visible set is narrowed to the GPUs in use)  */
 int         fxh_gpu_count(void);                /* FASTX_GPUS=<n> (default 1): tools that can use several GPUs */
 void        fxh_gpu_check(fxg_ctx *ctx, int rc, const char *what);
 int64_t     fxh_batch_reads(void);              /* FASTX_BATCH_READS (default 2 M) */

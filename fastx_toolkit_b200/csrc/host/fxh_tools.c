@@ -45,7 +45,7 @@ static int batch_q(const fxh_batch *b) { return b->numeric_qual ? 33 : fxh_q_off
  * path does not reproduce bit-exactly by construction (broken structure, illegal bytes, mixed quality encodings) and
  * leaves the reader positioned there, so the record-by-record host path that follows produces the reference's output
  * and message. */
-static int first_gpu(void) { return getenv("FASTX_GPU") ? atoi(getenv("FASTX_GPU")) : 0; }
+static int first_gpu(void) { return fxh_first_device(); }
 
 static void text_fast_path(fxh_reader *rd, fxh_writer *wr, int op, int a0, int a1)
 {
@@ -251,7 +251,7 @@ static void clip_text_path(fxh_reader *rd, fxh_writer *wr, const fxg_clip_opts *
     job.op = FXS_CLIP; job.a0 = cl_show_adapter_only; job.clip = o;
     job.ngpu = fxh_gpu_count(); job.first_dev = first_gpu();
     (void)fxs_run(&job, rd, wr);
-    *count_input += (unsigned int)job.records;
+    *count_input += (unsigned int)job.reads;          /* get_reads_count() per record (fastx_clipper.cpp:259,277) */
     for (int k = 0; k < 6; k++) cnt[k] += job.clip_class[k];
 }
 
@@ -470,7 +470,7 @@ static int main_stats(int argc, char **argv)
     /* FASTX_GPUS=N: chunks go to the GPUs round-robin, each GPU keeps a partial histogram, and one NCCL all-reduce
      * (fxg_comm_allreduce_u64) merges them before printing — the only collective this tool needs. */
     const int ngpu = fxh_gpu_count();
-    const int dev0 = getenv("FASTX_GPU") ? atoi(getenv("FASTX_GPU")) : 0;
+    const int dev0 = first_gpu();
     fxg_ctx *ctxs[64]; uint64_t *hists[64]; int devs[64];
     const int max_cycles = FXH_MAX_LINE;
     const size_t hist_bytes = (size_t)max_cycles * 5 * FXG_QBINS * sizeof(uint64_t);

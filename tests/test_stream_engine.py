@@ -73,6 +73,14 @@ def test_valid_inputs_go_through_the_engine_in_order(harness, tmp_path):
     m = subprocess.run([harness, "-v", "-i", fq, "-o", out1], capture_output=True, env=dict(os.environ, **ENVS[1]))
     r = subprocess.run([REF, "-v", "-i", fq, "-o", out2], capture_output=True)
     assert (m.returncode, m.stdout) == (r.returncode, r.stdout) and open(out1, "rb").read() == open(out2, "rb").read()
+    # one 5 MB block into a regular file: stored through the shared mapping by several threads (fxh.c store_parallel), after
+    # some bytes written the ordinary way so that the mapping starts in the middle of a page
+    big = str(tmp_path / "big.fq")
+    open(big, "wb").write(text * 3)
+    for wt in ("4", "1"):
+        m = subprocess.run([harness, "-i", big, "-o", out1], capture_output=True, env=dict(os.environ, FASTX_WRITE_THREADS=wt, FASTX_CHUNK_BYTES=str(6 << 20)))
+        r = subprocess.run([REF, "-i", big, "-o", out2], capture_output=True)
+        assert m.returncode == r.returncode == 0 and open(out1, "rb").read() == open(out2, "rb").read()
 
 
 def test_broken_inputs_hand_over_to_the_record_path(harness, tmp_path):
