@@ -525,25 +525,49 @@ def main():
     stat = {"in_bytes": 0, "out_bytes": 0}
     stat_lock = threading.Lock()
 
-    def text_worker(w, first_chunk, count):
+    dec_len = [torch.empty(chunk_reads, dtype=torch.int32).pin_memory() for _ in range(W)]
+    dec_start = [torch.empty(chunk_reads * 4, dtype=torch.int32).pin_memory() for _ in range(W)]
+
+    def text_worker(w, first_chunk, count, mode):
+        """mode 0: FASTQ text out; 1: the same text deflated on the GPU (-z); 2: per-record decisions + line table out"""
         wctx, tp, wout = workers[w]
         rep = F.TextReport()
         ib = ob = 0
         for k in range(count):
             hin = host_ins[(first_chunk + k) % NROT]
-            rc = Lib.fxg_text_run_host(tp.h, 0, hin.data_ptr(), hin.numel(), Q, T, MINLEN, wout.data_ptr(), C.byref(rep))
+            if mode == 2:
+                rc = Lib.fxg_text_decide_host(tp.h, 0, hin.data_ptr(), hin.numel(), Q, T, MINLEN, dec_len[w].data_ptr(), dec_start[w].data_ptr(), C.byref(rep))
+                nout = chunk_reads * 20
+            else:
+                rc = Lib.fxg_text_run_host(tp.h, 0, hin.data_ptr(), hin.numel(), Q, T, MINLEN, wout.data_ptr(), C.byref(rep))
+                nout = int(rep.out_bytes)
             if rc != 0 or rep.anomaly != 0 or rep.n_records != chunk_reads:
                 raise RuntimeError("text path failed: rc=%d anomaly=%d" % (rc, rep.anomaly))
-            ib += hin.numel(); ob += int(rep.out_bytes)
+            ib += hin.numel(); ob += nout
         with stat_lock:
             stat["in_bytes"] += ib; stat["out_bytes"] += ob
 
-    def text_pass():
+    def text_pass(mode=0):
         per = [nchunks // W + (1 if w < nchunks % W else 0) for w in range(W)]
         starts = [sum(per[:w]) for w in range(W)]
-        th = [threading.Thread(target=text_worker, args=(w, starts[w], per[w])) for w in range(W)]
+        th = [threading.Thread(target=text_worker, args=(w, starts[w], per[w], mode)) for w in range(W)]
         [t.start() for t in th]
         [t.join() for t in th]
+
+    def timed_passes(mode):
+        for _ in range(2):
+            text_pass(mode)
+        barrier()
+        stat["in_bytes"] = stat["out_bytes"] = 0
+        t0_ = time.perf_counter()
+        for _ in range(args.steps):
+            text_pass(mode)
+        torch.cuda.synchronize()
+        loc = time.perf_counter() - t0_
+        d = max_over_ranks(loc)
+        return {"value": world * nchunks * chunk_reads * args.steps / d / 1e6, "unit": UNIT,
+                "h2d_GBps_this_gpu": stat["in_bytes"] / loc / 1e9, "d2h_GBps_this_gpu": stat["out_bytes"] / loc / 1e9,
+                "d2h_bytes_per_read": stat["out_bytes"] / max(1, nchunks * chunk_reads * args.steps)}
 
     for _ in range(max(args.warmup, 3)):
         text_pass()
@@ -573,6 +597,18 @@ def main():
                 assert got[4 * k] == src[4 * i] and got[4 * k + 1] == src[4 * i + 1][: first[i]] and got[4 * k + 3] == src[4 * i + 3][: first[i]], "text path output differs"
                 k += 1
         assert len(got) == 4 * k + 1
+    # the same input with less coming back over PCIe: (1) the output deflated on the GPU (what `-z` does), (2) only the
+    # per-record decisions + line table (for a writer that gathers from its own copy of the input)
+    variants = {}
+    for w in workers:
+        w[1].set_deflate(True)
+    variants["text_in_gzip_out"] = timed_passes(1)
+    for w in workers:
+        w[1].set_deflate(False)
+    variants["text_in_decisions_out"] = timed_passes(2)
+    if rank == 0:      # the decisions must be the kernel's own
+        Lib.fxg_text_decide_host(workers[0][1].h, 0, host_ins[0].data_ptr(), host_ins[0].numel(), Q, T, MINLEN, dec_len[0].data_ptr(), dec_start[0].data_ptr(), C.byref(rep0))
+        assert bool((dec_len[0].numpy() == first).all()), "decisions differ from the HBM-resident result"
     for w in workers:
         w[1].close(); w[0].close()
     del workers, host_ins
@@ -605,6 +641,7 @@ def main():
                      "kernel_ms": kernel_ms, "peak_source": peak_src},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * e2e_h2d_step, "d2h_bytes_per_step": world * e2e_d2h_step,
                 "pcie_rank0": pcie, "input_rotation": "%d distinct chunks of %d reads per GPU (%.0f MB, larger than the host L3) sent in rotation" % (NROT, chunk_reads, NROT * cb / 1e6),
+                "less_d2h": variants,
                 "file_to_file": f2f,
                 "reads_per_step_per_gpu": nchunks * chunk_reads,
                 "api": "fxg_text_run_host: FASTQ text in pinned host memory -> H2D -> parse/pack/K-TRIM/emit on the GPU -> D2H -> trimmed FASTQ text "

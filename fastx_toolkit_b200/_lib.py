@@ -43,7 +43,8 @@ class TextReport(C.Structure):
     """struct fxg_text_report"""
     _fields_ = [("n_records", C.c_int64), ("n_out_records", C.c_int64), ("consumed_bytes", C.c_int64), ("out_bytes", C.c_int64),
                 ("max_len", C.c_int32), ("anomaly", C.c_int32), ("anomaly_record", C.c_int64),
-                ("min_len", C.c_int32), ("reserved", C.c_int32), ("clip_class", C.c_int64 * 6), ("n_reads", C.c_int64), ("n_out_reads", C.c_int64)]
+                ("min_len", C.c_int32), ("reserved", C.c_int32), ("clip_class", C.c_int64 * 6), ("n_reads", C.c_int64), ("n_out_reads", C.c_int64),
+                ("raw_out_bytes", C.c_int64), ("out_crc32_pure", C.c_uint32), ("deflated", C.c_uint32)]
 
 
 class DCollapseReport(C.Structure):
@@ -144,9 +145,13 @@ def lib():
         "fxg_text_new": (i32, [vp, i32, sz, C.POINTER(vp)]),
         "fxg_text_free": (None, [vp]),
         "fxg_text_run_host": (i32, [vp, i32, vp, sz, i32, i32, i32, vp, C.POINTER(TextReport)]),
+        "fxg_text_decide_host": (i32, [vp, i32, vp, sz, i32, i32, i32, vp, vp, C.POINTER(TextReport)]),
         "fxg_text_clip_host": (i32, [vp, vp, sz, i32, C.POINTER(ClipOpts), i32, i32, vp, C.POINTER(TextReport)]),
         "fxg_text_stats_host": (i32, [vp, vp, sz, i32, vp, C.c_int32, C.POINTER(TextReport)]),
         "fxg_text_set_format": (i32, [vp, i32]),
+        "fxg_text_set_deflate": (i32, [vp, i32]),
+        "fxg_crc32_concat": (C.c_uint32, [C.c_uint32, C.c_uint32, C.c_uint64]),
+        "fxg_crc32_finish": (C.c_uint32, [C.c_uint32, C.c_uint64]),
         "fxg_text_collapse_host": (i32, [vp, vp, sz, i32, vp, i64, C.POINTER(TextReport)]),
         "fxg_text_numeric_chunks": (i64, [vp]),
         "fxg_text_fasta_chunks": (i64, [vp]),
@@ -353,6 +358,11 @@ class TextPipe:
         if rc != FXG_OK:
             raise FxgError(rc, self.L.fxg_text_error(self.h).decode())
         return out[: rep.out_bytes].tobytes(), rep
+
+    def set_deflate(self, on):
+        rc = self.L.fxg_text_set_deflate(self.h, 1 if on else 0)
+        if rc != FXG_OK:
+            raise FxgError(rc, self.L.fxg_text_error(self.h).decode())
 
     def set_format(self, fasta):
         rc = self.L.fxg_text_set_format(self.h, 1 if fasta else 0)

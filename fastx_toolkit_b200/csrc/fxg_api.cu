@@ -507,6 +507,7 @@ static int stats_enqueue(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint64_
     if (fast4) {
         p.tile_reads = (int)rfit4;
         { const char *ep = getenv("FXG_STATS_PAIR"); p.stages = (ep && atoi(ep) == 1) ? 1 : 2; }      // 2: warp pairs share a tile buffer
+        if (getenv("FXG_STATS_NOBFAST")) p.stages |= 4;                                                 // A/B switch: masked B region only
         const uint32_t smem = (uint32_t)((size_t)S4_HIST_BYTES + S4_DUMMY_BYTES + (size_t)S4_WARPS * 2 * b->stride * rfit4);
         const int64_t ntiles = (b->n + rfit4 - 1) / rfit4;
         int64_t grid = ctx->sm_count;

@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(TILES * PAIR * 32, 1) k_stats4(const __grid_co
             // ---- B region: words 32..39 (the read's last bases included) ----
             {
                 const int LpB = Lp - 128;
-                const bool b_full4 = __all_sync(0xFFFFFFFFu, LpB >= 16);      // every read holds words 32..35 complete
+                const bool b_full4 = (P.stages & 4) == 0 && __all_sync(0xFFFFFFFFu, LpB >= 16);      // every read holds words 32..35 complete
                 if (b_full4) {
                     // words 32..35 without masks: lane l visits word (l>>2 + a) & 3 — two lanes per counter (same address:
                     // two wavefronts per RED), a fraction of the masked steps' instructions
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(TILES * PAIR * 32, 1) k_stats4(const __grid_co
 
 cudaError_t launch_stats4(const StatsParams &p, int grid, uint32_t smem_bytes, cudaStream_t st)
 {
-    if (p.stages == 2) {          // warp pairs
+    if ((p.stages & 3) == 2) {          // warp pairs
         cudaFuncSetAttribute(k_stats4<S4_WARPS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
         k_stats4<S4_WARPS, 2><<<grid, S4_WARPS * 64, smem_bytes, st>>>(p);
     } else {

@@ -355,6 +355,13 @@ __global__ void k_clip_class_weights(const uint8_t *cls, const int32_t *weight, 
     }
 }
 
+// decisions-only output: one int32 per record (surviving length, -1 = dropped)
+__global__ void k_decisions(const int32_t *out_len, const uint8_t *keep_flags, const int32_t *seq_len, uint32_t n_rec, int32_t *dec)
+{
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += gridDim.x * blockDim.x)
+        dec[r] = keep_flags ? (keep_flags[r] ? seq_len[r] : -1) : out_len[r];
+}
+
 __global__ void k_count_kept(const int32_t *out_len, const uint8_t *keep_flags, const int32_t *weight, uint32_t n_rec, unsigned long long *sc)
 {
     unsigned c = 0;
@@ -407,6 +414,10 @@ struct fxg_text {
     unsigned long long *h_scalars; // pinned mirror (+ 8 words for the context's counters)
     int64_t launches;
     int64_t n_numeric_chunks, n_fasta_chunks;      // chunks that took the numeric-quality / FASTA forms of the path
+    int32_t *decide_len_host;      // fxg_text_decide_host: per-record decision goes here instead of any text
+    uint32_t *decide_start_host;
+    int deflate;                   // emit DEFLATE blocks instead of plain text (fxg_deflate.cu)
+    uint8_t *d_dfl; void *d_dfl_scratch; size_t dfl_scratch_bytes; uint32_t *h_dfl_crc;
     char err[256];
 };
 
@@ -425,6 +436,29 @@ extern "C" const char *fxg_text_error(const fxg_text *t) { return t ? t->err : "
 extern "C" int64_t fxg_text_launches(const fxg_text *t) { return t ? t->launches : 0; }
 extern "C" int64_t fxg_text_numeric_chunks(const fxg_text *t) { return t ? t->n_numeric_chunks : 0; }
 extern "C" int64_t fxg_text_fasta_chunks(const fxg_text *t) { return t ? t->n_fasta_chunks : 0; }
+namespace fxg {
+size_t deflate_scratch_bytes(size_t max_text_bytes);
+size_t deflate_out_bound(size_t text_bytes);
+cudaError_t deflate_run(const uint8_t *d_text, size_t bytes, uint8_t *d_out, void *d_scratch, size_t scratch_bytes, uint64_t *h_pinned,
+                        uint32_t *h_crc_blocks, size_t *out_bytes, uint32_t *crc_pure, int sm_count, cudaStream_t st, int64_t *launches);
+}
+
+// `-z`: the emitted text leaves the GPU as byte-aligned DEFLATE blocks (see fxg_deflate.cu and fxg.h)
+extern "C" int fxg_text_set_deflate(fxg_text *t, int on)
+{
+    if (!t) return FXG_ERR_ARG;
+    if (on && !t->d_dfl) {
+        CKT(t, cudaSetDevice(t->device));
+        const size_t text_cap = t->cap_bytes + t->cap_bytes / 4 + 64;
+        t->dfl_scratch_bytes = deflate_scratch_bytes(text_cap);
+        CKT(t, cudaMalloc(&t->d_dfl, deflate_out_bound(text_cap)));
+        CKT(t, cudaMalloc(&t->d_dfl_scratch, t->dfl_scratch_bytes));
+        CKT(t, cudaMallocHost(&t->h_dfl_crc, (text_cap / 65536 + 2) * sizeof(uint32_t)));
+    }
+    t->deflate = on ? 1 : 0;
+    return FXG_OK;
+}
+
 extern "C" int fxg_text_set_format(fxg_text *t, int fasta)
 {
     if (!t) return FXG_ERR_ARG;
@@ -440,6 +474,7 @@ extern "C" void fxg_text_free(fxg_text *t)
     cudaFree(t->d_start); cudaFree(t->d_llen); cudaFree(t->d_seq_len); cudaFree(t->d_out_len); cudaFree(t->d_weight); cudaFree(t->d_keep);
     cudaFree(t->d_sizes); cudaFree(t->d_offs); cudaFree(t->d_seq); cudaFree(t->d_qual); cudaFree(t->d_oseq); cudaFree(t->d_oqual); cudaFree(t->d_tmp);
     cudaFree(t->d_scalars); cudaFreeHost(t->h_scalars);
+    cudaFree(t->d_dfl); cudaFree(t->d_dfl_scratch); if (t->h_dfl_crc) cudaFreeHost(t->h_dfl_crc);
     if (t->st) cudaStreamDestroy(t->st);
     free(t);
 }
@@ -631,6 +666,23 @@ static int text_run(fxg_text *t, int op, const char *text_host, size_t bytes, in
     }
     const int32_t *ol = (op == 0 || op == 4) ? t->d_out_len : (op == 2 ? t->d_seq_len : NULL);   // revcomp keeps every read at full length
     const uint8_t *kf = op == 1 ? t->d_keep : NULL;
+    if (t->decide_len_host) {
+        // the caller keeps the input text and writes the output itself: only the decisions (and the line table) travel back
+        int32_t *dec = reinterpret_cast<int32_t *>(t->d_sizes);
+        k_decisions<<<tgrid(n_rec), 256, 0, st>>>(ol, kf, t->d_seq_len, n_rec, dec);
+        k_count_kept<<<tgrid(n_rec), 256, 0, st>>>(ol, kf, NULL, n_rec, t->d_scalars);
+        CKT(t, cudaMemcpyAsync(t->decide_len_host, dec, (size_t)n_rec * 4, cudaMemcpyDeviceToHost, st));
+        if (t->decide_start_host) CKT(t, cudaMemcpyAsync(t->decide_start_host, t->d_start, (size_t)n_rec * lpr * 4, cudaMemcpyDeviceToHost, st));
+        CKT(t, cudaMemcpyAsync(t->h_scalars, t->d_scalars, 8 * SC_WORDS, cudaMemcpyDeviceToHost, st));
+        CKT(t, cudaMemcpyAsync(t->h_scalars + SC_WORDS, (unsigned long long *)fxg_internal_counters(t->ctx), 64, cudaMemcpyDeviceToHost, st));
+        CKT(t, cudaStreamSynchronize(st));
+        t->launches += 2;
+        if (t->h_scalars[SC_ANOM] != ~0ull) { rep->anomaly = (int32_t)(t->h_scalars[SC_ANOM] & 0xFF); rep->anomaly_record = (int64_t)(t->h_scalars[SC_ANOM] >> 8); return FXG_OK; }
+        if (t->h_scalars[SC_WORDS + 1] != ~0ull) { rep->anomaly = AN_BAD_RECORD; rep->anomaly_record = (int64_t)t->h_scalars[SC_WORDS + 1]; return FXG_OK; }
+        rep->n_out_records = (int64_t)t->h_scalars[SC_KEPT];
+        rep->n_out_reads = rep->n_out_records;
+        return FXG_OK;
+    }
     const uint8_t *numq = numeric ? (alt_qual ? alt_qual : t->d_qual) : NULL;
     k_emit_sizes<<<tgrid(n_rec), 256, 0, st>>>(rt, n_rec, ol, kf, numq, stride, t->d_sizes);
     CKT(t, cudaMemsetAsync(t->d_sizes + n_rec, 0, 8, st));
@@ -660,7 +712,19 @@ static int text_run(fxg_text *t, int op, const char *text_host, size_t bytes, in
     rep->n_out_records = (int64_t)t->h_scalars[SC_KEPT];
     rep->n_out_reads = t->fasta ? (int64_t)t->h_scalars[SC_WKEPT] : rep->n_out_records;
     rep->out_bytes = (int64_t)out_bytes;
-    if (out_bytes) {
+    rep->raw_out_bytes = (int64_t)out_bytes;
+    if (out_bytes && t->deflate) {
+        size_t zbytes = 0; uint32_t crc = 0;
+        int sm = 148;
+        cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, t->device);
+        CKT(t, deflate_run(t->d_out, (size_t)out_bytes, t->d_dfl, t->d_dfl_scratch, t->dfl_scratch_bytes, (uint64_t *)(t->h_scalars + SC_WORDS),
+                           t->h_dfl_crc, &zbytes, &crc, sm, st, &t->launches));
+        rep->out_bytes = (int64_t)zbytes;
+        rep->out_crc32_pure = crc;
+        rep->deflated = 1;
+        CKT(t, cudaMemcpyAsync(out_host, t->d_dfl, zbytes, cudaMemcpyDeviceToHost, st));
+        CKT(t, cudaStreamSynchronize(st));
+    } else if (out_bytes) {
         CKT(t, cudaMemcpyAsync(out_host, t->d_out, out_bytes, cudaMemcpyDeviceToHost, st));
         CKT(t, cudaStreamSynchronize(st));
     }
@@ -672,6 +736,20 @@ extern "C" int fxg_text_run_host(fxg_text *t, int op, const char *text_host, siz
 {
     if (op < 0 || op > 2) return FXG_ERR_ARG;
     return text_run(t, op, text_host, bytes, q_offset, a0, a1, out_host, NULL, 0, NULL, NULL, 0, rep);
+}
+
+// op 0 / 1 with the per-record decision as the only result: out_len_host[r] = surviving length or -1; line_start_host (may be
+// NULL) = byte offset of each of the record's 4 lines in the chunk.  For callers that keep the input text and write the output
+// from it (device-to-host traffic: 4 to 20 bytes per record instead of the whole text).
+extern "C" int fxg_text_decide_host(fxg_text *t, int op, const char *text_host, size_t bytes, int q_offset, int a0, int a1,
+                                    int32_t *out_len_host, uint32_t *line_start_host, fxg_text_report *rep)
+{
+    if (!t || op < 0 || op > 1 || !out_len_host || t->fasta) return FXG_ERR_ARG;
+    t->decide_len_host = out_len_host; t->decide_start_host = line_start_host;
+    char dummy = 0;
+    const int rc = text_run(t, op, text_host, bytes, q_offset, a0, a1, &dummy, NULL, 0, NULL, NULL, 0, rep);
+    t->decide_len_host = NULL; t->decide_start_host = NULL;
+    return rc;
 }
 
 extern "C" int fxg_text_clip_host(fxg_text *t, const char *text_host, size_t bytes, int q_offset, const fxg_clip_opts *o,

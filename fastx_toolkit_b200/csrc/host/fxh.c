@@ -582,10 +582,40 @@ struct fxh_writer {
     size_t aw_bytes;
     int fastq;
     int regular, store_threads;       /* output is a regular file (no gzip child): large blocks may be stored through a mapping */
+    int gz;                           /* -z without a gzip child: this writer frames the gzip stream itself */
+    uint32_t gz_crc; uint64_t gz_len; /* pure CRC-32 register and length of the uncompressed stream so far */
     char *buf;
     size_t cap, len;
     size_t n_seq, n_reads;
 };
+
+/* ---- -z: gzip framing (RFC 1952) around DEFLATE blocks that are either made by the GPU (fxg_text_set_deflate) or, for text
+ * formatted on the host, plain stored blocks.  The reference pipes its text through a forked gzip (fastx.c:214-248); what
+ * matters to a reader of the file is the uncompressed stream, which is the same. ---- */
+#define GZ_POLY 0xEDB88320u
+static uint32_t gz_tab[256];
+static void gz_tab_init(void)
+{
+    if (gz_tab[1]) return;
+    for (uint32_t i = 0; i < 256; i++) { uint32_t c = i; for (int k = 0; k < 8; k++) c = (c & 1u) ? (c >> 1) ^ GZ_POLY : c >> 1; gz_tab[i] = c; }
+}
+static uint32_t gz_multmodp(uint32_t a, uint32_t b)
+{
+    uint32_t m = 1u << 31, p = 0;
+    for (;;) {
+        if (a & m) { p ^= b; if ((a & (m - 1u)) == 0u) break; }
+        m >>= 1;
+        b = (b & 1u) ? (b >> 1) ^ GZ_POLY : b >> 1;
+    }
+    return p;
+}
+static uint32_t gz_shift(uint32_t crc, uint64_t nbytes)      /* crc * x^(8 nbytes) mod P: the register after nbytes more zero bytes */
+{
+    uint32_t sq = 1u << 30, p = 1u << 31;                    /* x^1, x^0 */
+    for (int k = 0; k < 3; k++) sq = gz_multmodp(sq, sq);    /* x^8 */
+    while (nbytes) { if (nbytes & 1) p = gz_multmodp(sq, p); sq = gz_multmodp(sq, sq); nbytes >>= 1; }
+    return gz_multmodp(p, crc);
+}
 
 static int open_output_file(const char *filename)
 {
@@ -623,7 +653,14 @@ fxh_writer *fxh_writer_open(const char *filename, int fastq, int compress)
     if (!w) err(1, "out of memory");
     if (!g_open_writer) atexit(flush_at_exit);
     g_open_writer = w;
-    w->fd = compress ? open_output_compressor(filename, &w->gzip_pid) : open_output_file(filename);
+    if (compress && !getenv("FASTX_GZIP_CHILD")) {
+        static const unsigned char hdr[10] = { 0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 0, 3 };
+        w->fd = open_output_file(filename);
+        w->gz = 1;
+        gz_tab_init();
+        if (write(w->fd, hdr, sizeof hdr) != (ssize_t)sizeof hdr) err(1, "writing nucleotides failed");
+    } else
+        w->fd = compress ? open_output_compressor(filename, &w->gzip_pid) : open_output_file(filename);
     w->fastq = fastq;
     {
         struct stat sb;
@@ -638,9 +675,27 @@ fxh_writer *fxh_writer_open(const char *filename, int fastq, int compress)
 }
 
 static void aw_wait(fxh_writer *w);
+static void write_all(int fd, const char *text, size_t bytes);
+
+/* -z framing: host-formatted text goes out as stored DEFLATE blocks (at most 65 535 bytes each), byte aligned */
+static void gz_write_stored(fxh_writer *w, const char *text, size_t bytes)
+{
+    uint32_t reg = 0;
+    for (size_t i = 0; i < bytes; i++) reg = gz_tab[(reg ^ (unsigned char)text[i]) & 0xFFu] ^ (reg >> 8);
+    w->gz_crc = gz_shift(w->gz_crc, bytes) ^ reg;
+    w->gz_len += bytes;
+    for (size_t off = 0; off < bytes; off += 65535) {
+        const size_t n = bytes - off < 65535 ? bytes - off : 65535;
+        const unsigned char h[5] = { 0, (unsigned char)(n & 0xFF), (unsigned char)(n >> 8), (unsigned char)(~n & 0xFF), (unsigned char)((~n >> 8) & 0xFF) };
+        write_all(w->fd, (const char *)h, 5);
+        write_all(w->fd, text + off, n);
+    }
+}
+
 static void writer_flush(fxh_writer *w)
 {
     aw_wait(w);          /* keep the byte order: a background block goes out before anything buffered later */
+    if (w->gz) { if (w->len) gz_write_stored(w, w->buf, w->len); w->len = 0; return; }
     size_t off = 0;
     while (off < w->len) {
         ssize_t k = write(w->fd, w->buf + off, w->len - off);
@@ -732,6 +787,7 @@ static void aw_wait(fxh_writer *w)
 void fxh_write_raw(fxh_writer *w, const char *text, size_t bytes, int64_t records)
 {
     writer_flush(w);
+    if (w->gz) { if (bytes) gz_write_stored(w, text, bytes); w->n_seq += (size_t)records; w->n_reads += (size_t)records; return; }
     if (!w->aw_started) {
         pthread_mutex_init(&w->aw_mu, NULL);
         pthread_cond_init(&w->aw_cv, NULL);
@@ -783,7 +839,21 @@ static int store_parallel(fxh_writer *w, const char *text, size_t bytes)
 void fxh_writer_write_now(fxh_writer *w, const char *text, size_t bytes, int64_t records, int64_t reads)
 {
     writer_flush(w);
-    if (!store_parallel(w, text, bytes)) write_all(w->fd, text, bytes);
+    if (w->gz) gz_write_stored(w, text, bytes);
+    else if (!store_parallel(w, text, bytes)) write_all(w->fd, text, bytes);
+    w->n_seq += (size_t)records;
+    w->n_reads += (size_t)reads;
+}
+
+int fxh_writer_frames_gzip(const fxh_writer *w) { return w->gz; }
+
+/* -z: DEFLATE blocks made by the GPU for `raw_len` bytes of text whose pure CRC-32 register is `crc_pure` */
+void fxh_writer_write_deflated(fxh_writer *w, const char *blocks, size_t bytes, uint64_t raw_len, uint32_t crc_pure, int64_t records, int64_t reads)
+{
+    writer_flush(w);
+    write_all(w->fd, blocks, bytes);
+    w->gz_crc = gz_shift(w->gz_crc, raw_len) ^ crc_pure;
+    w->gz_len += raw_len;
     w->n_seq += (size_t)records;
     w->n_reads += (size_t)reads;
 }
@@ -801,6 +871,12 @@ void fxh_writer_close(fxh_writer *w)
         pthread_mutex_unlock(&w->aw_mu);
         pthread_join(w->aw_thread, NULL);
         w->aw_started = 0;
+    }
+    if (w->gz) {          /* final empty stored block, CRC-32 and ISIZE */
+        const uint32_t crc = (gz_shift(0xFFFFFFFFu, w->gz_len) ^ w->gz_crc) ^ 0xFFFFFFFFu, isz = (uint32_t)(w->gz_len & 0xFFFFFFFFu);
+        const unsigned char t[13] = { 1, 0, 0, 0xFF, 0xFF, (unsigned char)crc, (unsigned char)(crc >> 8), (unsigned char)(crc >> 16), (unsigned char)(crc >> 24),
+                                      (unsigned char)isz, (unsigned char)(isz >> 8), (unsigned char)(isz >> 16), (unsigned char)(isz >> 24) };
+        write_all(w->fd, (const char *)t, sizeof t);
     }
     if (w->fd != STDOUT_FILENO) close(w->fd);
     if (w->gzip_pid > 0) { int st; waitpid(w->gzip_pid, &st, 0); }   /* let gzip finish before we exit */

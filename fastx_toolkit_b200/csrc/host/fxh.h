@@ -95,6 +95,9 @@ void        fxh_write_record_named(fxh_writer *w, const fxh_batch *b, int64_t i,
                                    int32_t out_len, const char *name, int32_t name_len);
 void        fxh_write_raw(fxh_writer *w, const char *text, size_t bytes, int64_t records);   /* already formatted */
 void        fxh_writer_write_now(fxh_writer *w, const char *text, size_t bytes, int64_t records, int64_t reads);
+int         fxh_writer_frames_gzip(const fxh_writer *w);      /* -z handled by this writer (GPU DEFLATE blocks / stored blocks) */
+void        fxh_writer_write_deflated(fxh_writer *w, const char *blocks, size_t bytes, uint64_t raw_len, uint32_t crc_pure, int64_t records,
+                                      int64_t reads);
 void        fxh_writer_close(fxh_writer *w);
 size_t      fxh_num_output_sequences(const fxh_writer *w);
 size_t      fxh_num_output_reads(const fxh_writer *w);

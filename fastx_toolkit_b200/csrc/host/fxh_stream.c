@@ -53,6 +53,7 @@ typedef struct {
     int64_t n_chunks;           /* valid once reader_done */
     int expect_len;             /* CLIP: read length of chunk 0 (0 = not known yet) */
     int reader_failed; char reader_err[256];
+    int deflate;                /* -z: the chunks leave the GPU as DEFLATE blocks */
     pthread_mutex_t col_mu;
 } fxs_state;
 
@@ -224,6 +225,7 @@ static void *worker_main(void *arg)
     int rc = fxg_text_new(ctx, w->dev, FXS_HEAD + s->chunk_bytes, &tx);
     if (rc != FXG_OK) errx(1, "fxg_text_new failed on GPU %d: %s", w->dev, fxg_strerror(rc));
     fxg_text_set_format(tx, !s->fastq);
+    if (s->deflate && fxg_text_set_deflate(tx, 1) != FXG_OK) errx(1, "fxg_text_set_deflate failed on GPU %d: %s", w->dev, fxg_text_error(tx));
     for (;;) {
         pthread_mutex_lock(&s->mu);
         while (s->n_free_out == 0 && !s->stop) pthread_cond_wait(&s->cv, &s->mu);
@@ -314,13 +316,24 @@ int fxs_run(fxs_job *job, fxh_reader *rd, fxh_writer *wr)
     if (mem_eof && mem_len + 4096 < s->chunk_bytes) s->chunk_bytes = (mem_len + 4096 + 4095) & ~(size_t)4095;   /* small input: one chunk */
     s->read_threads = (int)env_size("FASTX_READ_THREADS", 4, 1);
     if (s->read_threads > 16) s->read_threads = 16;
-    const int ngpu = job->ngpu > 0 ? job->ngpu : 1;
+    int ngpu = job->ngpu > 0 ? job->ngpu : 1;
+    if (ngpu > 1 && s->regular && !getenv("FASTX_GPUS_FORCE")) {
+        /* every extra GPU costs a CUDA context (~0.5 s): worth it from about 4 GB of input per GPU on */
+        struct stat sb;
+        if (fstat(s->fd, &sb) == 0) {
+            const long long per_gpu = 4ll << 30;
+            const int useful = (int)((sb.st_size + per_gpu - 1) / per_gpu);
+            if (useful < ngpu) ngpu = useful < 1 ? 1 : useful;
+        }
+    }
+    if (job->op == FXS_STATS && ngpu != job->ngpu) ngpu = job->ngpu;      /* the caller all-reduces ngpu histograms */
     int W = (int)env_size("FASTX_WORKERS", 3, 1);
     if (W > 8) W = 8;
     int nworkers = ngpu * W;
     if (mem_eof && mem_len <= s->chunk_bytes) nworkers = 1;                 /* one chunk in all */
     if (job->op == FXS_COLLAPSE) nworkers = nworkers > 2 ? 2 : nworkers;    /* the table is one object: adds are serialised */
     const int has_out = job->op == FXS_TRIM || job->op == FXS_FILTER || job->op == FXS_REVCOMP || job->op == FXS_CLIP;
+    s->deflate = has_out && wr && fxh_writer_frames_gzip(wr);
     s->out_cap = has_out ? (FXS_HEAD + s->chunk_bytes) + (FXS_HEAD + s->chunk_bytes) / 4 + 64 : 64;
     const int n_in = 2 * nworkers + 2, n_out = nworkers + 1;
     pthread_mutex_init(&s->mu, NULL); pthread_cond_init(&s->cv, NULL); pthread_mutex_init(&s->col_mu, NULL);
@@ -377,7 +390,11 @@ int fxs_run(fxs_job *job, fxh_reader *rd, fxh_writer *wr)
         if (c->rep.anomaly != 0 || c->rep.n_records == 0) { fallback = 1; fallback_at = c->head; fb_chunk = c; break; }
         if (wr && has_out) {
             const double t1 = fxh_now();
-            fxh_writer_write_now(wr, c->out, (size_t)c->rep.out_bytes, c->rep.n_out_records, s->fastq ? c->rep.n_out_records : c->rep.n_out_reads);
+            if (c->rep.deflated)
+                fxh_writer_write_deflated(wr, c->out, (size_t)c->rep.out_bytes, (uint64_t)c->rep.raw_out_bytes, c->rep.out_crc32_pure, c->rep.n_out_records,
+                                          s->fastq ? c->rep.n_out_records : c->rep.n_out_reads);
+            else
+                fxh_writer_write_now(wr, c->out, (size_t)c->rep.out_bytes, c->rep.n_out_records, s->fastq ? c->rep.n_out_records : c->rep.n_out_reads);
             job->t_write += fxh_now() - t1;
         }
         fxh_reader_account(rd, c->rep.n_records, s->fastq ? c->rep.n_records : c->rep.n_reads, lpr);

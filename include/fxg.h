@@ -329,6 +329,9 @@ typedef struct {
     int64_t clip_class[6];    /* fxg_text_clip_host: reads per FXG_CLIP_* class               */
     int64_t n_reads;          /* sum of get_reads_count() over the records (FASTA "N-COUNT" ids; = n_records for FASTQ) */
     int64_t n_out_reads;      /* the same over the emitted records                            */
+    int64_t raw_out_bytes;    /* bytes of emitted TEXT (= out_bytes unless the chunk left the GPU deflated) */
+    uint32_t out_crc32_pure;  /* deflated chunks: CRC-32 register of that text (init 0, no final xor)       */
+    uint32_t deflated;        /* 1: out_host holds byte-aligned DEFLATE blocks                               */
 } fxg_text_report;
 #define FXG_TEXT_PREFIX     1
 #define FXG_TEXT_EMPTY_SEQ  2
@@ -341,6 +344,11 @@ int         fxg_text_new(fxg_ctx *ctx, int device, size_t max_chunk_bytes, fxg_t
 void        fxg_text_free(fxg_text *t);
 int         fxg_text_run_host(fxg_text *t, int op, const char *text_host, size_t bytes, int q_offset, int a0, int a1,
                               char *out_host, fxg_text_report *rep);
+/* The trimmer / filter decision alone: out_len_host[r] = surviving length of record r or -1; line_start_host (may be NULL)
+ * receives the byte offset of each of the record's 4 lines inside the chunk.  For a caller that keeps the input text and
+ * writes the output from it: 4 to 20 bytes per record come back instead of the whole text. */
+int         fxg_text_decide_host(fxg_text *t, int op, const char *text_host, size_t bytes, int q_offset, int a0, int a1,
+                                 int32_t *out_len_host, uint32_t *line_start_host, fxg_text_report *rep);
 /* fastx_clipper on a chunk of equal-length reads (expect_len = the length of every earlier read, 0 = none yet); other
  * chunks come back as FXG_TEXT_MIXED_LEN because the reference's aligner then depends on earlier reads' bytes. */
 int         fxg_text_clip_host(fxg_text *t, const char *text_host, size_t bytes, int q_offset, const fxg_clip_opts *o,
@@ -358,6 +366,14 @@ int         fxg_text_set_format(fxg_text *t, int fasta);
  * in any order); < 0: the number of rows added so far. */
 int         fxg_text_collapse_host(fxg_text *t, const char *text_host, size_t bytes, int q_offset, fxg_collapser *col, int64_t first_base,
                                    fxg_text_report *rep);
+/* `-z` (src/libfastx/fastx.c:214-248 pipes the text through a forked gzip): with deflate on, the emitted text of every
+ * chunk leaves the GPU as non-final, byte-aligned DEFLATE blocks (dynamic Huffman codes over the literals, one per 64 KB),
+ * so chunks concatenate.  The caller frames them: 10-byte gzip header, the chunks, a final empty stored block
+ * (01 00 00 FF FF), then CRC-32 and ISIZE.  fxg_crc32_concat() chains the chunks' pure CRCs, fxg_crc32_finish() turns the
+ * result into the CRC-32 gzip stores.  Any gunzip yields exactly the text the plain path emits. */
+int         fxg_text_set_deflate(fxg_text *t, int on);
+uint32_t    fxg_crc32_concat(uint32_t crc_pure_a, uint32_t crc_pure_b, uint64_t len_b);
+uint32_t    fxg_crc32_finish(uint32_t crc_pure, uint64_t total_len);
 const char *fxg_text_error(const fxg_text *t);
 int64_t     fxg_text_launches(const fxg_text *t);
 int64_t     fxg_text_numeric_chunks(const fxg_text *t);   /* chunks that went through the numeric-quality form of the path */

@@ -31,6 +31,7 @@ int fxg_text_new(fxg_ctx *ctx, int device, size_t max_chunk_bytes, fxg_text **ou
 }
 void fxg_text_free(fxg_text *t) { free(t); }
 int fxg_text_set_format(fxg_text *t, int fasta) { t->fasta = fasta; return FXG_OK; }
+int fxg_text_set_deflate(fxg_text *t, int on) { (void)t; (void)on; return FXG_OK; }      /* the double emits plain text: the writer stores it */
 const char *fxg_text_error(const fxg_text *t) { (void)t; return "stub"; }
 
 /* identity "op": whole records of the chunk, copied through; the structural checks of K-RECS */

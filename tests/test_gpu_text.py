@@ -303,3 +303,74 @@ def test_text_path_fasta_and_collapser(ctx):
     rep = tq.collapse(fastq_bytes(seq, q2, lens, L), 33, col)
     assert (rep.anomaly, rep.anomaly_record) == (5, 4321)
     col.close(); tq.close()
+
+
+def test_text_path_deflate_blocks(ctx):
+    """fxg_text_set_deflate: the emitted text leaves the GPU as byte-aligned DEFLATE blocks; framed as gzip they must inflate to
+    exactly the plain output, and the chained block CRCs must be the CRC-32 of that text"""
+    import struct
+    import zlib
+    import fastx_toolkit_b200 as F
+    n, L = 40000, 150
+    seq, qual = H.synth_slab(H.SEED_BASE + 16, n, L, H.WITH_N)
+    text = fastq_bytes(seq, qual, None, L, plus_names=True)
+    tp = F.TextPipe(ctx, len(text) + 4096)
+    L_ = F.lib()
+    for op, a0, a1 in ((0, 20, 20), (1, 20, 90), (2, 0, 0), (0, 41, 1)):
+        tp.set_deflate(False)
+        plain, rep0 = tp.run(op, text, 33, a0, a1)
+        tp.set_deflate(True)
+        z, rep = tp.run(op, text, 33, a0, a1)
+        assert rep.anomaly == 0 and rep.n_out_records == rep0.n_out_records and rep.raw_out_bytes == len(plain)
+        if not plain:
+            assert rep.out_bytes == 0
+            continue
+        assert rep.deflated == 1 and rep.out_bytes == len(z) < 0.6 * len(plain)
+        crc = L_.fxg_crc32_finish(rep.out_crc32_pure, len(plain))
+        assert crc == zlib.crc32(plain) & 0xFFFFFFFF
+        gz = b"\x1f\x8b\x08\x00\x00\x00\x00\x00\x00\x03" + z + b"\x01\x00\x00\xff\xff" + struct.pack("<II", crc, len(plain) & 0xFFFFFFFF)
+        import gzip
+        assert gzip.decompress(gz) == plain
+        # two chunks concatenate: blocks end on byte boundaries
+        half = text[: text.index(b"\n@", len(text) // 2) + 1]
+        z1, r1 = tp.run(op, half, 33, a0, a1)
+        z2, r2 = tp.run(op, text[len(half):], 33, a0, a1)
+        c12 = L_.fxg_crc32_concat(r1.out_crc32_pure, r2.out_crc32_pure, r2.raw_out_bytes)
+        assert L_.fxg_crc32_finish(c12, len(plain)) == crc
+        assert zlib.decompress(z1 + z2 + b"\x01\x00\x00\xff\xff", -15) == plain
+    # tiny and skewed inputs: one literal dominates, a single record, every byte value in the names
+    tp.set_deflate(True)
+    odd = b"@" + bytes(range(33, 127)) + b"\nACGT\n+\nIIII\n" + b"@x\n" + b"A" * 150 + b"\n+\n" + b"I" * 150 + b"\n"
+    z, rep = tp.run(2, odd, 33, 0, 0)
+    tp.set_deflate(False)
+    plain, _ = tp.run(2, odd, 33, 0, 0)
+    assert zlib.decompress(z + b"\x01\x00\x00\xff\xff", -15) == plain
+    tp.close()
+
+
+def test_text_path_decisions_only(ctx):
+    """fxg_text_decide_host: the per-record decision and the line table instead of any text"""
+    import ctypes as C
+    import fastx_toolkit_b200 as F
+    n, L = 20000, 100
+    seq, qual = H.synth_slab(H.SEED_BASE + 17, n, L, H.PLAIN)
+    lens = H.ragged(seq, qual, np.random.default_rng(2), min_len=1)
+    text = fastq_bytes(seq, qual, lens, L, plus_names=True)
+    src = np.frombuffer(text, np.uint8)
+    tp = F.TextPipe(ctx, len(text) + 4096)
+    dec, starts = np.empty(n, np.int32), np.empty(4 * n, np.uint32)
+    rep = F.TextReport()
+    for op, a0, a1 in ((0, 20, 20), (1, 20, 80)):
+        rc = tp.L.fxg_text_decide_host(tp.h, op, src.ctypes.data, src.size, 33, a0, a1, dec.ctypes.data, starts.ctypes.data, C.byref(rep))
+        assert rc == 0 and rep.anomaly == 0 and rep.n_records == n
+        if op == 0:
+            exp, _ = H.o_trim(seq, qual, lens, 0, seq.shape[1], 33, a0, a1)
+        else:
+            keep, _ = H.o_filter(seq, qual, lens, 0, seq.shape[1], 33, a0, a1)
+            exp = np.where(keep != 0, lens, -1)
+        assert np.array_equal(dec, exp) and rep.n_out_records == int((exp >= 0).sum())
+        # the line table lets the caller cut the records out of its own copy of the text
+        for r in (0, 1, n // 2, n - 1):
+            s1 = int(starts[4 * r + 1])
+            assert text[int(starts[4 * r])] == ord("@") and text[s1:s1 + int(lens[r])] == seq[r, :lens[r]].tobytes()
+    tp.close()

@@ -34,7 +34,10 @@ def both(tool, args, stdin=None):
 def assert_same(tool, args, stdin=None):
     mine, ref = both(tool, args, stdin)
     assert mine[0] == ref[0], (tool, args, mine[2][-300:], ref[2][-300:])
-    assert mine[1] == ref[1], (tool, args, "stdout differs")
+    if "-z" in args and mine[0] == 0:      # gzip framing differs (GPU DEFLATE blocks vs the reference's gzip child): the payload is the contract
+        assert gzip.decompress(mine[1]) == gzip.decompress(ref[1]), (tool, args, "gunzip payload differs")
+    else:
+        assert mine[1] == ref[1], (tool, args, "stdout differs")
     assert mine[2] == ref[2], (tool, args, mine[2][-300:], ref[2][-300:])
     return ref
 
@@ -238,6 +241,40 @@ def test_output_file_report_stream_and_gzip(tmp_path):
     import time
     time.sleep(0.5)   # the reference does not wait for its gzip child
     assert gzip.open(z1).read() == gzip.open(z2).read()
+
+
+@gpu
+@needs_ref
+def test_gzip_output_is_deflated_on_the_gpu(tmp_path):
+    """-z: the emitted text leaves the GPU as DEFLATE blocks (fxg_deflate.cu), the writer frames the gzip stream; gunzip must
+    give exactly the reference's payload, for several chunk sizes, tools and a host-path tail"""
+    fq = str(tmp_path / "in.fq")
+    synth_fastq(fq, 60000, 150, H.WITH_N)
+    text = open(fq, "rb").read()
+    for env in (dict(), dict(FASTX_CHUNK_BYTES="300000", FASTX_WORKERS="3"), dict(FASTX_CHUNK_BYTES="70000")):
+        os.environ.update(env)
+        try:
+            for tool, args in (("fastq_quality_trimmer", ["-t", "20", "-l", "20"]), ("fastq_quality_filter", ["-q", "20", "-p", "80"]),
+                               ("fastx_reverse_complement", []), ("fastx_clipper", ["-a", "AGATCGGAAGAGC", "-l", "20"])):
+                z1, z2 = str(tmp_path / "mine.gz"), str(tmp_path / "ref.gz")
+                m = run_tool(os.path.join(BIN, tool), args + ["-z", "-i", fq, "-o", z1])
+                r = run_tool(H.ref_tool(tool), args + ["-z", "-i", fq, "-o", z2])
+                assert m[0] == r[0] == 0, m[2][-300:]
+                import time
+                time.sleep(0.3)   # the reference does not wait for its gzip child
+                a, b = gzip.open(z1).read(), gzip.open(z2).read()
+                assert a == b, (tool, env, len(a), len(b))
+                assert os.path.getsize(z1) < 0.62 * len(a), (tool, os.path.getsize(z1), len(a))      # really compressed
+            # stdout, and a file whose last record has no newline (host path writes the tail as a stored block)
+            m = run_tool(os.path.join(BIN, "fastq_quality_trimmer"), ["-t", "20", "-l", "20", "-z"], stdin=text[:-1])
+            r = run_tool(H.ref_tool("fastq_quality_trimmer"), ["-t", "20", "-l", "20", "-z"], stdin=text[:-1])
+            assert m[0] == r[0] == 0 and gzip.decompress(m[1]) == gzip.decompress(r[1])
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+    # the standard tool must accept the stream, too
+    import subprocess
+    assert subprocess.run(["gzip", "-t", z1]).returncode == 0
 
 
 @gpu
