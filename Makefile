@@ -5,7 +5,7 @@ ARCH     := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS  := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Iinclude -Ifastx_toolkit_b200/csrc
 CSRC     := fastx_toolkit_b200/csrc
 LIB      := fastx_toolkit_b200/libfxg.so
-CU       := $(CSRC)/fxg_kernels.cu $(CSRC)/fxg_stats.cu $(CSRC)/fxg_stats3.cu $(CSRC)/fxg_stats4.cu $(CSRC)/fxg_clip.cu $(CSRC)/fxg_collapse.cu $(CSRC)/fxg_text.cu $(CSRC)/fxg_deflate.cu $(CSRC)/fxg_extra.cu $(CSRC)/fxg_barcode.cu $(CSRC)/fxg_pipeline.cu $(CSRC)/fxg_comm.cu $(CSRC)/fxg_dcollapse.cu $(CSRC)/fxg_api.cu
+CU       := $(CSRC)/fxg_kernels.cu $(CSRC)/fxg_stats.cu $(CSRC)/fxg_stats4.cu $(CSRC)/fxg_clip.cu $(CSRC)/fxg_collapse.cu $(CSRC)/fxg_text.cu $(CSRC)/fxg_deflate.cu $(CSRC)/fxg_extra.cu $(CSRC)/fxg_barcode.cu $(CSRC)/fxg_pipeline.cu $(CSRC)/fxg_comm.cu $(CSRC)/fxg_dcollapse.cu $(CSRC)/fxg_api.cu
 HDR      := include/fxg.h include/fxg_synth.h $(CSRC)/fxg_device.cuh $(CSRC)/fxg_kernels.cuh $(CSRC)/fxg_clip_dpx.cuh $(CSRC)/fxg_collapse.cuh $(CSRC)/fxg_comm.h
 
 .PHONY: all lib tools oracle clean ptxas

@@ -124,7 +124,8 @@ def lib():
         "fxg_comm_collectives": (i64, [vp]),
         "fxg_dcollapse_new": (i32, [vp, C.c_int32, C.POINTER(vp)]),
         "fxg_dcollapse_free": (None, [vp]),
-        "fxg_dcollapse_run": (i32, [vp, BP, C.POINTER(i64), C.POINTER(vp), i32, C.POINTER(DCollapseReport)]),
+        "fxg_dcollapse_run": (i32, [vp, BP, C.POINTER(i64), C.POINTER(vp), C.POINTER(vp), i32, C.POINTER(DCollapseReport)]),
+        "fxg_collapse_reserve": (i32, [vp, i64, C.c_int32]),
         "fxg_dcollapse_fetch_local": (i32, [vp, i32, vp, vp, vp, vp, vp]),
         "fxg_dcollapse_fetch_order": (i32, [vp, vp, vp, vp, vp]),
         "fxg_dcollapse_error": (C.c_char_p, [vp]),
@@ -310,7 +311,7 @@ class DCollapser:
         if rc != FXG_OK:
             raise FxgError(rc, self.L.fxg_dcollapse_error(self.h).decode() or self.L.fxg_strerror(rc).decode())
 
-    def run(self, batches, index_bases, weights=None, root=0):
+    def run(self, batches, index_bases, weights=None, root=0, firsts=None):
         """batches: one Batch per local GPU (device slabs); returns DCollapseReport"""
         n = len(batches)
         arr = (Batch * n)(*batches)
@@ -318,8 +319,11 @@ class DCollapser:
         w = None
         if weights is not None:
             w = (C.c_void_p * n)(*[_ptr(x) for x in weights])
+        f = None
+        if firsts is not None:
+            f = (C.c_void_p * n)(*[_ptr(x) for x in firsts])
         rep = DCollapseReport()
-        self._ck(self.L.fxg_dcollapse_run(self.h, arr, bases, w, root, C.byref(rep)))
+        self._ck(self.L.fxg_dcollapse_run(self.h, arr, bases, w, f, root, C.byref(rep)))
         return rep
 
     def fetch_local(self, local_index, out_seq=None, out_len=None, out_count=None, out_first=None, out_hash=None):

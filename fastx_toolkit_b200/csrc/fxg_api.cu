@@ -478,87 +478,29 @@ static int stats_enqueue(fxg_ctx *ctx, const fxg_batch *b, int q_offset, uint64_
     p.hist = (unsigned long long *)hist; p.index_base = index_base; p.counters = ctx->d_counters;
     const int lmax = b->len ? b->stride : b->uniform_len;
     const int words = (lmax + 3) / 4;
-    const int nw_pass = words < ST_MAXW ? words : ST_MAXW;
-    const size_t hist_al = (((size_t)nw_pass * ST_WBLK) + 127) & ~(size_t)127;
     int t_ring, t_g, t_stages, t_ctas;
     env_tune(&t_ring, &t_g, &t_stages, &t_ctas);
-    const int stages = (t_stages > 0 && t_stages <= 2) ? t_stages : 1;
-    // FXG_STATS_V=1 selects the first-generation kernel (k_stats); default: k_stats2 (conflict-free layout),
-    // which needs Q-15 <= 64 so that "0 <= q' < 64" implies the reader's range check
-    const char *ev = getenv("FXG_STATS_V");
-    const int ver = ev ? atoi(ev) : 2;
-    const int warps2 = (t_g == 12 || t_g == 16 || t_g == 20 || t_g == 24) ? t_g : 24;
-    long rfit2 = ((long)MAX_DYN_SMEM - (long)S2_HIST_BYTES - S2_DUMMY_BYTES) / warps2 / (2L * b->stride);
-    if (rfit2 > S2_TILE_READS) rfit2 = S2_TILE_READS;
-    const bool fast2 = ver == 2 && b->qual && !weight && rfit2 >= 4 && t_ring != 0 && q_offset - 15 <= 64 && b->n / rfit2 < (1ll << 31);
-    const int g = (t_g == 1 || t_g == 2 || t_g == 4) ? t_g : 4;     // k_stats: lanes per read; 6*g warps per CTA (measured: g=4 best)
-    const int warps = ST_WARPS * g;
-    long rfit = ((long)MAX_DYN_SMEM - (long)hist_al) / warps / stages / (2L * b->stride);
-    if (rfit > 32 / g) rfit = 32 / g;
-    const bool fast = b->qual && !weight && rfit * g >= 8 && t_ring != 0;
-    // FXG_STATS_V=3: experimental u16-counter / double-buffered kernel (fxg_stats3.cu), same preconditions as k_stats2
-    long rfit3 = ((long)MAX_DYN_SMEM - 98432L) / 24 / (4L * b->stride);
-    if (rfit3 > S2_TILE_READS) rfit3 = S2_TILE_READS;
-    const bool fast3 = ver == 3 && b->qual && !weight && rfit3 >= 4 && t_ring != 0 && q_offset - 15 <= 64 && b->n / rfit3 < (1ll << 31);
-    // FXG_STATS_V=4: lane-per-read kernel (fxg_stats4.cu)
+    // k_stats4 (shared histogram, lane = read, warp pairs per tile buffer) needs qualities, unit weights, a tile of at least 8
+    // reads beside the histogram and Q - 15 <= 64 (so that "0 <= q' < 64" implies the reader's range check); everything else
+    // (FASTA, weights, -Q > 79, very long rows) goes to the global-atomics kernel
     long rfit4 = ((long)MAX_DYN_SMEM - (long)S4_HIST_BYTES - S4_DUMMY_BYTES) / S4_WARPS / (2L * b->stride);
     if (rfit4 > S4_TILE_READS) rfit4 = S4_TILE_READS;
-    const bool fast4 = ver == 4 && b->qual && !weight && rfit4 >= 8 && t_ring != 0 && q_offset - 15 <= 64 && b->n / rfit4 < (1ll << 31);
+    const bool fast4 = b->qual && !weight && rfit4 >= 8 && t_ring != 0 && q_offset - 15 <= 64 && b->n / rfit4 < (1ll << 31);
     if (fast4) {
-        p.tile_reads = (int)rfit4;
-        { const char *ep = getenv("FXG_STATS_PAIR"); p.stages = (ep && atoi(ep) == 1) ? 1 : 2; }      // 2: warp pairs share a tile buffer
-        if (getenv("FXG_STATS_NOBFAST")) p.stages |= 4;                                                 // A/B switch: masked B region only
+        p.tile_reads = (int)rfit4; p.stages = 2;
         const uint32_t smem = (uint32_t)((size_t)S4_HIST_BYTES + S4_DUMMY_BYTES + (size_t)S4_WARPS * 2 * b->stride * rfit4);
         const int64_t ntiles = (b->n + rfit4 - 1) / rfit4;
         int64_t grid = ctx->sm_count;
         const int64_t need = (ntiles + S4_WARPS - 1) / S4_WARPS;
         if (grid > need) grid = need;
-        for (int w0 = 0; w0 < words; w0 += ST_MAXW) {
+        for (int w0 = 0; w0 < words; w0 += ST_MAXW) {     // reads longer than 160 bases: one pass per 160 cycles
             p.w0 = w0; p.nw = (words - w0 < ST_MAXW) ? (words - w0) : ST_MAXW;
             CK(ctx, launch_stats4(p, (int)grid, smem, st));
             ctx->launches++;
         }
-    } else
-    if (fast3) {
-        p.tile_reads = (int)rfit3; p.stages = 2;
-        const uint32_t smem = (uint32_t)(98432u + (size_t)24 * 4 * b->stride * rfit3);
-        const int64_t ntiles = (b->n + rfit3 - 1) / rfit3;
-        int64_t grid = ctx->sm_count;
-        const int64_t need = (ntiles + 23) / 24;
-        if (grid > need) grid = need;
-        for (int w0 = 0; w0 < words; w0 += ST_MAXW) {
-            p.w0 = w0; p.nw = (words - w0 < ST_MAXW) ? (words - w0) : ST_MAXW;
-            CK(ctx, launch_stats3(p, (int)grid, smem, st));
-            ctx->launches++;
-        }
-    } else if (fast2) {
-        p.tile_reads = (int)rfit2;
-        { const char *eb = getenv("FXG_STATS_B"); p.stages = eb ? atoi(eb) : 0; }     // B scheme (see launch_stats2): masked blocks by default
-        const uint32_t smem = (uint32_t)((size_t)S2_HIST_BYTES + S2_DUMMY_BYTES + (size_t)warps2 * 2 * b->stride * rfit2);
-        const int64_t ntiles = (b->n + rfit2 - 1) / rfit2;
-        int64_t grid = ctx->sm_count;
-        const int64_t need = (ntiles + warps2 - 1) / warps2;
-        if (grid > need) grid = need;
-        for (int w0 = 0; w0 < words; w0 += ST_MAXW) {     // reads longer than 160 bases: one pass per 160 cycles
-            p.w0 = w0; p.nw = (words - w0 < ST_MAXW) ? (words - w0) : ST_MAXW;
-            CK(ctx, launch_stats2(p, warps2, (int)grid, smem, st));
-            ctx->launches++;
-        }
-    } else if (!fast) {
+    } else {
         CK(ctx, launch_stats_simple(p, ctx->sm_count, st));
         ctx->launches++;
-    } else {
-        p.tile_reads = (int)rfit; p.stages = stages;
-        const uint32_t smem = (uint32_t)(hist_al + (size_t)warps * stages * 2 * b->stride * rfit);
-        const int64_t ntiles = (b->n + rfit - 1) / rfit;
-        int64_t grid = ctx->sm_count;
-        const int64_t need = (ntiles + warps - 1) / warps;
-        if (grid > need) grid = need;
-        for (int w0 = 0; w0 < words; w0 += nw_pass) {     // reads longer than 160 bases: one pass per 160 cycles
-            p.w0 = w0; p.nw = (words - w0 < nw_pass) ? (words - w0) : nw_pass;
-            CK(ctx, launch_stats(p, g, (int)grid, smem, st));
-            ctx->launches++;
-        }
     }
     ctx->report.n_in += b->n;
     return FXG_OK;

@@ -465,6 +465,13 @@ static int collapse_reserve(fxg_collapser *c, int64_t rows, int32_t stride)
     return FXG_OK;
 }
 
+extern "C" int fxg_collapse_reserve(fxg_collapser *c, int64_t rows, int32_t stride)
+{
+    if (!c || stride < 0 || (stride & 15)) return FXG_ERR_ARG;
+    CKO(c, cudaSetDevice(c->device));
+    return collapse_reserve(c, rows > c->cap ? rows : c->cap, stride > c->stride ? stride : c->stride);
+}
+
 // Append rows (device or host memory — cudaMemcpyDefault) and insert them.  weight/first: see fxg.h.
 extern "C" int fxg_collapse_add(fxg_collapser *c, const fxg_batch *b, const int32_t *weight, const int64_t *first, int64_t index_base)
 {

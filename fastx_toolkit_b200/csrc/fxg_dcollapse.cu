@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(256) k_route_count(const uint8_t *seq, const i
 
 // pass 2: a position in the owner's segment of the send slab for every read, and its meta record
 __global__ void __launch_bounds__(256) k_route_place(const uint8_t *owner, const int32_t *len, int uniform_len, const int32_t *weight,
-                                                     int64_t n, int64_t index_base, unsigned long long *cursor, uint32_t *pos, RowMeta *meta)
+                                                     const int64_t *first, int64_t n, int64_t index_base, unsigned long long *cursor, uint32_t *pos,
+                                                     RowMeta *meta)
 {
     for (int64_t t0 = (int64_t)blockIdx.x * blockDim.x; t0 < n; t0 += (int64_t)gridDim.x * blockDim.x) {
         const int64_t t = t0 + threadIdx.x;
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(256) k_route_place(const uint8_t *owner, const
         const uint32_t p = (uint32_t)(base + __popc(peers & ((1u << lane) - 1u)));
         pos[t] = p;
         RowMeta m;
-        m.first = index_base + t;
+        m.first = first ? first[t] : index_base + t;
         m.weight = weight ? (uint32_t)__ldg(weight + t) : 1u;
         m.len = len ? __ldg(len + t) : uniform_len;
         meta[p] = m;
@@ -220,10 +221,10 @@ extern "C" int fxg_dcollapse_new(fxg_comm *comm, int32_t stride, fxg_dcollapse *
 }
 
 // One collapse of the reads resident on the local GPUs: batches[i] (DEVICE slabs on local GPU i, seq only; len == NULL for a
-// uniform length) holds reads whose global indices are index_base[i] + row; weight_dev[i] (or weight_dev == NULL) as in
-// fxg_collapse_add.  On return every owner holds its uniques, and the root's process holds the output order.
+// uniform length) holds reads whose global indices are index_base[i] + row, or first_dev[i][row] when first_dev (and
+// first_dev[i]) is given; weight_dev[i] (or weight_dev == NULL) as in fxg_collapse_add.  On return every owner holds its uniques, and the root's process holds the output order.
 extern "C" int fxg_dcollapse_run(fxg_dcollapse *d, const fxg_batch *batches, const int64_t *index_base, const int32_t *const *weight_dev,
-                                 int root, fxg_dcollapse_report *rep)
+                                 const int64_t *const *first_dev, int root, fxg_dcollapse_report *rep)
 {
     if (!d || !batches || !index_base || root < 0 || root >= d->G) return FXG_ERR_ARG;
     fxg_comm *c = d->comm;
@@ -301,7 +302,7 @@ extern "C" int fxg_dcollapse_run(fxg_dcollapse *d, const fxg_batch *batches, con
         CKD(d, cudaMemcpyAsync(cursor, h_cur, sizeof(unsigned long long) * (size_t)G, cudaMemcpyHostToDevice, st));
         if (b->n > 0) {
             k_route_place<<<dgrid((uint64_t)b->n), 256, 0, st>>>((const uint8_t *)l->owner.p, b->len, b->uniform_len,
-                                                                 weight_dev ? weight_dev[i] : NULL, b->n, index_base[i], cursor,
+                                                                 weight_dev ? weight_dev[i] : NULL, first_dev ? first_dev[i] : NULL, b->n, index_base[i], cursor,
                                                                  (uint32_t *)l->pos.p, (RowMeta *)l->smeta.p);
             k_route_rows<<<dgrid((uint64_t)b->n * (S >> 4)), 256, 0, st>>>(b->seq, (const uint32_t *)l->pos.p, d->stride, b->n, (uint8_t *)l->srows.p);
             CKD(d, cudaGetLastError());
@@ -334,7 +335,7 @@ extern "C" int fxg_dcollapse_run(fxg_dcollapse *d, const fxg_batch *batches, con
         CKD(d, cudaMemsetAsync(l->slots.p, 0, ns * 8, st)); CKD(d, cudaMemsetAsync(l->count.p, 0, ns * 8, st));
         CKD(d, cudaMemsetAsync(l->firsts.p, 0xFF, ns * 8, st));
         unsigned long long *cnt = (unsigned long long *)l->small.p;      // [0] = uniques, [1] = first bad read (CNT_FIRST_BAD), [2] = bound of the first indices put in here
-        const unsigned long long init[3] = { 0ull, ~0ull, (unsigned long long)(index_base[i] + batches[i].n) };
+        const unsigned long long init[3] = { 0ull, ~0ull, (first_dev && first_dev[i]) ? ~0ull : (unsigned long long)(index_base[i] + batches[i].n) };
         CKD(d, cudaMemcpyAsync(cnt, init, sizeof init, cudaMemcpyHostToDevice, st));
         if (l->m > 0) {
             DedupParams p;
@@ -393,7 +394,7 @@ extern "C" int fxg_dcollapse_run(fxg_dcollapse *d, const fxg_batch *batches, con
         CKD(d, cudaSetDevice(l->device));
         // every first index is below the largest index_base + n of the job: that bound sizes the radix passes of the first sort
         int rc = fxg_order_impl((const uint64_t *)d->g_hash.p, (const uint64_t *)d->g_first.p, (const uint64_t *)d->g_count.p, (uint32_t)d->U_total,
-                                (uint32_t *)d->g_perm.p, (uint64_t)max_first, c->streams[d->root_local], d->err, sizeof d->err, &d->launches);
+                                (uint32_t *)d->g_perm.p, max_first == ~0ull ? 0 : (uint64_t)max_first, c->streams[d->root_local], d->err, sizeof d->err, &d->launches);
         if (rc) return rc;
     }
     for (int i = 0; i < NL; i++) { CKD(d, cudaSetDevice(d->loc[i].device)); CKD(d, cudaEventRecord(d->loc[i].ev[5], c->streams[i])); }

@@ -72,21 +72,10 @@ struct SynthParams {
     int32_t kind, q_offset;
 };
 
-// ---- K-STATS (fxg_stats.cu) ------------------------------------------------------------------------
-// shared-memory histogram geometry: [word w][byte k][nuc A,C,G,T][q' 0..63] u32 counters; a word block
-// is padded by 36 bytes so that lanes working on consecutive words with equal q' hit distinct banks
-constexpr int ST_WARPS = 6;
+// ---- K-STATS (fxg_stats4.cu; global-atomics fallback in fxg_stats.cu) ---------------------------------------------------
 constexpr int ST_QWIN = 64;                       // q' = q+15 in [0,64) lives in shared memory
-constexpr int ST_KBLK = 4 * ST_QWIN * 4;          // bytes per (word, byte k): 4 nucs x 64 x u32 = 1024
-constexpr int ST_WBLK = 4 * ST_KBLK + 36;         // bytes per word block
 constexpr int ST_MAXW = 40;                       // words (4 cycles each) per pass: 160 cycles
-// second-generation layout (k_stats2): [bin = nuc*64 + q'][column 40k + w] u32 — bank = (8k + w) mod 32
-constexpr int S2_PITCH = 4 * ST_MAXW * 4;         // bytes per bin: 160 columns x u32 = 640
-constexpr int S2_HIST_BYTES = 4 * ST_QWIN * S2_PITCH;   // 256 bins: 163 840 bytes
-constexpr int S2_DUMMY_BYTES = 128;               // 32 scratch counters behind the histogram (masked-off increments land here)
-constexpr int S2_TILE_READS = 8;                  // reads per warp tile (4 lanes per read)
-
-// third layout (k_stats4, fxg_stats4.cu): lane = read; a bin owns 96 words: 64 words of u16 pairs for cycles 0..127 (word
+// k_stats4: lane = read; a bin owns 96 words: 64 words of u16 pairs for cycles 0..127 (word
 // 32*(wi>>1) + 8k + c, half wi&1, for window word w = 4c + wi and byte k) + 32 full words for cycles 128..159 (64 + 4(w-32) + k)
 constexpr int S4_PITCH = 96 * 4;                  // bytes per bin; 96 = 0 (mod 32): the bank of a counter never depends on the data
 constexpr int S4_HIST_BYTES = 4 * ST_QWIN * S4_PITCH;   // 256 bins: 98 304 bytes
@@ -159,8 +148,6 @@ struct BarcodeParams {
 
 cudaError_t launch_barcode(const BarcodeParams &p, int sm_count, cudaStream_t st);
 
-cudaError_t launch_stats(const StatsParams &p, int g, int grid, uint32_t smem_bytes, cudaStream_t st);
-cudaError_t launch_stats2(const StatsParams &p, int warps, int grid, uint32_t smem_bytes, cudaStream_t st);
 // ---- fused pipelines (fxg_pipeline.cu) ----
 size_t pipe_scan_tmp_bytes(int64_t n);
 cudaError_t launch_pipe_flags_scan(const int32_t *new_len, const uint8_t *keep, int64_t n, int32_t *flags, int32_t *pos, void *tmp, size_t tmp_bytes,
@@ -174,7 +161,6 @@ cudaError_t launch_pipe_keep_all(int64_t n, const int32_t *cur_len, int uniform_
                                  cudaStream_t st);
 cudaError_t launch_pipe_scatter(int64_t n, const int32_t *flags, const int32_t *new_len, const int32_t *cur_len, int uniform_len, const int32_t *cur_idx,
                                 int32_t *final_len, int sm_count, cudaStream_t st);
-cudaError_t launch_stats3(const StatsParams &p, int grid, uint32_t smem_bytes, cudaStream_t st);   // experimental (fxg_stats3.cu)
 cudaError_t launch_stats_simple(const StatsParams &p, int sm_count, cudaStream_t st);
 cudaError_t launch_clip(const ClipParams &p, int sm_count, int max_width, cudaStream_t st);
 cudaError_t stats_set_smem_attrs();

@@ -1,9 +1,9 @@
-// fxg_stats4.cu — K-STATS, third layout (`k_stats4`): lane = read, 32-read warp tiles.
+// fxg_stats4.cu — K-STATS (`k_stats4`): lane = read, 32-read tiles, two warps per tile.
 // Accumulates hist[cycle][nuc][q+15] of src/fastx_quality_stats/fastx_quality_stats.c:166-216 (`read_file`).
 //
-// Why another kernel: k_stats2 (4 lanes per read, 8-read tiles) is bound by instruction issue — per tile it pays ~160
-// warp-instructions of prologue and TMA issue for only 1 200 bases, and the six words past the 32-word superblock cost
-// 3.8x more per word than the rest (profiles/r01_ncu_stats_full.txt).  Here a lane owns a whole read, so
+// Round 1's kernel (4 lanes per read, 8-read tiles; profiles/r01_ncu_stats_full.txt) was bound by instruction issue — per
+// tile it paid ~160 warp-instructions of prologue and TMA issue for only 1 200 bases, and the six words past its 32-word
+// superblock cost 3.8x more per word than the rest.  Here a lane owns a whole read, so
 //   * the per-tile cost (barrier wait, lengths, TMA issue by lane 0) is spread over 32 reads instead of 8,
 //   * every lane is busy in every step of the A region (words 0..31 = eight 16-byte chunks, read with LDS.128) and of the
 //     B region (words 32..39), with no cross-lane reduction anywhere,
@@ -253,10 +253,15 @@ __global__ void __launch_bounds__(TILES * PAIR * 32, 1) k_stats4(const __grid_co
                 }
             } else {
                 // some read of the tile ends inside the A region: every word carries its count of valid bytes
+                // short reads: the rotation runs over the smallest power of two of chunks that covers the longest read of the
+                // tile (several lanes then share a counter: a same-address RED costs wavefronts, not instructions)
                 const int tmax = (__reduce_max_sync(0xFFFFFFFFu, Lp) + 15) >> 4;     // chunks any lane still needs (warp uniform)
                 if (tmax > 0) {
-                    for (int t = tbeg; t < tbeg + T0; t++) {
-                        const uint32_t c = (uint32_t)((t + r_l) & 7);
+                    const int nc = tmax > 4 ? 8 : tmax > 2 ? 4 : tmax > 1 ? 2 : 1;
+                    const int per = nc >= PAIR ? nc / PAIR : 1;                      // chunk steps per warp of the pair
+                    const int t_lo = nc >= PAIR ? half * per : 0, t_hi = nc >= PAIR ? t_lo + per : (half == 0 ? 1 : 0);
+                    for (int t = t_lo; t < t_hi; t++) {
+                        const uint32_t c = (uint32_t)((t + r_l) & (nc - 1));
                         const int vbc = Lp - 16 * (int)c;                            // valid bytes from this chunk on
                         if (!__any_sync(0xFFFFFFFFu, vbc > 0)) continue;
                         uint4 s4 = make_uint4(0, 0, 0, 0), q4 = make_uint4(0, 0, 0, 0);
@@ -286,7 +291,7 @@ __global__ void __launch_bounds__(TILES * PAIR * 32, 1) k_stats4(const __grid_co
             // ---- B region: words 32..39 (the read's last bases included) ----
             {
                 const int LpB = Lp - 128;
-                const bool b_full4 = (P.stages & 4) == 0 && __all_sync(0xFFFFFFFFu, LpB >= 16);      // every read holds words 32..35 complete
+                const bool b_full4 = __all_sync(0xFFFFFFFFu, LpB >= 16);      // every read holds words 32..35 complete
                 if (b_full4) {
                     // words 32..35 without masks: lane l visits word (l>>2 + a) & 3 — two lanes per counter (same address:
                     // two wavefronts per RED), a fraction of the masked steps' instructions
@@ -365,13 +370,9 @@ __global__ void __launch_bounds__(TILES * PAIR * 32, 1) k_stats4(const __grid_co
 
 cudaError_t launch_stats4(const StatsParams &p, int grid, uint32_t smem_bytes, cudaStream_t st)
 {
-    if ((p.stages & 3) == 2) {          // warp pairs
-        cudaFuncSetAttribute(k_stats4<S4_WARPS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
-        k_stats4<S4_WARPS, 2><<<grid, S4_WARPS * 64, smem_bytes, st>>>(p);
-    } else {
-        cudaFuncSetAttribute(k_stats4<S4_WARPS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
-        k_stats4<S4_WARPS, 1><<<grid, S4_WARPS * 32, smem_bytes, st>>>(p);
-    }
+    // two warps per tile buffer: 24 warps hide the latencies that 12 do not (13.7 -> 13.9-14.5 G reads/s at 150 bp, round 2)
+    cudaFuncSetAttribute(k_stats4<S4_WARPS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+    k_stats4<S4_WARPS, 2><<<grid, S4_WARPS * 64, smem_bytes, st>>>(p);
     return cudaGetLastError();
 }
 

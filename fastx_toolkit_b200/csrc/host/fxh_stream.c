@@ -54,7 +54,7 @@ typedef struct {
     int expect_len;             /* CLIP: read length of chunk 0 (0 = not known yet) */
     int reader_failed; char reader_err[256];
     int deflate;                /* -z: the chunks leave the GPU as DEFLATE blocks */
-    pthread_mutex_t col_mu;
+    pthread_mutex_t col_mu[64];
 } fxs_state;
 
 typedef struct { fxs_state *s; int index, dev; pthread_t th; int started; } fxs_worker;
@@ -258,9 +258,9 @@ static void *worker_main(void *arg)
             c->rc = fxg_text_stats_host(tx, text, c->len, s->q_offset, job->hist_dev[w->dev - job->first_dev], job->max_cycles, &c->rep);
             break;
         case FXS_COLLAPSE:
-            pthread_mutex_lock(&s->col_mu);
-            c->rc = fxg_text_collapse_host(tx, text, c->len, s->q_offset, job->collapser, c->seq << 32, &c->rep);
-            pthread_mutex_unlock(&s->col_mu);
+            pthread_mutex_lock(&s->col_mu[w->dev - job->first_dev]);
+            c->rc = fxg_text_collapse_host(tx, text, c->len, s->q_offset, job->collapsers[w->dev - job->first_dev], c->seq << 32, &c->rep);
+            pthread_mutex_unlock(&s->col_mu[w->dev - job->first_dev]);
             break;
         default: c->rc = FXG_ERR_ARG;
         }
@@ -326,17 +326,18 @@ int fxs_run(fxs_job *job, fxh_reader *rd, fxh_writer *wr)
             if (useful < ngpu) ngpu = useful < 1 ? 1 : useful;
         }
     }
-    if (job->op == FXS_STATS && ngpu != job->ngpu) ngpu = job->ngpu;      /* the caller all-reduces ngpu histograms */
+    if ((job->op == FXS_STATS || job->op == FXS_COLLAPSE) && ngpu != job->ngpu) ngpu = job->ngpu;      /* the caller merges ngpu partial results */
     int W = (int)env_size("FASTX_WORKERS", 3, 1);
     if (W > 8) W = 8;
     int nworkers = ngpu * W;
     if (mem_eof && mem_len <= s->chunk_bytes) nworkers = 1;                 /* one chunk in all */
-    if (job->op == FXS_COLLAPSE) nworkers = nworkers > 2 ? 2 : nworkers;    /* the table is one object: adds are serialised */
+    if (job->op == FXS_COLLAPSE && nworkers > 2 * ngpu) nworkers = 2 * ngpu;  /* a table is one object: adds to it are serialised */
     const int has_out = job->op == FXS_TRIM || job->op == FXS_FILTER || job->op == FXS_REVCOMP || job->op == FXS_CLIP;
     s->deflate = has_out && wr && fxh_writer_frames_gzip(wr);
     s->out_cap = has_out ? (FXS_HEAD + s->chunk_bytes) + (FXS_HEAD + s->chunk_bytes) / 4 + 64 : 64;
     const int n_in = 2 * nworkers + 2, n_out = nworkers + 1;
-    pthread_mutex_init(&s->mu, NULL); pthread_cond_init(&s->cv, NULL); pthread_mutex_init(&s->col_mu, NULL);
+    pthread_mutex_init(&s->mu, NULL); pthread_cond_init(&s->cv, NULL);
+    for (int g = 0; g < 64; g++) pthread_mutex_init(&s->col_mu[g], NULL);
     s->done_cap = n_in + 2;
     s->done = (fxs_chunk **)calloc((size_t)s->done_cap, sizeof(fxs_chunk *));
     s->free_out = (char **)calloc((size_t)n_out, sizeof(char *));
@@ -458,7 +459,8 @@ int fxs_run(fxs_job *job, fxh_reader *rd, fxh_writer *wr)
     for (int i = 0; i < n_in; i++) { fxg_free_pinned(chunks[i].buf); free(chunks[i].lastseq); }
     for (int i = 0; i < n_out; i++) fxg_free_pinned(outs[i]);
     free(chunks); free(outs); free(workers); free(s->done); free(s->free_out);
-    pthread_mutex_destroy(&s->mu); pthread_cond_destroy(&s->cv); pthread_mutex_destroy(&s->col_mu);
+    pthread_mutex_destroy(&s->mu); pthread_cond_destroy(&s->cv);
+    for (int g = 0; g < 64; g++) pthread_mutex_destroy(&s->col_mu[g]);
     job->t_total = fxh_now() - t0;
     if (getenv("FASTX_TIMING"))
         fprintf(stderr, "[timing] stream engine: %lld chunks, %lld records, %d workers on %d GPU(s), total %.3f s (waiting for the GPU path %.3f s, write(2) %.3f s)%s\n",

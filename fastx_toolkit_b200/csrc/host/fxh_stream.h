@@ -23,7 +23,7 @@ typedef struct {
     int ngpu, first_dev;            /* GPUs first_dev .. first_dev + ngpu - 1                                          */
     uint64_t **hist_dev;            /* STATS: one device histogram per GPU (zeroed by the caller), max_cycles cycles   */
     int32_t max_cycles;
-    fxg_collapser *collapser;       /* COLLAPSE (one GPU)                                                              */
+    fxg_collapser **collapsers;     /* COLLAPSE: one count map per GPU (several GPUs: merged afterwards, fxg_dcollapse_*)     */
     /* results */
     int64_t records, reads;         /* consumed by the engine                                                          */
     int64_t chunks, numeric_chunks; /* text chunks pushed through the GPU path / of them with numeric qualities        */

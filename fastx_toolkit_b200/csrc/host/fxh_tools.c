@@ -321,14 +321,25 @@ static int main_collapser(int argc, char **argv)
         out = fopen(fxh_output_filename(), "w");
         if (!out) errx(1, "Failed to create output file (%s)", fxh_output_filename());
     }
-    fxg_ctx *ctx = fxh_gpu_open();
-    /* the count map lives on the GPU from the first read on (fastx_collapser.cpp:112-114); it grows as the input arrives */
-    fxg_collapser *col = NULL;
-    int rc = fxg_collapse_new(first_gpu(), 1 << 20, 64, &col);
-    if (rc != FXG_OK) errx(1, "fxg_collapse_new failed: %s", fxg_strerror(rc));
+    /* the count map lives on the GPU(s) from the first read on (fastx_collapser.cpp:112-114) and grows as the input arrives.
+     * FASTX_GPUS=N: every GPU dedups the chunks it gets; afterwards the partial maps are merged by owner = std::hash mod N
+     * over NVLink and the output order is computed once (fxg_dcollapse_*). */
+    const int ngpu = fxh_gpu_count(), dev0 = first_gpu();
+    fxg_ctx *ctxs[64];
+    fxg_collapser *cols[64];
+    int devs[64];
+    for (int g = 0; g < ngpu; g++) {
+        devs[g] = dev0 + g;
+        ctxs[g] = fxh_gpu_open_dev(devs[g]);
+        int rc0 = fxg_collapse_new(devs[g], 1 << 20, 64, &cols[g]);
+        if (rc0 != FXG_OK) errx(1, "fxg_collapse_new failed: %s", fxg_strerror(rc0));
+    }
+    fxg_ctx *ctx = ctxs[0];
+    fxg_collapser *col = cols[0];
+    int rc;
     fxs_job job;
     memset(&job, 0, sizeof job);
-    job.op = FXS_COLLAPSE; job.ngpu = 1; job.first_dev = first_gpu(); job.collapser = col;
+    job.op = FXS_COLLAPSE; job.ngpu = ngpu; job.first_dev = dev0; job.collapsers = cols;
     (void)fxs_run(&job, rd, NULL);
     /* whatever the GPU text path handed back: record by record, validated as the reader validates (K-VALIDATE) */
     int64_t host_rows = 0;
@@ -344,16 +355,80 @@ static int main_collapser(int argc, char **argv)
         host_rows += b->n;
     }
     int64_t U = 0, bad = -1;
-    rc = fxg_collapse_finish(col, 1, &U, &bad);
-    if (rc != FXG_OK) errx(1, "fxg_collapse_finish failed: %s (%s)", fxg_strerror(rc), fxg_collapse_error(col));
-    if (bad >= 0) errx(1, "internal error: the count map rejected a read the validation had accepted (index %lld)", (long long)bad);
-    const int32_t stride = fxg_collapse_stride(col);
-    uint8_t *useq = (uint8_t *)malloc((size_t)(U > 0 ? U : 1) * (size_t)stride);
-    int32_t *ulen = (int32_t *)malloc((size_t)(U > 0 ? U : 1) * sizeof(int32_t));
-    uint64_t *ucnt = (uint64_t *)malloc((size_t)(U > 0 ? U : 1) * sizeof(uint64_t));
-    if (!useq || !ulen || !ucnt) err(1, "out of memory");
-    rc = fxg_collapse_fetch(col, useq, ulen, ucnt, NULL, NULL);
-    if (rc != FXG_OK) errx(1, "fxg_collapse_fetch failed: %s (%s)", fxg_strerror(rc), fxg_collapse_error(col));
+    int32_t stride = 0;
+    uint8_t *useq = NULL; int32_t *ulen = NULL; uint64_t *ucnt = NULL;
+    if (ngpu == 1) {
+        rc = fxg_collapse_finish(col, 1, &U, &bad);
+        if (rc != FXG_OK) errx(1, "fxg_collapse_finish failed: %s (%s)", fxg_strerror(rc), fxg_collapse_error(col));
+        if (bad >= 0) errx(1, "internal error: the count map rejected a read the validation had accepted (index %lld)", (long long)bad);
+        stride = fxg_collapse_stride(col);
+        useq = (uint8_t *)malloc((size_t)(U > 0 ? U : 1) * (size_t)stride);
+        ulen = (int32_t *)malloc((size_t)(U > 0 ? U : 1) * sizeof(int32_t));
+        ucnt = (uint64_t *)malloc((size_t)(U > 0 ? U : 1) * sizeof(uint64_t));
+        if (!useq || !ulen || !ucnt) err(1, "out of memory");
+        rc = fxg_collapse_fetch(col, useq, ulen, ucnt, NULL, NULL);
+        if (rc != FXG_OK) errx(1, "fxg_collapse_fetch failed: %s (%s)", fxg_strerror(rc), fxg_collapse_error(col));
+    } else {
+        /* the partial maps' uniques (rows, lengths, counts, first indices) stay in HBM and go through the owner exchange */
+        int64_t ul[64];
+        fxg_batch pb[64]; int64_t base[64];
+        const int32_t *wdev[64]; const int64_t *fdev[64];
+        for (int g = 0; g < ngpu; g++) {
+            rc = fxg_collapse_finish(cols[g], 0, &ul[g], &bad);
+            if (rc != FXG_OK) errx(1, "fxg_collapse_finish failed: %s (%s)", fxg_strerror(rc), fxg_collapse_error(cols[g]));
+            if (fxg_collapse_stride(cols[g]) > stride) stride = fxg_collapse_stride(cols[g]);
+        }
+        for (int g = 0; g < ngpu; g++) {
+            const size_t u = (size_t)(ul[g] > 0 ? ul[g] : 1);
+            if ((rc = fxg_collapse_reserve(cols[g], 0, stride)) != FXG_OK) errx(1, "fxg_collapse_reserve failed: %s", fxg_collapse_error(cols[g]));
+            uint8_t *d_rows = (uint8_t *)fxg_alloc_device(ctxs[g], u * (size_t)stride);
+            int32_t *d_len = (int32_t *)fxg_alloc_device(ctxs[g], u * 4), *d_w = (int32_t *)fxg_alloc_device(ctxs[g], u * 4);
+            uint64_t *d_cnt = (uint64_t *)fxg_alloc_device(ctxs[g], u * 8);
+            int64_t *d_first = (int64_t *)fxg_alloc_device(ctxs[g], u * 8);
+            if (!d_rows || !d_len || !d_w || !d_cnt || !d_first) errx(1, "out of device memory on GPU %d", devs[g]);
+            rc = fxg_collapse_fetch(cols[g], d_rows, d_len, d_cnt, d_first, NULL);
+            if (rc != FXG_OK) errx(1, "fxg_collapse_fetch failed: %s (%s)", fxg_strerror(rc), fxg_collapse_error(cols[g]));
+            /* counts as the 32-bit weights the exchange carries */
+            uint64_t *hc = (uint64_t *)malloc(u * 8); int32_t *hw = (int32_t *)malloc(u * 4);
+            if (!hc || !hw) err(1, "out of memory");
+            fxh_gpu_check(ctxs[g], fxg_memcpy_d2h(ctxs[g], hc, d_cnt, (size_t)ul[g] * 8), "fxg_memcpy_d2h");
+            for (int64_t k = 0; k < ul[g]; k++) hw[k] = (int32_t)hc[k];
+            fxh_gpu_check(ctxs[g], fxg_memcpy_h2d(ctxs[g], d_w, hw, (size_t)ul[g] * 4), "fxg_memcpy_h2d");
+            free(hc); free(hw);
+            fxg_collapse_free(cols[g]); cols[g] = NULL;
+            pb[g].seq = d_rows; pb[g].qual = NULL; pb[g].len = d_len; pb[g].uniform_len = 0; pb[g].stride = stride; pb[g].n = ul[g];
+            base[g] = 0; wdev[g] = d_w; fdev[g] = d_first;
+        }
+        fxg_comm *comm = NULL;
+        if ((rc = fxg_comm_init_all(ngpu, devs, &comm)) != FXG_OK) errx(1, "fxg_comm_init_all failed: %s (%s)", fxg_strerror(rc), fxg_comm_error(NULL));
+        fxg_dcollapse *dc = NULL;
+        if ((rc = fxg_dcollapse_new(comm, stride, &dc)) != FXG_OK) errx(1, "fxg_dcollapse_new failed: %s", fxg_strerror(rc));
+        fxg_dcollapse_report drep;
+        if ((rc = fxg_dcollapse_run(dc, pb, base, wdev, fdev, 0, &drep)) != FXG_OK) errx(1, "fxg_dcollapse_run failed: %s (%s)", fxg_strerror(rc), fxg_dcollapse_error(dc));
+        U = drep.n_unique;
+        const size_t u = (size_t)(U > 0 ? U : 1);
+        int32_t *powner = (int32_t *)malloc(u * 4); uint32_t *pidx = (uint32_t *)malloc(u * 4);
+        ucnt = (uint64_t *)malloc(u * 8);
+        useq = (uint8_t *)malloc(u * (size_t)stride);
+        ulen = (int32_t *)malloc(u * sizeof(int32_t));
+        if (!powner || !pidx || !ucnt || !useq || !ulen) err(1, "out of memory");
+        if ((rc = fxg_dcollapse_fetch_order(dc, powner, pidx, NULL, ucnt)) != FXG_OK) errx(1, "fxg_dcollapse_fetch_order failed: %s", fxg_dcollapse_error(dc));
+        /* every owner's rows come back over its own PCIe link; the output is gathered in the order the root computed */
+        uint8_t *orow[64]; int32_t *olen[64];
+        for (int g = 0; g < ngpu; g++) {
+            orow[g] = (uint8_t *)malloc(u * (size_t)stride); olen[g] = (int32_t *)malloc(u * 4);
+            if (!orow[g] || !olen[g]) err(1, "out of memory");
+            if ((rc = fxg_dcollapse_fetch_local(dc, g, orow[g], olen[g], NULL, NULL, NULL)) != FXG_OK) errx(1, "fxg_dcollapse_fetch_local failed: %s", fxg_dcollapse_error(dc));
+        }
+        for (int64_t k = 0; k < U; k++) {
+            memcpy(useq + (size_t)k * stride, orow[powner[k]] + (size_t)pidx[k] * stride, (size_t)stride);
+            ulen[k] = olen[powner[k]][pidx[k]];
+        }
+        for (int g = 0; g < ngpu; g++) { free(orow[g]); free(olen[g]); }
+        free(powner); free(pidx);
+        fxg_dcollapse_free(dc);
+        fxg_comm_free(comm);
+    }
     static char obuf[1 << 22];
     setvbuf(out, obuf, _IOFBF, sizeof obuf);
     size_t total_reads = 0;
@@ -368,8 +443,7 @@ static int main_collapser(int argc, char **argv)
         fprintf(f, "Input: %zu sequences (representing %zu reads)\n", fxh_num_input_sequences(rd), fxh_num_input_reads(rd));
         fprintf(f, "Output: %zu sequences (representing %zu reads)\n", (size_t)U, total_reads);
     }
-    fxg_collapse_free(col);
-    fxg_destroy(ctx);
+    for (int g = 0; g < ngpu; g++) { if (cols[g]) fxg_collapse_free(cols[g]); fxg_destroy(ctxs[g]); }
     return 0;
 }
 

@@ -168,6 +168,7 @@ typedef struct fxg_collapser fxg_collapser;
 int         fxg_collapse_new(int device, int64_t max_reads, int32_t stride, fxg_collapser **out);
 void        fxg_collapse_free(fxg_collapser *c);
 int         fxg_collapse_add(fxg_collapser *c, const fxg_batch *b, const int32_t *weight, const int64_t *first, int64_t index_base);
+int         fxg_collapse_reserve(fxg_collapser *c, int64_t rows, int32_t stride);   /* grow now (e.g. to a common stride) */
 int         fxg_collapse_add_next(fxg_collapser *c, const fxg_batch *b);   /* add(): weight 1, first = rows added so far + i */
 int         fxg_collapse_finish(fxg_collapser *c, int order, int64_t *n_unique, int64_t *first_bad_read);
 int         fxg_collapse_fetch(fxg_collapser *c, uint8_t *out_seq, int32_t *out_len, uint64_t *out_count, int64_t *out_first,
@@ -218,7 +219,8 @@ const char *fxg_comm_error(const fxg_comm *c);
 /* ---- a8/a9 across GPUs: the collapser's global count map (src/fastx_collapser/fastx_collapser.cpp:112-114) partitioned by
  * owner = std::hash(sequence) mod nranks, then the reference's output order (:116-122) computed once on the root GPU.
  * run(): batches[i] = DEVICE slabs on the communicator's i-th local GPU (seq only; len == NULL: uniform_len), global read
- * index of row r = index_base[i] + r, weight_dev (or weight_dev[i]) NULL = 1 per read.  Phases: K-ROUTE (hash, owner, send
+ * index of row r = index_base[i] + r (or first_dev[i][r] when given: rows that are already partial results, e.g. the uniques of
+ * a per-GPU fxg_collapser with their first indices), weight_dev (or weight_dev[i]) NULL = 1 per read.  Phases: K-ROUTE (hash, owner, send
  * slabs) -> exchange of key rows + 16-byte {first, weight, len} records -> K-DEDUP on the owners -> gather of the uniques'
  * (hash, first, count) to the root -> K-ORDER.  Key rows never leave their owner: fetch_local() returns an owner's uniques
  * in its table order, fetch_order() (root's process) says which (owner, index) is printed at every rank of the output.    */
@@ -236,7 +238,7 @@ typedef struct fxg_dcollapse fxg_dcollapse;
 int         fxg_dcollapse_new(fxg_comm *comm, int32_t stride, fxg_dcollapse **out);
 void        fxg_dcollapse_free(fxg_dcollapse *d);
 int         fxg_dcollapse_run(fxg_dcollapse *d, const fxg_batch *batches, const int64_t *index_base, const int32_t *const *weight_dev,
-                              int root, fxg_dcollapse_report *rep);
+                              const int64_t *const *first_dev, int root, fxg_dcollapse_report *rep);
 int         fxg_dcollapse_fetch_local(fxg_dcollapse *d, int local_index, uint8_t *out_seq, int32_t *out_len, uint64_t *out_count,
                                       int64_t *out_first, uint64_t *out_hash);
 int         fxg_dcollapse_fetch_order(fxg_dcollapse *d, int32_t *perm_owner_host, uint32_t *perm_index_host, int64_t *ordered_first_host,

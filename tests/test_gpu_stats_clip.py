@@ -202,11 +202,11 @@ def test_clip_golden_fixture(ctx):
     assert emit(recs, d_len.cpu().numpy(), 64) == golden("fastx_clipper1a.out")
 
 
-# ------------------------------------------------------------------- second-generation kernels (round 1, late)
+# ------------------------------------------------------------------- k_stats4 geometry / fallback coverage
 
 @pytest.mark.parametrize("L", [1, 2, 4, 5, 31, 32, 33, 63, 64, 65, 127, 128, 129, 131, 159, 160, 200, 320, 321])
-def test_stats2_length_sweep(ctx, L):
-    """k_stats2: A scheme (32-word superblock), B scheme (8-word blocks), tail bytes, multi-pass (> 160 cycles)."""
+def test_stats_length_sweep(ctx, L):
+    """k_stats4: A region (8 chunks, fewer for short reads), unmasked and masked B region, tail bytes, multi-pass (> 160 cycles)."""
     n = 4099
     seq, qual = H.synth_slab(H.SEED_BASE + 11, n, L, H.WITH_N)
     exp, cyc = H.o_stats_hist(seq, qual, None, L, seq.shape[1], 33, L)
@@ -221,18 +221,16 @@ def test_stats2_length_sweep(ctx, L):
     assert rep2.first_bad_read == -1 and np.array_equal(got2, exp2)
 
 
-def test_stats_kernel_generations_agree(ctx, monkeypatch):
-    """FXG_STATS_V=1 (first kernel) and the default (k_stats2) give the same table; bad reads are found by both."""
+def test_stats_full_range_bad_reads_and_fallback_kernel(ctx):
+    """the whole legal quality range (q' >= 64 leaves the shared histogram for the global table), bad reads at the corners of the
+    layout, and the inputs only the global-atomics fallback takes (-Q 90)."""
     n, L = 40001, 150
     seq, qual = H.synth_slab(H.SEED_BASE + 12, n, L, H.WITH_N)
     rng = np.random.default_rng(5)
     qual[:, :L] = rng.integers(33 - 15, 127, size=(n, L), dtype=np.uint8)     # full legal range: q' >= 64 goes to the global table
     exp, _ = H.o_stats_hist(seq, qual, None, L, seq.shape[1], 33, L)
     got2, _ = gpu_hist(ctx, seq, qual, None, L, 33, L)
-    monkeypatch.setenv("FXG_STATS_V", "1")
-    got1, _ = gpu_hist(ctx, seq, qual, None, L, 33, L)
-    monkeypatch.delenv("FXG_STATS_V")
-    assert np.array_equal(got2, exp) and np.array_equal(got1, exp)
+    assert np.array_equal(got2, exp)
     for pos, (arr, val) in enumerate([(seq, ord("a")), (qual, 17), (seq, 0), (qual, 200), (seq, ord("X"))]):
         a2 = arr.copy()
         r, c = 1000 + 7 * pos, [0, 37, 148, 149, 75][pos]
@@ -240,7 +238,7 @@ def test_stats_kernel_generations_agree(ctx, monkeypatch):
         s2, q2 = (a2, qual) if arr is seq else (seq, a2)
         _, rep = gpu_hist(ctx, s2, q2, None, L, 33, L)
         assert rep.first_bad_read == r
-    # Q = 64 and an offset too large for the packed range test (falls back to the first kernel)
+    # Q = 64 and an offset too large for the packed range test (the global-atomics kernel)
     for Q in (64, 90):
         q3 = np.zeros_like(qual)
         q3[:, :L] = rng.integers(Q - 15, min(Q + 93, 127) + 1, size=(n, L), dtype=np.uint8)
@@ -340,6 +338,23 @@ def test_stats_config_d_share_100m(ctx):
     ctx.stats_accum_dev(ctx.batch(dseq[h:], dqual[h:], n - h, stride, L), 33, halves, L, None, h)
     ctx.sync()
     assert torch.equal(whole, halves)
+    # 12 M reads: every CTA goes through more than 65 280 reads, i.e. through a flush of its 16-bit counters; checked against an
+    # independent count made with library ops (torch.bincount), cycle range by cycle range
+    k12 = min(n, 12_000_000)
+    h12 = torch.zeros((L, 5, 109), dtype=torch.int64, device="cuda")
+    ctx.stats_accum_dev(ctx.batch(dseq, dqual, k12, stride, L), 33, h12, L)
+    ctx.sync()
+    lut = torch.full((256,), 4, dtype=torch.int64, device="cuda")
+    for ch, v in ((ord("A"), 0), (ord("C"), 1), (ord("G"), 2), (ord("T"), 3), (ord("N"), 4)):
+        lut[ch] = v
+    for c0 in range(0, L, 25):
+        c1 = min(L, c0 + 25)
+        nuc = lut[dseq[:k12, c0:c1].long()]
+        qp = dqual[:k12, c0:c1].long() - (33 - 15)
+        cyc = torch.arange(c0, c1, device="cuda").view(1, -1).expand(k12, -1)
+        ref = torch.bincount(((cyc * 5 + nuc) * 109 + qp).reshape(-1), minlength=L * 5 * 109).view(L, 5, 109)
+        assert torch.equal(ref[c0:c1], h12[c0:c1]), (c0, c1)
+        del nuc, qp, cyc, ref
     m = 500000
     pre = torch.zeros((L, 5, 109), dtype=torch.int64, device="cuda")
     ctx.stats_accum_dev(ctx.batch(dseq, dqual, m, stride, L), 33, pre, L)

@@ -68,3 +68,31 @@ def test_native_nccl_allreduce_and_multi_gpu_stats_tool(tmp_path):
     r = subprocess.run([os.path.join(BIN, "fastx_quality_stats"), "-i", fq], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     ref = run_tool(H.ref_tool("fastx_quality_stats"), ["-i", fq])
     assert (r.returncode, r.stdout) == (ref[0], ref[1]), r.stderr.decode()[-500:]
+
+
+def test_drop_in_tools_on_two_gpus(tmp_path):
+    """FASTX_GPUS=2: the streaming engine spreads the text chunks over both GPUs (in-order writer); the collapser merges the two
+    partial count maps through the native owner exchange.  Output, report and exit status must be the reference's."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    if H.ref_tool("fastx_collapser") is None:
+        pytest.skip("oracle/_ref not built")
+    from test_tools_cli import assert_same
+    fq = str(tmp_path / "in.fq")
+    seq, qual = H.synth_slab(H.SEED_BASE + 4, 400000, 50, H.DUPS)
+    H.write_fastq(fq, seq, qual, None, 50)
+    fa = str(tmp_path / "in.fa")
+    H.write_fasta(fa, seq[:150000], None, 50, prefix="7-")
+    env = dict(FASTX_GPUS="2", FASTX_GPUS_FORCE="1", FASTX_CHUNK_BYTES="2000000")
+    os.environ.update(env)
+    try:
+        assert_same("fastq_quality_trimmer", ["-t", "20", "-l", "20", "-v", "-i", fq])
+        assert_same("fastq_quality_filter", ["-q", "20", "-p", "80", "-v", "-i", fq])
+        assert_same("fastx_reverse_complement", ["-v", "-i", fq])
+        assert_same("fastx_clipper", ["-a", "AGATCGGAAGAGC", "-l", "10", "-v", "-i", fq])
+        assert_same("fastx_collapser", ["-v", "-i", fq])
+        assert_same("fastx_collapser", ["-v", "-i", fa])
+        assert_same("fastx_quality_stats", ["-i", fq])
+    finally:
+        for k in env:
+            os.environ.pop(k, None)

@@ -296,6 +296,24 @@ def test_numeric_quality_and_fasta_inputs(tmp_path):
     # FASTA into quality_stats: the reference walks off its (empty) quality tables; the old format stays inside the
     # cycle's own entries and is reproduced, "-N" on FASTA runs off the end of the reference's static table (undefined)
     assert_same("fastx_quality_stats", ["-i", fa])
+    # all of these take the GPU text path (K-NUMQ / 2-line FASTA records), not the host parser: FASTX_PATH_REPORT=1 says so
+    big = str(tmp_path / "numeric.fq")
+    s2, q2 = H.synth_slab(H.SEED_BASE + 5, 30000, 60, H.PLAIN)
+    with open(big, "wb") as f:
+        for i in range(30000):
+            f.write(b"@n%d\n%s\n+\n%s\n" % (i, s2[i, :60].tobytes(), b" ".join(b"%d" % (int(v) - 33) for v in q2[i, :60])))
+    os.environ["FASTX_PATH_REPORT"] = "1"
+    try:
+        for tool, args, path, nrec in (("fastq_quality_trimmer", ["-t", "20", "-l", "5"], big, 30000), ("fastq_quality_filter", ["-q", "20", "-p", "50"], big, 30000),
+                                       ("fastx_reverse_complement", [], big, 30000), ("fastx_quality_stats", [], big, 30000),
+                                       ("fastx_collapser", [], big, 30000), ("fastx_reverse_complement", [], fa, 20000),
+                                       ("fastx_collapser", [], fa, 20000), ("fastx_clipper", ["-a", "ACGTACGT", "-n"], fa, 20000)):
+            m = run_tool(os.path.join(BIN, tool), args + ["-i", path])
+            r = run_tool(H.ref_tool(tool), args + ["-i", path])
+            assert m[0] == r[0] == 0 and m[1] == r[1], (tool, path)
+            assert ("[path] gpu_text_records=%d fallback=0" % nrec).encode() in m[2], (tool, path, m[2][-200:])
+    finally:
+        os.environ.pop("FASTX_PATH_REPORT", None)
 
 
 @gpu
