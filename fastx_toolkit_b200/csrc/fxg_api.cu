@@ -633,7 +633,7 @@ static int extra_enqueue(fxg_ctx *ctx, int op, const fxg_batch *b, int q_offset,
                          uint8_t *flags, int64_t index_base, cudaStream_t st)
 {
     if (b->n == 0) return FXG_OK;
-    if (b->qual && (op == 0 || op == 2 || op == 3) && !getenv("FXG_EXTRA_PLAIN")) {
+    if (b->qual && (op == 0 || op == 2 || op == 3)) {
         // FASTQ batches of short reads: the same warp-private TMA tile ring as K-TRIM (fxg_kernels.cu k_scan_w), with the op's
         // per-word work in place of the quality compare
         TilePlan plan;
