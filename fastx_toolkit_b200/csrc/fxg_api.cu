@@ -99,11 +99,19 @@ extern "C" int fxg_init(int device, fxg_ctx **out)
     ctx->cc_major = prop.major;
     ctx->cc_minor = prop.minor;
     ctx->hbm_bytes = prop.totalGlobalMem;
-    if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { free(ctx); INIT_FAIL("cudaStreamCreate", e); }
+    // anything that fails from here on releases what was created before it (fxg_destroy copes with the NULL members)
+#define INIT_FAIL_CTX(what, e)                                                                     \
+    do {                                                                                           \
+        snprintf(g_init_err, sizeof(g_init_err), "fxg_init: %s: %s", what, cudaGetErrorString(e)); \
+        cudaGetLastError();                                                                        \
+        fxg_destroy(ctx);                                                                          \
+        return FXG_ERR_CUDA;                                                                       \
+    } while (0)
+    if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) INIT_FAIL_CTX("cudaStreamCreate", e);
     ctx->stream = ctx->own_stream;
     for (int l = 0; l < PIPE_LANES; l++)
-        if ((e = cudaStreamCreateWithFlags(&ctx->lane_stream[l], cudaStreamNonBlocking)) != cudaSuccess) { free(ctx); INIT_FAIL("cudaStreamCreate", e); }
-    if ((e = cudaMalloc(&ctx->d_counters, CNT_WORDS * sizeof(unsigned long long))) != cudaSuccess) { free(ctx); INIT_FAIL("cudaMalloc", e); }
+        if ((e = cudaStreamCreateWithFlags(&ctx->lane_stream[l], cudaStreamNonBlocking)) != cudaSuccess) INIT_FAIL_CTX("cudaStreamCreate", e);
+    if ((e = cudaMalloc(&ctx->d_counters, CNT_WORDS * sizeof(unsigned long long))) != cudaSuccess) INIT_FAIL_CTX("cudaMalloc", e);
     {   // stream-ordered scratch (clipper work list): keep freed blocks in the pool instead of returning them at every sync
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -112,8 +120,8 @@ extern "C" int fxg_init(int device, fxg_ctx **out)
         }
         cudaGetLastError();
     }
-    if ((e = cudaMallocHost(&ctx->h_counters, CNT_WORDS * sizeof(unsigned long long))) != cudaSuccess) { free(ctx); INIT_FAIL("cudaMallocHost", e); }
-    if ((e = kernels_set_smem_attrs()) != cudaSuccess || (e = stats_set_smem_attrs()) != cudaSuccess) { free(ctx); INIT_FAIL("cudaFuncSetAttribute(max dynamic smem)", e); }
+    if ((e = cudaMallocHost(&ctx->h_counters, CNT_WORDS * sizeof(unsigned long long))) != cudaSuccess) INIT_FAIL_CTX("cudaMallocHost", e);
+#undef INIT_FAIL_CTX
     *out = ctx;
     return fxg_report_reset(ctx);
 }
@@ -125,11 +133,11 @@ extern "C" void fxg_destroy(fxg_ctx *ctx)
     cudaDeviceSynchronize();
     for (int l = 0; l < PIPE_LANES; l++) {
         for (int b = 0; b < 6; b++) if (ctx->lane_buf[l][b]) cudaFree(ctx->lane_buf[l][b]);
-        cudaStreamDestroy(ctx->lane_stream[l]);
+        if (ctx->lane_stream[l]) cudaStreamDestroy(ctx->lane_stream[l]);
     }
-    cudaFree(ctx->d_counters);
-    cudaFreeHost(ctx->h_counters);
-    cudaStreamDestroy(ctx->own_stream);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     free(ctx);
 }
 

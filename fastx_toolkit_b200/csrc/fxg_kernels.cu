@@ -788,6 +788,4 @@ cudaError_t launch_synth(const SynthParams &p, cudaStream_t st)
     return cudaGetLastError();
 }
 
-cudaError_t kernels_set_smem_attrs() { return cudaSuccess; }   // attributes are set per launch (FXG_LAUNCH_DYN)
-
 }  // namespace fxg

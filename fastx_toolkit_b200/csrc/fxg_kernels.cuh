@@ -163,7 +163,6 @@ cudaError_t launch_pipe_scatter(int64_t n, const int32_t *flags, const int32_t *
                                 int32_t *final_len, int sm_count, cudaStream_t st);
 cudaError_t launch_stats_simple(const StatsParams &p, int sm_count, cudaStream_t st);
 cudaError_t launch_clip(const ClipParams &p, int sm_count, int max_width, cudaStream_t st);
-cudaError_t stats_set_smem_attrs();
 cudaError_t launch_extra(int op, const uint8_t *seq, const uint8_t *qual, const int32_t *len, int uniform_len, int stride, int64_t n,
                          int q_offset, int thr_q, int mask_char, uint8_t *out_seq, uint8_t *flags, int64_t index_base,
                          unsigned long long *counters, int sm_count, cudaStream_t st);
@@ -173,6 +172,5 @@ cudaError_t launch_hash(const uint8_t *seq, const int32_t *len, int uniform_len,
 cudaError_t launch_scan(int mode, bool has_seq, const TilePlan &plan, const ScanParams &p, cudaStream_t st);
 cudaError_t launch_revcomp(bool has_qual, const TilePlan &plan, const RevcompParams &p, cudaStream_t st);
 cudaError_t launch_synth(const SynthParams &p, cudaStream_t st);
-cudaError_t kernels_set_smem_attrs();   // opt in to > 48 KB dynamic shared memory for every kernel
 
 }  // namespace fxg

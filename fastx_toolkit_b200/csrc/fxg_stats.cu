@@ -70,6 +70,4 @@ cudaError_t launch_stats_simple(const StatsParams &p, int sm_count, cudaStream_t
     return cudaGetLastError();
 }
 
-cudaError_t stats_set_smem_attrs() { return cudaSuccess; }
-
 }  // namespace fxg

@@ -308,11 +308,17 @@ __global__ void __launch_bounds__(TILES * PAIR * 32, 1) k_stats4(const __grid_co
                         }
                     }
                 }
-                // the rest (words 36..39 after the full block, else 32..39): every byte carries its validity
-                const int wlo = b_full4 ? 4 : 0, wn = b_full4 ? 4 : 8;       // wn words starting at 32 + wlo
-                if (__any_sync(0xFFFFFFFFu, LpB > 4 * wlo)) {
+                // the rest (words 36.. after the full block, else 32..): every byte carries its validity.  The rotation runs over
+                // the smallest power of two of words that covers the tile's longest read (150 bp: words 36 and 37 only — lanes
+                // then share counters, which costs wavefronts of the half-idle LSU, not issue slots)
+                const int wlo = b_full4 ? 4 : 0;
+                const int need = (__reduce_max_sync(0xFFFFFFFFu, LpB) - 4 * wlo + 3) >> 2;        // words any lane still needs
+                if (need > 0) {
+                    const int wn = need > 4 ? 8 : need > 2 ? 4 : need > 1 ? 2 : 1;
+                    const int per = wn >= PAIR ? wn / PAIR : 1;
+                    const int a_lo = wn >= PAIR ? half * per : 0, a_hi = wn >= PAIR ? a_lo + per : (half == 0 ? 1 : 0);
 #pragma unroll 2
-                    for (int a = half * (wn / PAIR); a < (half + 1) * (wn / PAIR); a++) {
+                    for (int a = a_lo; a < a_hi; a++) {
                         const uint32_t W = (uint32_t)(wlo + ((wb0 + a) & (wn - 1)));
                         const int vb = LpB - 4 * (int)W;
                         uint32_t sw = 0, qw = 0;
