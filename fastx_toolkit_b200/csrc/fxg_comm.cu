@@ -9,6 +9,8 @@
 // NCCL instance a host program (e.g. PyTorch) may already have loaded.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <strings.h>
 #include <nccl.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -40,8 +42,10 @@ static NcclApi g_nccl;
 static int nccl_load(void)
 {
     if (g_nccl.lib) return FXG_OK;
-    // the drop-in tools write their DATA to stdout: NCCL's version banner / debug log must never land there
+    // the drop-in tools write their DATA to stdout and their stderr is part of the drop-in contract: NCCL's debug log must
+    // never land on stdout, and a bare version banner (NCCL_DEBUG=VERSION, which this image exports) is not worth a line on stderr
     setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
+    { const char *lvl = getenv("NCCL_DEBUG"); if (lvl && !strcasecmp(lvl, "VERSION")) unsetenv("NCCL_DEBUG"); }
     void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
     if (!lib) { snprintf(g_comm_err, sizeof g_comm_err, "dlopen(libnccl.so.2): %s", dlerror()); return FXG_ERR_NCCL; }
     NcclApi a;
@@ -67,11 +71,21 @@ static int nccl_load(void)
     return FXG_OK;
 }
 
-// NCCL prints its version banner with printf() when NCCL_DEBUG=VERSION/WARN (this image exports NCCL_DEBUG=VERSION):
-// point fd 1 at stderr while communicators are created, then restore it.
+// NCCL prints its version banner with printf() when NCCL_DEBUG=VERSION/WARN (this image exports NCCL_DEBUG=VERSION).  The
+// drop-in tools' stdout is DATA and their stderr is compared with the reference's, so while communicators are created fd 1
+// points at /dev/null (at stderr when the user asked for NCCL's INFO / TRACE log), then it is restored.
 struct StdoutGuard {
     int saved;
-    StdoutGuard() { fflush(stdout); saved = dup(STDOUT_FILENO); if (saved >= 0) dup2(STDERR_FILENO, STDOUT_FILENO); }
+    StdoutGuard()
+    {
+        fflush(stdout);
+        saved = dup(STDOUT_FILENO);
+        const char *lvl = getenv("NCCL_DEBUG");
+        const bool chatty = lvl && (!strcasecmp(lvl, "INFO") || !strcasecmp(lvl, "TRACE") || !strcasecmp(lvl, "ABORT"));
+        int to = chatty ? -1 : open("/dev/null", O_WRONLY);
+        if (saved >= 0) dup2(to >= 0 ? to : STDERR_FILENO, STDOUT_FILENO);
+        if (to >= 0) close(to);
+    }
     ~StdoutGuard() { fflush(stdout); if (saved >= 0) { dup2(saved, STDOUT_FILENO); close(saved); } }
 };
 
