@@ -67,12 +67,15 @@ __device__ __forceinline__ void scan_seq_word(ScanAcc &a, uint32_t x, uint32_t m
         const uint32_t z = x ^ 0x4E4E4E4Eu;
         a.hasn |= ~(((z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | z) & HI & m;
     }
-    if (MODE == MODE_ARTIFACT) {                  // legal bases are < 128: (x ^ pat) + 0x7F.. has bit7 set iff the byte differs
-        const uint32_t mh = m & HI;
-        a.ba += (~((x ^ 0x41414141u) + 0x7F7F7F7Fu) & mh) >> 7;
-        a.bc += (~((x ^ 0x43434343u) + 0x7F7F7F7Fu) & mh) >> 7;
-        a.bg += (~((x ^ 0x47474747u) + 0x7F7F7F7Fu) & mh) >> 7;
-        a.bt += (~((x ^ 0x54545454u) + 0x7F7F7F7Fu) & mh) >> 7;
+    if (MODE == MODE_ARTIFACT) {
+        // nucleotide index per byte by table (A 0, C 1, G 2, T 3, N 4; the selector is the one the validation computes):
+        // bit 0 = C or T, bit 1 = G or T, bit 2 = N.  C, G, T and N are counted per byte lane, A is what is left of the length.
+        const uint32_t nuc4 = __byte_perm(0x01800080u, 0x02048003u, base_selector(x)) & m;
+        const uint32_t b0 = nuc4 & ONES, b1 = (nuc4 >> 1) & ONES, t = b0 & b1;
+        a.bt += t;
+        a.bc += b0 ^ t;
+        a.bg += b1 ^ t;
+        a.ba += (nuc4 >> 2) & ONES;               // N
     }
 }
 __device__ __forceinline__ void scan_flush_counts(ScanAcc &a)
@@ -388,7 +391,8 @@ __global__ void __launch_bounds__(W_THREADS) k_scan_w(const __grid_constant__ Sc
                 kept_local += hn ? 1u : 0u;
             }
         } else if (MODE == MODE_ARTIFACT) {
-            const uint32_t ca = group_sum<G>(a.ca), cc = group_sum<G>(a.cc), cg = group_sum<G>(a.cg), ct = group_sum<G>(a.ct);
+            const uint32_t cn = group_sum<G>(a.ca), cc = group_sum<G>(a.cc), cg = group_sum<G>(a.cg), ct = group_sum<G>(a.ct);
+            const uint32_t ca = (uint32_t)L - cn - cc - cg - ct;       // (a.ca holds the N count, see scan_seq_word)
             if (j == 0 && active) {
                 const int lim = L - 3;      // max_allowed_different_bases = 3 (fastx_artifacts_filter.c:66,99-107)
                 const bool artifact = (int)ca >= lim || (int)cc >= lim || (int)cg >= lim || (int)ct >= lim;

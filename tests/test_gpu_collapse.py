@@ -296,3 +296,43 @@ def test_collapse_config_e_200m_properties(ctx):
     for k in range(3):
         same = (dseq[:, :L] == torch.from_numpy(top[k, :L]).cuda()).all(dim=1)
         assert int(same.sum().item()) == int(ocnt[k]) and int(torch.nonzero(same)[0].item()) == int(ofirst[k])
+
+
+def test_collapser_grows_rows_stride_and_table(ctx):
+    """a streaming caller knows neither the number of reads nor the longest one when it creates the table: the row store is
+    re-strided when a longer batch arrives, and the table rebuilt (k_rehash) when it would get more than half full"""
+    import fastx_toolkit_b200 as F
+    rng = np.random.default_rng(11)
+    parts = []
+    for n, L in ((3000, 20), (50000, 45), (120000, 100), (40000, 30)):
+        seq, _ = H.synth_slab(H.SEED_BASE + 4 + L, n, L, H.DUPS)
+        parts.append((seq, L))
+    col = F.Collapser(0, 1024, 32)                      # far too small on purpose
+    base = 0
+    for seq, L in parts:
+        n, stride = seq.shape
+        col.add(F.Batch(seq.ctypes.data, None, None, L, stride, n), None, None, base)
+        base += n
+    u = col.finish(True)
+    stride = int(col.L.fxg_collapse_stride(col.h))
+    assert stride == 112
+    oseq, olen, ocnt, ofirst = np.zeros((u, stride), np.uint8), np.zeros(u, np.int32), np.zeros(u, np.uint64), np.zeros(u, np.int64)
+    col.fetch(oseq, olen, ocnt, ofirst, None)
+    col.close()
+    # the oracle on the same reads, in the same order
+    O = H.oracle()
+    oc = O.fxo_collapser_new()
+    rows = []
+    for seq, L in parts:
+        for i in range(seq.shape[0]):
+            r = np.ascontiguousarray(seq[i])
+            O.fxo_collapser_add(oc, H._p(r, H.u8p), L, 1)
+            rows.append((seq, i, L))
+    eu = O.fxo_collapser_unique(oc)
+    efirst, ecnt = np.empty(eu, np.int64), np.empty(eu, np.uint64)
+    O.fxo_collapser_order(oc, H._p(efirst, H.i64p), H._p(ecnt, H.u64p))
+    O.fxo_collapser_free(oc)
+    assert u == eu and np.array_equal(ocnt, ecnt) and np.array_equal(ofirst, efirst)
+    for k in (0, 1, u // 3, u // 2, u - 1):
+        seq, i, L = rows[int(efirst[k])]
+        assert olen[k] == L and oseq[k, :L].tobytes() == seq[i, :L].tobytes()
