@@ -54,6 +54,10 @@ typedef struct {
     int expect_len;             /* CLIP: read length of chunk 0 (0 = not known yet) */
     int reader_failed; char reader_err[256];
     int deflate;                /* -z: the chunks leave the GPU as DEFLATE blocks */
+    int ordered_apply;          /* STATS / COLLAPSE: a chunk changes state on the GPU, so it runs only once every earlier chunk is
+                                   known to be clean — a chunk that is handed back to the record path must not have successors
+                                   that were already counted */
+    int64_t next_apply;
     pthread_mutex_t col_mu[64];
 } fxs_state;
 
@@ -240,7 +244,18 @@ static void *worker_main(void *arg)
         if (job->op == FXS_CLIP && c->seq > 0)
             while (s->expect_len == 0 && !s->stop) pthread_cond_wait(&s->cv, &s->mu);
         const int expect = s->expect_len;
+        int skip = 0;
+        if (s->ordered_apply) {
+            while (s->next_apply != c->seq && !s->stop) pthread_cond_wait(&s->cv, &s->mu);
+            skip = s->stop;
+        }
         pthread_mutex_unlock(&s->mu);
+        if (skip) {                                    /* the engine is winding down: the chunk stays unprocessed (its bytes go back to the reader) */
+            pthread_mutex_lock(&s->mu);
+            s->free_out[s->n_free_out++] = out;
+            pthread_mutex_unlock(&s->mu);
+            break;
+        }
 
         c->out = out;
         const char *text = c->buf + c->head;
@@ -279,6 +294,8 @@ static void *worker_main(void *arg)
             c->lastseq_len = L;
         }
         pthread_mutex_lock(&s->mu);
+        if (s->ordered_apply && c->rc == FXG_OK && c->rep.anomaly == 0 && c->rep.n_records > 0 && (size_t)c->rep.consumed_bytes == c->len)
+            s->next_apply = c->seq + 1;                /* clean and complete: the next chunk may run */
         if (job->op == FXS_CLIP && c->seq == 0 && s->expect_len == 0)
             s->expect_len = (c->rc == FXG_OK && c->rep.anomaly == 0 && c->rep.max_len > 0) ? c->rep.max_len : -1;
         s->done[c->seq % s->done_cap] = c;
@@ -334,6 +351,7 @@ int fxs_run(fxs_job *job, fxh_reader *rd, fxh_writer *wr)
     if (job->op == FXS_COLLAPSE && nworkers > 2 * ngpu) nworkers = 2 * ngpu;  /* a table is one object: adds to it are serialised */
     const int has_out = job->op == FXS_TRIM || job->op == FXS_FILTER || job->op == FXS_REVCOMP || job->op == FXS_CLIP;
     s->deflate = has_out && wr && fxh_writer_frames_gzip(wr);
+    s->ordered_apply = (job->op == FXS_STATS || job->op == FXS_COLLAPSE);
     s->out_cap = has_out ? (FXS_HEAD + s->chunk_bytes) + (FXS_HEAD + s->chunk_bytes) / 4 + 64 : 64;
     const int n_in = 2 * nworkers + 2, n_out = nworkers + 1;
     pthread_mutex_init(&s->mu, NULL); pthread_cond_init(&s->cv, NULL);

@@ -76,8 +76,17 @@ int fxg_text_run_host(fxg_text *t, int op, const char *text, size_t bytes, int q
 }
 int fxg_text_clip_host(fxg_text *t, const char *a, size_t b, int c, const fxg_clip_opts *d, int e, int f, char *g, fxg_text_report *h)
 { (void)t; (void)a; (void)b; (void)c; (void)d; (void)e; (void)f; (void)g; (void)h; return FXG_ERR_UNSUPPORTED; }
-int fxg_text_stats_host(fxg_text *t, const char *a, size_t b, int c, uint64_t *d, int32_t e, fxg_text_report *f)
-{ (void)t; (void)a; (void)b; (void)c; (void)d; (void)e; (void)f; return FXG_ERR_UNSUPPORTED; }
+/* a stateful op (what K-STATS / the collapser are): the records of a clean chunk are counted into *hist; the engine must
+ * never let a chunk count whose predecessor is handed back to the record path */
+int fxg_text_stats_host(fxg_text *t, const char *text, size_t bytes, int q, uint64_t *hist, int32_t e, fxg_text_report *rep)
+{
+    (void)e;
+    static char sink[1 << 26];
+    if (bytes > sizeof sink) return FXG_ERR_ARG;
+    int rc = fxg_text_run_host(t, 2, text, bytes, q, 0, 0, sink, rep);
+    if (rc == FXG_OK && rep->anomaly == 0) __atomic_fetch_add(hist, (uint64_t)rep->n_records, __ATOMIC_RELAXED);
+    return rc;
+}
 int fxg_text_collapse_host(fxg_text *t, const char *a, size_t b, int c, fxg_collapser *d, int64_t e, fxg_text_report *f)
 { (void)t; (void)a; (void)b; (void)c; (void)d; (void)e; (void)f; return FXG_ERR_UNSUPPORTED; }
 
@@ -92,11 +101,18 @@ int main(int argc, char **argv)
     fxs_job job;
     memset(&job, 0, sizeof job);
     job.op = FXS_REVCOMP; job.ngpu = 2; job.first_dev = 0;
-    const int fell_back = fxs_run(&job, rd, wr);
+    uint64_t counted[2] = { 0, 0 }, *hists[2] = { &counted[0], &counted[1] };
+    const int stateful = getenv("FXS_HARNESS_STATEFUL") != NULL;
+    if (stateful) { job.op = FXS_STATS; job.hist_dev = hists; job.max_cycles = 1; }
+    const int fell_back = fxs_run(&job, rd, stateful ? NULL : wr);
     fxh_batch *b;
-    while ((b = fxh_reader_next(rd, fxh_batch_reads())) != NULL)
-        for (int64_t i = 0; i < b->n; i++)
+    uint64_t host_counted = 0;
+    while ((b = fxh_reader_next(rd, fxh_batch_reads())) != NULL) {
+        host_counted += (uint64_t)b->n;
+        for (int64_t i = 0; i < b->n && !stateful; i++)
             fxh_write_record(wr, b, i, b->seq + (size_t)i * b->stride, b->qual ? b->qual + (size_t)i * b->stride : NULL, b->len[i]);
+    }
+    if (stateful) fprintf(stderr, "[harness] counted=%llu\n", (unsigned long long)(counted[0] + counted[1] + host_counted));
     fxh_writer_close(wr);
     if (fxh_verbose()) {
         FILE *f = fxh_report_file();

@@ -119,3 +119,21 @@ def test_broken_inputs_hand_over_to_the_record_path(harness, tmp_path):
     # a record path that takes over must continue to the end of a valid file: a numeric record in the middle, then 5000 more
     rep = same(harness, ["-v", "-i", cases[9]], env=ENVS[1])
     assert "fallback=1" in rep
+
+
+def test_stateful_ops_never_count_a_chunk_twice(harness, tmp_path):
+    """quality stats and the collapser change state on the GPU: when a chunk is handed back to the record path (here: one record with
+    numeric qualities in the middle of an ASCII file — valid input), no later chunk may already have been counted"""
+    seq, qual = H.synth_slab(H.SEED_BASE + 25, 20000, 50, H.PLAIN)
+    fq = str(tmp_path / "mixed.fq")
+    H.write_fastq(fq, seq, qual, None, 50)
+    lines = open(fq, "rb").read().split(b"\n")[:-1]
+    lines[4 * 7000 + 3] = b" ".join([b"40"] * 50)
+    open(fq, "wb").write(b"\n".join(lines) + b"\n")
+    for env in ENVS:
+        e = dict(os.environ, FXS_HARNESS_STATEFUL="1", FXS_HARNESS_REPORT="1")
+        e.update(env)
+        for _ in range(3):
+            m = subprocess.run([harness, "-i", fq], capture_output=True, env=e, timeout=300)
+            assert m.returncode == 0, m.stderr[-300:]
+            assert b"[harness] counted=20000\n" in m.stderr, (env, m.stderr[-200:])
