@@ -1,6 +1,7 @@
 // fxg_api.cu — the C ABI declared in include/fxg.h: context, memory, launch planning and the
 // host-buffer pipelines (pinned host slab -> H2D on a side stream -> kernel -> D2H).
 // No CPU fallback anywhere: every failure is reported as an error code.
+#include <vector>
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -393,8 +394,9 @@ extern "C" int fxg_synth_dev(fxg_ctx *ctx, uint8_t *seq, uint8_t *qual, int64_t 
 }
 
 // ---- trim / filter -----------------------------------------------------------------------------------
+// n_dev (device memory, fused pipelines only): the live reads among the b->n the launch is sized for
 static int scan_enqueue(fxg_ctx *ctx, int mode, const fxg_batch *b, int q_offset, int thr_q, int min_len, int min_percent,
-                        void *out, int64_t index_base, cudaStream_t st)
+                        void *out, int64_t index_base, cudaStream_t st, const int64_t *n_dev = NULL)
 {
     if (b->n == 0) return FXG_OK;
     const bool has_seq = b->seq != NULL;
@@ -403,6 +405,7 @@ static int scan_enqueue(fxg_ctx *ctx, int mode, const fxg_batch *b, int q_offset
     if (rc) return rc;
     ScanParams p;
     p.seq = b->seq; p.qual = b->qual; p.len = b->len; p.uniform_len = b->uniform_len; p.stride = b->stride; p.n = b->n;
+    p.n_dev = n_dev;
     p.tile_reads = plan.tile_reads; p.stages = plan.stages; p.rot_shift = plan.rot_shift;
     p.qk = make_qualk(q_offset, thr_q);
     p.min_len = min_len;
@@ -526,11 +529,13 @@ extern "C" int fxg_stats_accum_dev(fxg_ctx *ctx, const fxg_batch *b, int q_offse
 
 // ---- clipper ---------------------------------------------------------------------------------------
 static int clip_enqueue(fxg_ctx *ctx, const fxg_batch *b, const int32_t *width, int q_offset, const fxg_clip_opts *o,
-                        int32_t *out_len, uint8_t *out_class, int32_t *out_cut, int64_t index_base, cudaStream_t st)
+                        int32_t *out_len, uint8_t *out_class, int32_t *out_cut, int64_t index_base, cudaStream_t st,
+                        const int64_t *n_dev = NULL)
 {
     if (b->n == 0) return FXG_OK;
     ClipParams p;
     memset(&p, 0, sizeof(p));
+    p.n_dev = n_dev;
     p.seq = b->seq; p.qual = b->qual; p.len = b->len; p.width = width; p.uniform_len = b->uniform_len;
     p.stride = b->stride; p.n = b->n; p.qk = make_qualk(q_offset, 0);
     p.alen = (int)strlen(o->adapter);
@@ -542,7 +547,7 @@ static int clip_enqueue(fxg_ctx *ctx, const fxg_batch *b, const int32_t *width, 
     // A/C/G/T only, up to 16 characters.  Reads with an 'N' go on a list and through the fp32 kernel in a second
     // launch.  FXG_CLIP_V=1 selects the fp32 kernel for everything.
     const char *cv = getenv("FXG_CLIP_V");
-    bool dpx = !(cv && cv[0] == '1') && !width && !b->len && p.alen >= 1 && p.alen <= 16 && b->uniform_len <= 256 &&
+    bool dpx = !(cv && cv[0] == '1') && !width && !b->len && !n_dev && p.alen >= 1 && p.alen <= 16 && b->uniform_len <= 256 &&
                b->n < (1ll << 31);
     for (int i = 0; i < p.alen && dpx; i++) {
         const char c = o->adapter[i];
@@ -811,105 +816,128 @@ extern "C" int fxg_pipeline_dev(fxg_ctx *ctx, const fxg_batch *b, int q_offset, 
     if (n == 0) return FXG_OK;
     CK(ctx, cudaMemsetAsync(final_len, 0xFF, (size_t)n * sizeof(int32_t), st));
 
-    // per-stage scratch, sized by the input: decision (int32 or bytes), flags, positions, scan workspace
+    // per-stage scratch, sized by the input: decision (int32 or bytes), flags, positions, scan workspace, and the survivor
+    // count after each stage.  The counts STAY on the device: every later kernel is launched over the bound n and reads its
+    // true row count from d_cnt, so the chain is enqueued back to back and the host reads the counts once, at the end.
     const size_t tmp_bytes = pipe_scan_tmp_bytes(n);
     const size_t ib = (((size_t)n * sizeof(int32_t)) + 255) & ~(size_t)255;
+    const size_t cb = (((size_t)(n_stages + 1) * sizeof(int64_t)) + 255) & ~(size_t)255;
     void *scr = NULL;
-    CK(ctx, cudaMallocAsync(&scr, 3 * ib + ((tmp_bytes + 255) & ~(size_t)255), st));
-    int32_t *d_dec = (int32_t *)scr, *d_flags = (int32_t *)((char *)scr + ib), *d_pos = (int32_t *)((char *)scr + 2 * ib);
-    void *d_tmp = (char *)scr + 3 * ib;
-    // working slabs of the survivors (ping-pong), allocated when the first compaction's size is known
+    CK(ctx, cudaMallocAsync(&scr, cb + 3 * ib + ((tmp_bytes + 255) & ~(size_t)255), st));
+    int64_t *d_cnt = (int64_t *)scr;                              // d_cnt[k] = reads entering stage k (k >= 1)
+    int32_t *d_dec = (int32_t *)((char *)scr + cb), *d_flags = (int32_t *)((char *)scr + cb + ib), *d_pos = (int32_t *)((char *)scr + cb + 2 * ib);
+    void *d_tmp = (char *)scr + cb + 3 * ib;
+    // working slabs of the survivors (ping-pong), sized by the bound
     void *work[2] = { NULL, NULL };
     uint8_t *wseq[2] = { NULL, NULL }, *wqual[2] = { NULL, NULL };
     int32_t *wlen[2] = { NULL, NULL }, *widx[2] = { NULL, NULL };
+    std::vector<int64_t> h_cnt((size_t)n_stages + 1, 0);
+    h_cnt[0] = n;
 
     fxg_batch cur = *b;
     const int32_t *cur_idx = NULL;
-    int64_t cur_n = n;
-    int which = 0;
+    const int64_t *cur_cnt = NULL;       // device count of the reads entering the stage (NULL: all n)
+    const int64_t n_in0 = ctx->report.n_in;
+    int which = 0, stages_run = 0;
     rc = FXG_OK;
-    for (int k = 0; k < n_stages && cur_n > 0; k++) {
+    for (int k = 0; k < n_stages; k++) {
         const fxg_stage &sg = stages[k];
-        cur.n = cur_n;
+        cur.n = n;
         if (sg.op == FXG_STAGE_COLLAPSE) {
             // the survivors (already compacted, in input order) enter the count map exactly as the next process of the pipe
-            // would read them (fastx_collapser.cpp:112-114); their lengths also go back to final_len
-            cudaError_t e = launch_pipe_keep_all(cur_n, cur.len, cur.uniform_len, cur_idx, final_len, ctx->sm_count, st);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            // would read them (fastx_collapser.cpp:112-114); their lengths also go back to final_len.  The count map is
+            // sized on the host, so this (last) stage is where the survivor count is read back.
+            int64_t alive = n;
+            cudaError_t e = cudaSuccess;
+            if (cur_cnt) {
+                e = cudaMemcpyAsync(h_cnt.data() + 1, d_cnt + 1, (size_t)k * sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+                alive = h_cnt[k];
+            }
+            if (e == cudaSuccess && alive > 0) {
+                e = launch_pipe_keep_all(alive, cur.len, cur.uniform_len, cur_idx, final_len, ctx->sm_count, st);
+                ctx->launches++;
+            }
             if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "pipeline collapse stage: %s", cudaGetErrorString(e)); rc = FXG_ERR_CUDA; break; }
-            ctx->launches++;
-            fxg_batch kb = cur;
-            kb.qual = NULL;
-            rc = fxg_collapse_add_next(sg.collapser, &kb);
-            if (rc) snprintf(ctx->err, sizeof(ctx->err), "pipeline collapse stage: %s", fxg_collapse_error(sg.collapser));
+            if (alive > 0) {
+                if ((e = cudaStreamSynchronize(st)) != cudaSuccess) {
+                    snprintf(ctx->err, sizeof(ctx->err), "pipeline collapse stage: %s", cudaGetErrorString(e)); rc = FXG_ERR_CUDA; break;
+                }
+                fxg_batch kb = cur;
+                kb.n = alive;
+                kb.qual = NULL;
+                rc = fxg_collapse_add_next(sg.collapser, &kb);
+                if (rc) snprintf(ctx->err, sizeof(ctx->err), "pipeline collapse stage: %s", fxg_collapse_error(sg.collapser));
+            }
             break;
         }
         const bool bytes = sg.op == FXG_STAGE_FILTER;
-        if (sg.op == FXG_STAGE_TRIM) rc = scan_enqueue(ctx, MODE_TRIM, &cur, q_offset, sg.a0, sg.a1, 0, d_dec, 0, st);
-        else if (sg.op == FXG_STAGE_FILTER) rc = scan_enqueue(ctx, MODE_FILTER, &cur, q_offset, sg.a0, 0, sg.a1, d_dec, 0, st);
-        else if (!cur.len) rc = clip_enqueue(ctx, &cur, NULL, q_offset, sg.clip, d_dec, NULL, NULL, 0, st);
+        if (sg.op == FXG_STAGE_TRIM) rc = scan_enqueue(ctx, MODE_TRIM, &cur, q_offset, sg.a0, sg.a1, 0, d_dec, 0, st, cur_cnt);
+        else if (sg.op == FXG_STAGE_FILTER) rc = scan_enqueue(ctx, MODE_FILTER, &cur, q_offset, sg.a0, 0, sg.a1, d_dec, 0, st, cur_cnt);
+        else if (!cur.len) rc = clip_enqueue(ctx, &cur, NULL, q_offset, sg.clip, d_dec, NULL, NULL, 0, st, cur_cnt);
         else {
             // mixed lengths: the clipper works on the reference's stale-buffer rows (one scan over the survivors, in order)
             size_t need = 0;
-            cudaError_t e2 = launch_stale_rows(cur.seq, cur.len, S, cur_n, NULL, NULL, NULL, 0, &need, ctx->sm_count, st);
+            cudaError_t e2 = launch_stale_rows(cur.seq, cur.len, S, n, cur_cnt, NULL, NULL, NULL, 0, &need, ctx->sm_count, st);
             void *sscr = NULL, *srows = NULL;
-            const size_t rb = (((size_t)cur_n * S) + 255) & ~(size_t)255;
+            const size_t rb = (((size_t)n * S) + 255) & ~(size_t)255;
             if (e2 == cudaSuccess) e2 = cudaMallocAsync(&sscr, need, st);
-            if (e2 == cudaSuccess) e2 = cudaMallocAsync(&srows, rb + (size_t)cur_n * sizeof(int32_t), st);
-            if (e2 == cudaSuccess) e2 = launch_stale_rows(cur.seq, cur.len, S, cur_n, (uint8_t *)srows, (int32_t *)((char *)srows + rb), sscr, need, NULL,
-                                                          ctx->sm_count, st);
+            if (e2 == cudaSuccess) e2 = cudaMallocAsync(&srows, rb + (size_t)n * sizeof(int32_t), st);
+            if (e2 == cudaSuccess) e2 = launch_stale_rows(cur.seq, cur.len, S, n, cur_cnt, (uint8_t *)srows, (int32_t *)((char *)srows + rb), sscr, need,
+                                                          NULL, ctx->sm_count, st);
             if (e2 != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "pipeline stale rows: %s", cudaGetErrorString(e2)); rc = FXG_ERR_CUDA; }
             else {
                 fxg_batch sb = cur;
                 sb.seq = (const uint8_t *)srows;
-                rc = clip_enqueue(ctx, &sb, (const int32_t *)((char *)srows + rb), q_offset, sg.clip, d_dec, NULL, NULL, 0, st);
+                rc = clip_enqueue(ctx, &sb, (const int32_t *)((char *)srows + rb), q_offset, sg.clip, d_dec, NULL, NULL, 0, st, cur_cnt);
                 ctx->launches += 2;
             }
             if (sscr) cudaFreeAsync(sscr, st);
             if (srows) cudaFreeAsync(srows, st);
         }
         if (rc) break;
-        cudaError_t e = launch_pipe_flags_scan(bytes ? NULL : d_dec, bytes ? (const uint8_t *)d_dec : NULL, cur_n, d_flags, d_pos, d_tmp, tmp_bytes,
-                                              ctx->sm_count, st);
-        int32_t last_pos = 0, last_flag = 0;
-        if (e == cudaSuccess) e = cudaMemcpyAsync(&last_pos, d_pos + (cur_n - 1), 4, cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(&last_flag, d_flags + (cur_n - 1), 4, cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        stages_run = k + 1;
+        cudaError_t e = launch_pipe_flags_scan(bytes ? NULL : d_dec, bytes ? (const uint8_t *)d_dec : NULL, n, cur_cnt, d_flags, d_pos, d_tmp, tmp_bytes,
+                                              d_cnt + (k + 1), ctx->sm_count, st);
         if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "pipeline stage %d: %s", k, cudaGetErrorString(e)); rc = FXG_ERR_CUDA; break; }
-        ctx->launches += 2;
-        const int64_t alive = (int64_t)last_pos + last_flag;
-        if (k == n_stages - 1 || alive == 0) {
-            if (alive > 0) {
-                e = launch_pipe_scatter(cur_n, d_flags, bytes ? NULL : d_dec, cur.len, cur.uniform_len, cur_idx, final_len, ctx->sm_count, st);
-                if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "pipeline scatter: %s", cudaGetErrorString(e)); rc = FXG_ERR_CUDA; break; }
-                ctx->launches++;
-            }
-            cur_n = alive;
+        ctx->launches += 3;
+        if (k == n_stages - 1) {
+            e = launch_pipe_scatter(n, cur_cnt, d_flags, bytes ? NULL : d_dec, cur.len, cur.uniform_len, cur_idx, final_len, ctx->sm_count, st);
+            if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "pipeline scatter: %s", cudaGetErrorString(e)); rc = FXG_ERR_CUDA; break; }
+            ctx->launches++;
             break;
         }
         // compact the survivors into the other working slab pair
         const int dst = which;
         if (!work[dst]) {
-            const size_t sb = (((size_t)alive * S) + 255) & ~(size_t)255, lb = (((size_t)alive * sizeof(int32_t)) + 255) & ~(size_t)255;
+            const size_t sb = (((size_t)n * S) + 255) & ~(size_t)255, lb = (((size_t)n * sizeof(int32_t)) + 255) & ~(size_t)255;
             e = cudaMallocAsync(&work[dst], 2 * sb + 2 * lb, st);
             if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "pipeline: cudaMallocAsync: %s", cudaGetErrorString(e)); rc = FXG_ERR_CUDA; break; }
             wseq[dst] = (uint8_t *)work[dst]; wqual[dst] = wseq[dst] + sb;
             wlen[dst] = (int32_t *)(wqual[dst] + sb); widx[dst] = (int32_t *)((char *)wlen[dst] + lb);
         }
-        e = launch_pipe_gather(cur.seq, cur.qual, S, cur_n, d_flags, d_pos, bytes ? NULL : d_dec, cur.len, cur.uniform_len, cur_idx, wseq[dst], wqual[dst],
-                               wlen[dst], widx[dst], ctx->sm_count, st);
+        e = launch_pipe_gather(cur.seq, cur.qual, S, n, cur_cnt, d_flags, d_pos, bytes ? NULL : d_dec, cur.len, cur.uniform_len, cur_idx, wseq[dst],
+                               wqual[dst], wlen[dst], widx[dst], ctx->sm_count, st);
         if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "pipeline gather: %s", cudaGetErrorString(e)); rc = FXG_ERR_CUDA; break; }
         ctx->launches++;
         cur.seq = wseq[dst]; cur.qual = wqual[dst]; cur.len = wlen[dst]; cur.uniform_len = 0;
         cur_idx = widx[dst];
-        cur_n = alive;
-        which ^= 1;                      // survivors only shrink: the slab sized for stage k's survivors fits every later stage
+        cur_cnt = d_cnt + (k + 1);
+        which ^= 1;
     }
-    cudaStreamSynchronize(st);
+    // the one read-back of the call: the survivor counts of all stages
+    if (!rc && stages_run > 0) {
+        cudaError_t e = cudaMemcpyAsync(h_cnt.data() + 1, d_cnt + 1, (size_t)stages_run * sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "pipeline: %s", cudaGetErrorString(e)); rc = FXG_ERR_CUDA; }
+    } else cudaStreamSynchronize(st);
     for (int w = 0; w < 2; w++) if (work[w]) cudaFreeAsync(work[w], st);
     cudaFreeAsync(scr, st);
     if (rc) return rc;
-    if (n_survivors) *n_survivors = cur_n;
+    // the kernels counted the bound as their input; the report counts the reads each stage really saw
+    ctx->report.n_in = n_in0;
+    for (int k = 0; k < stages_run; k++) ctx->report.n_in += h_cnt[k];
+    if (n_survivors) *n_survivors = h_cnt[stages_run];
     return refresh_report(ctx, st);
 }
 

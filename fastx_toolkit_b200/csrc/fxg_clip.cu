@@ -142,9 +142,10 @@ __global__ void __launch_bounds__(128) k_clip(const __grid_constant__ ClipParams
 {
     const int H = P.alen;
     const int lane = threadIdx.x & 31;
-    for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ll; base < P.n; base += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t N = P.n_dev ? *P.n_dev : P.n;
+    for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ll; base < N; base += (int64_t)gridDim.x * blockDim.x) {
         const int64_t g = base + lane;
-        const bool active = g < P.n;
+        const bool active = g < N;
         int cls = -1;
         if (active) {
             int L = P.len ? __ldg(P.len + g) : P.uniform_len;
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(128) k_clip_bits(const __grid_constant__ ClipP
     const int H = P.alen;
     const int lane = threadIdx.x & 31;
     // list mode (second pass of the integer fast path): only the reads whose indices k_clip_dpx put on the list
-    const int64_t nn = P.list ? (int64_t)*P.list_count : P.n;
+    const int64_t nn = P.list ? (int64_t)*P.list_count : (P.n_dev ? *P.n_dev : P.n);
     for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ll; base < nn; base += (int64_t)gridDim.x * blockDim.x) {
         const bool active = base + lane < nn;
         const int64_t g = !active ? 0 : (P.list ? (int64_t)P.list[base + lane] : base + lane);
@@ -327,13 +328,14 @@ __global__ void __launch_bounds__(128) k_clip_dpx(const __grid_constant__ ClipPa
 {
     const int H = P.alen, L = P.uniform_len;
     const int lane = threadIdx.x & 31;
-    const int64_t npairs = (P.n + 1) >> 1;
+    const int64_t N = P.n_dev ? *P.n_dev : P.n;
+    const int64_t npairs = (N + 1) >> 1;
     for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ll; base < npairs; base += (int64_t)gridDim.x * blockDim.x) {
         const int64_t pair = base + lane;
         int cls0 = -1, cls1 = -1;
         if (pair < npairs) {
             const int64_t g0 = 2 * pair;
-            const bool has1 = g0 + 1 < P.n;
+            const bool has1 = g0 + 1 < N;
             const int64_t g1 = has1 ? g0 + 1 : g0;
             const uint8_t *row0 = P.seq + (size_t)g0 * P.stride, *row1 = P.seq + (size_t)g1 * P.stride;
             dpx::PairOut o;

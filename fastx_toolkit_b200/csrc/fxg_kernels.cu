@@ -211,6 +211,7 @@ template <int G, int MODE, bool HAS_SEQ>
 __global__ void __launch_bounds__(THREADS) k_scan(const __grid_constant__ ScanParams P)
 {
     extern __shared__ __align__(128) uint8_t smem[];
+    const int64_t N = P.n_dev ? *P.n_dev : P.n;       // reads in the batch (device-side count in fused pipelines)
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
     __shared__ unsigned int s_kept;
 
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(THREADS) k_scan(const __grid_constant__ ScanPa
     const int stages = P.stages;
     const uint32_t slab_bytes = (uint32_t)TR * (uint32_t)S;
     const uint32_t stage_bytes = slab_bytes * (HAS_SEQ ? 2u : 1u);
-    const int64_t ntiles = (P.n + TR - 1) / TR;
+    const int64_t ntiles = (N + TR - 1) / TR;
     const QualK qk = P.qk;
 
     if (tid == 0) {
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(THREADS) k_scan(const __grid_constant__ ScanPa
 
     auto issue = [&](int64_t tile, int s) {
         const int64_t r0 = tile * TR;
-        const int64_t left = P.n - r0;
+        const int64_t left = N - r0;
         const uint32_t bytes = (uint32_t)(left < TR ? left : TR) * (uint32_t)S;
         uint8_t *dst = smem + (size_t)s * stage_bytes;
         mbar_arrive_expect_tx(&full_bar[s], bytes * (HAS_SEQ ? 2u : 1u));
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(THREADS) k_scan(const __grid_constant__ ScanPa
         mbar_wait(&full_bar[s], parity);
         const uint8_t *stage = smem + (size_t)s * stage_bytes;
         const int64_t r0 = tile * TR;
-        const int64_t left = P.n - r0;
+        const int64_t left = N - r0;
         const int nr = (int)(left < TR ? left : TR);
 
         for (int rb = 0; rb < nr; rb += RPP) {
@@ -321,6 +322,7 @@ template <int G, int MODE, bool HAS_SEQ>
 __global__ void __launch_bounds__(W_THREADS) k_scan_w(const __grid_constant__ ScanParams P)
 {
     extern __shared__ __align__(128) uint8_t smem[];
+    const int64_t N = P.n_dev ? *P.n_dev : P.n;       // reads in the batch (device-side count in fused pipelines)
     __shared__ __align__(8) uint64_t full_bar[W_WARPS][MAX_STAGES];
 
     constexpr int R = 32 / G;
@@ -331,7 +333,7 @@ __global__ void __launch_bounds__(W_THREADS) k_scan_w(const __grid_constant__ Sc
     const uint32_t stage_bytes = slab_bytes * (HAS_SEQ ? 2u : 1u);
     uint8_t *wbase = smem + (size_t)w * stages * stage_bytes;
     uint64_t *bars = full_bar[w];
-    const int64_t ntiles = (P.n + R - 1) / R;
+    const int64_t ntiles = (N + R - 1) / R;
     const int64_t gw = (int64_t)blockIdx.x * W_WARPS + w, GW = (int64_t)gridDim.x * W_WARPS;
     const QualK qk = P.qk;
 
@@ -343,7 +345,7 @@ __global__ void __launch_bounds__(W_THREADS) k_scan_w(const __grid_constant__ Sc
 
     auto issue = [&](int64_t tile, int s) {
         const int64_t r0 = tile * R;
-        const int64_t left = P.n - r0;
+        const int64_t left = N - r0;
         const uint32_t bytes = (uint32_t)(left < R ? left : R) * (uint32_t)S;
         uint8_t *dst = wbase + (size_t)s * stage_bytes;
         mbar_arrive_expect_tx(&bars[s], bytes * (HAS_SEQ ? 2u : 1u));
@@ -370,7 +372,7 @@ __global__ void __launch_bounds__(W_THREADS) k_scan_w(const __grid_constant__ Sc
         const uint8_t *qrow = wbase + (size_t)s * stage_bytes + row_off;
         const uint8_t *srow = qrow + slab_bytes;
         const int64_t g = tile * R + rr;
-        const bool active = g < P.n;
+        const bool active = g < N;
         int L = 0;
         if (active) L = P.len ? __ldg(P.len + g) : P.uniform_len;
         const bool lenbad = active && (L <= 0 || L > S);

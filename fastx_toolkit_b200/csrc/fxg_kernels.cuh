@@ -35,6 +35,7 @@ struct ScanParams {
     int32_t uniform_len;
     int32_t stride;
     int64_t n;
+    const int64_t *n_dev; // when not NULL: the number of reads lives on the device (fused pipelines); n is then an upper bound
     int32_t tile_reads;
     int32_t stages;
     int32_t rot_shift;
@@ -111,6 +112,7 @@ struct ClipParams {
     int32_t uniform_len;
     int32_t stride;
     int64_t n;
+    const int64_t *n_dev;     // when not NULL: the number of reads lives on the device (fused pipelines); n is an upper bound
     QualK qk;
     uint8_t adapter[104];
     int32_t alen;
@@ -150,17 +152,18 @@ cudaError_t launch_barcode(const BarcodeParams &p, int sm_count, cudaStream_t st
 
 // ---- fused pipelines (fxg_pipeline.cu) ----
 size_t pipe_scan_tmp_bytes(int64_t n);
-cudaError_t launch_pipe_flags_scan(const int32_t *new_len, const uint8_t *keep, int64_t n, int32_t *flags, int32_t *pos, void *tmp, size_t tmp_bytes,
-                                   int sm_count, cudaStream_t st);
-cudaError_t launch_pipe_gather(const uint8_t *src_seq, const uint8_t *src_qual, int stride, int64_t n, const int32_t *flags, const int32_t *pos,
-                               const int32_t *new_len, const int32_t *cur_len, int uniform_len, const int32_t *cur_idx, uint8_t *dst_seq,
-                               uint8_t *dst_qual, int32_t *dst_len, int32_t *dst_idx, int sm_count, cudaStream_t st);
-cudaError_t launch_stale_rows(const uint8_t *seq, const int32_t *len, int stride, int64_t n, uint8_t *out_seq, int32_t *out_width, void *scratch,
-                              size_t scratch_bytes, size_t *need, int sm_count, cudaStream_t st);   // experimental
+// n = the bound the kernels are launched over; n_dev (device, may be NULL) = the live rows among them
+cudaError_t launch_pipe_flags_scan(const int32_t *new_len, const uint8_t *keep, int64_t n, const int64_t *n_dev, int32_t *flags, int32_t *pos,
+                                   void *tmp, size_t tmp_bytes, int64_t *count_out, int sm_count, cudaStream_t st);
+cudaError_t launch_pipe_gather(const uint8_t *src_seq, const uint8_t *src_qual, int stride, int64_t n, const int64_t *n_dev, const int32_t *flags,
+                               const int32_t *pos, const int32_t *new_len, const int32_t *cur_len, int uniform_len, const int32_t *cur_idx,
+                               uint8_t *dst_seq, uint8_t *dst_qual, int32_t *dst_len, int32_t *dst_idx, int sm_count, cudaStream_t st);
+cudaError_t launch_stale_rows(const uint8_t *seq, const int32_t *len, int stride, int64_t n, const int64_t *n_dev, uint8_t *out_seq,
+                              int32_t *out_width, void *scratch, size_t scratch_bytes, size_t *need, int sm_count, cudaStream_t st);
 cudaError_t launch_pipe_keep_all(int64_t n, const int32_t *cur_len, int uniform_len, const int32_t *cur_idx, int32_t *final_len, int sm_count,
                                  cudaStream_t st);
-cudaError_t launch_pipe_scatter(int64_t n, const int32_t *flags, const int32_t *new_len, const int32_t *cur_len, int uniform_len, const int32_t *cur_idx,
-                                int32_t *final_len, int sm_count, cudaStream_t st);
+cudaError_t launch_pipe_scatter(int64_t n, const int64_t *n_dev, const int32_t *flags, const int32_t *new_len, const int32_t *cur_len, int uniform_len,
+                                const int32_t *cur_idx, int32_t *final_len, int sm_count, cudaStream_t st);
 cudaError_t launch_stats_simple(const StatsParams &p, int sm_count, cudaStream_t st);
 cudaError_t launch_clip(const ClipParams &p, int sm_count, int max_width, cudaStream_t st);
 cudaError_t launch_extra(int op, const uint8_t *seq, const uint8_t *qual, const int32_t *len, int uniform_len, int stride, int64_t n,

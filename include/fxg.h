@@ -304,6 +304,8 @@ typedef struct {
     const fxg_clip_opts *clip;    /* CLIP                                                                   */
     fxg_collapser *collapser;     /* COLLAPSE                                                               */
 } fxg_stage;
+/* The survivor counts between the stages stay on the device: the whole chain is enqueued without a host round trip and
+ * the call reads them back once, at its end (a COLLAPSE stage reads them before it sizes its insert). */
 int fxg_pipeline_dev(fxg_ctx *ctx, const fxg_batch *b, int q_offset, const fxg_stage *stages, int n_stages, int32_t *final_len_dev,
                      int64_t *n_survivors);
 

@@ -13,11 +13,13 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
 
-def oracle_final_len(seq, qual, lens, stages):
+def oracle_final_len(seq, qual, lens, stages, entering=None):
     n = seq.shape[0]
     idx = np.arange(n)
     final = np.full(n, -1, np.int32)
     for st in stages:
+        if entering is not None:
+            entering.append(seq.shape[0])
         new = st(seq, qual, lens)
         keep = np.flatnonzero(new >= 0)
         seq, qual, lens, idx = np.ascontiguousarray(seq[keep]), np.ascontiguousarray(qual[keep]), new[keep].astype(np.int32), idx[keep]
@@ -57,10 +59,14 @@ def test_pipeline_matches_composed_oracle():
         final = torch.full((n,), 12345, dtype=torch.int32, device="cuda")
         ctx.report_reset()
         alive = ctx.pipeline_dev(ctx.batch(ds, dq, n, stride, L if dlens is None else 0, dlens), 33, stages, final)
-        exp = oracle_final_len(s2, q2, lens, ostages)
+        entering = []
+        exp = oracle_final_len(s2, q2, lens, ostages, entering)
         got = final.cpu().numpy()
         assert np.array_equal(got, exp), (len(stages), int((got != exp).sum()))
         assert alive == int((exp >= 0).sum())
+        # the survivor counts stay on the device between the stages (one read-back per call); the report still counts what
+        # each stage really saw, not the bound its kernels were launched over
+        assert ctx.report().n_in == sum(entering), (ctx.report().n_in, entering)
     ctx.close()
 
 
