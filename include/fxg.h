@@ -296,7 +296,8 @@ int fxg_barcode_host(fxg_ctx *ctx, const fxg_batch *fragments, const fxg_barcode
  * (a second call does not see the first call's reads, exactly like a second run of the shell pipe).
  * FXG_STAGE_COLLAPSE must be the last stage: the survivors are added, in input order, to stage.collapser
  * (fxg_collapse_new; finish/fetch it afterwards); several calls may feed one collapser.
- * Blocking (one small device-to-host read per stage); report.first_bad_read refers to the input batch. */
+ * Blocking, with ONE device-to-host read at the end of the call (the survivor counts of all stages; they stay on the device
+ * between the stages); report.first_bad_read refers to the input batch. */
 enum { FXG_STAGE_TRIM = 0, FXG_STAGE_FILTER = 1, FXG_STAGE_CLIP = 2, FXG_STAGE_COLLAPSE = 3 };
 typedef struct {
     int32_t op;                   /* FXG_STAGE_*                                                            */
@@ -304,8 +305,6 @@ typedef struct {
     const fxg_clip_opts *clip;    /* CLIP                                                                   */
     fxg_collapser *collapser;     /* COLLAPSE                                                               */
 } fxg_stage;
-/* The survivor counts between the stages stay on the device: the whole chain is enqueued without a host round trip and
- * the call reads them back once, at its end (a COLLAPSE stage reads them before it sizes its insert). */
 int fxg_pipeline_dev(fxg_ctx *ctx, const fxg_batch *b, int q_offset, const fxg_stage *stages, int n_stages, int32_t *final_len_dev,
                      int64_t *n_survivors);
 
