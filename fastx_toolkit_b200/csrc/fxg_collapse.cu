@@ -162,29 +162,55 @@ __global__ void __launch_bounds__(256) k_rehash(const unsigned long long *slots,
     }
 }
 
-// compact the occupied slots into dense arrays (order irrelevant: everything is sorted afterwards)
+// compact the occupied slots into dense arrays (order irrelevant: everything is sorted afterwards).  There is ONE position
+// counter for the whole table, and atomics on one address are serialised (~2.5 ns each), so a block takes the positions for a
+// tile of 256 x CP_ITEMS slots with a single atomicAdd: ballot + popc inside the warp, the eight warp totals through shared
+// memory.
+constexpr int CP_ITEMS = 8;
 __global__ void __launch_bounds__(256) k_compact(const unsigned long long *slots, const unsigned long long *count,
                                                  const unsigned long long *firsts, const uint64_t *hash, int64_t nslots,
                                                  unsigned long long *n_out, uint32_t *u_rep, uint64_t *u_hash,
                                                  uint64_t *u_first, uint64_t *u_count)
 {
-    // one position counter for the whole table: a warp takes its block of positions with ONE atomic (ballot + popc)
-    const int lane = threadIdx.x & 31;
-    for (int64_t t0 = (int64_t)blockIdx.x * blockDim.x; t0 < nslots; t0 += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t t = t0 + threadIdx.x;
-        const unsigned long long cur = t < nslots ? slots[t] : 0ull;
-        const unsigned occ = __ballot_sync(0xffffffffu, cur != 0ull);
-        if (occ == 0u) continue;
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(n_out, (unsigned long long)__popc(occ));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (cur == 0ull) continue;
-        const unsigned long long pos = base + (unsigned long long)__popc(occ & ((1u << lane) - 1u));
-        const uint32_t rep = (uint32_t)(cur & 0xFFFFFFFFull) - 1u;
-        u_rep[pos] = rep;
-        u_hash[pos] = hash[rep];
-        u_first[pos] = firsts[t];
-        u_count[pos] = count[t];
+    __shared__ unsigned s_warp[8];
+    __shared__ unsigned long long s_base;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t tile = 256 * CP_ITEMS;
+    for (int64_t t0 = (int64_t)blockIdx.x * tile; t0 < nslots; t0 += (int64_t)gridDim.x * tile) {
+        unsigned long long cur[CP_ITEMS];
+        unsigned occ[CP_ITEMS];
+        unsigned wtotal = 0;
+#pragma unroll
+        for (int i = 0; i < CP_ITEMS; i++) {
+            const int64_t t = t0 + i * 256 + threadIdx.x;
+            cur[i] = t < nslots ? slots[t] : 0ull;
+            occ[i] = __ballot_sync(0xffffffffu, cur[i] != 0ull);
+            wtotal += (unsigned)__popc(occ[i]);
+        }
+        if (lane == 0) s_warp[w] = wtotal;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned total = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { const unsigned c = s_warp[k]; s_warp[k] = total; total += c; }
+            s_base = total ? atomicAdd(n_out, (unsigned long long)total) : 0ull;
+        }
+        __syncthreads();
+        unsigned long long pos = s_base + s_warp[w];
+#pragma unroll
+        for (int i = 0; i < CP_ITEMS; i++) {
+            if (cur[i] != 0ull) {
+                const int64_t t = t0 + i * 256 + threadIdx.x;
+                const unsigned long long q = pos + (unsigned long long)__popc(occ[i] & ((1u << lane) - 1u));
+                const uint32_t rep = (uint32_t)(cur[i] & 0xFFFFFFFFull) - 1u;
+                u_rep[q] = rep;
+                u_hash[q] = hash[rep];
+                u_first[q] = firsts[t];
+                u_count[q] = count[t];
+            }
+            pos += (unsigned long long)__popc(occ[i]);
+        }
+        __syncthreads();              // s_warp / s_base are rewritten by the next tile
     }
 }
 
@@ -209,6 +235,34 @@ __global__ void __launch_bounds__(256) k_touch_min(const uint32_t *seq, const ui
 __global__ void __launch_bounds__(256) k_touch_key(const uint32_t *bucket, const uint32_t *touch, uint32_t m, uint32_t *key)
 {
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < m; t += gridDim.x * blockDim.x) key[t] = touch[bucket[t]];
+}
+// The same two steps for bucket tables that do not fit the L2 cache (B * 4 bytes against 126 MB): random atomicMin into
+// DRAM-resident memory runs at a fraction of the L2 rate.  The nodes are first PARTITIONED by the top bits of their bucket
+// number (one stable radix pass over (bucket, position << 32 | node)); the atomics and the read-back then walk the table
+// region by region, a few MB at a time.  Nodes with equal sort keys share a bucket, hence a partition, and the stable pass
+// keeps their positions ascending, so the stable sort by key that follows yields exactly the order of the direct version
+// (tests/test_order_partition_model.py).
+__global__ void __launch_bounds__(256) k_bucket_pos(const uint32_t *seq, const uint64_t *hash, uint64_t B, uint32_t m, uint32_t *bucket,
+                                                    unsigned long long *pos_node)
+{
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < m; t += gridDim.x * blockDim.x) {
+        const uint32_t node = seq[t];
+        bucket[t] = (uint32_t)(hash[node] % B);
+        pos_node[t] = ((unsigned long long)t << 32) | node;
+    }
+}
+__global__ void __launch_bounds__(256) k_touch_min_part(const uint32_t *bucket_p, const unsigned long long *pos_node_p, uint32_t m, uint32_t *touch)
+{
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < m; p += gridDim.x * blockDim.x)
+        atomicMin(&touch[bucket_p[p]], (uint32_t)(pos_node_p[p] >> 32));
+}
+__global__ void __launch_bounds__(256) k_touch_key_part(const uint32_t *bucket_p, const unsigned long long *pos_node_p, const uint32_t *touch,
+                                                        uint32_t m, uint32_t *key, uint32_t *node)
+{
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < m; p += gridDim.x * blockDim.x) {
+        key[p] = touch[bucket_p[p]];
+        node[p] = (uint32_t)pos_node_p[p];
+    }
 }
 __global__ void __launch_bounds__(256) k_reverse(const uint32_t *in, uint32_t *out, uint32_t n)
 {
@@ -260,6 +314,9 @@ static const int kLadderN = (int)(sizeof(kLadder) / sizeof(kLadder[0]));
         }                                                                                          \
     } while (0)
 
+// bucket tables up to this size take the direct atomicMin path (they stay in the 126 MB L2 next to the streams beside them)
+static const uint64_t kTouchDirectBytes = 32ull << 20;
+
 static inline unsigned grid_for(uint64_t n) { uint64_t b = (n + 255) / 256; if (b > 148 * 32) b = 148 * 32; if (b < 1) b = 1; return (unsigned)b; }
 static inline int bits_for(uint64_t max_value) { int b = 1; while (b < 64 && (max_value >> b)) b++; return b; }
 
@@ -303,6 +360,8 @@ int fxg_order_impl(const uint64_t *d_hash, const uint64_t *d_first, const uint64
     cub::DeviceRadixSort::SortPairs(NULL, need, k64_a, k64_b, ids_a, ids_b, (int)U, 0, 64, st); tmp_bytes = need;
     cub::DeviceRadixSort::SortPairsDescending(NULL, need, k64_a, k64_b, ids_a, ids_b, (int)U, 0, 64, st); if (need > tmp_bytes) tmp_bytes = need;
     cub::DeviceRadixSort::SortPairs(NULL, need, key, key_s, ord, ord_s, (int)U, 0, 32, st); if (need > tmp_bytes) tmp_bytes = need;
+    cub::DeviceRadixSort::SortPairs(NULL, need, bucket, key_s, (unsigned long long *)k64_a, (unsigned long long *)k64_b, (int)U, 24, 32, st);
+    if (need > tmp_bytes) tmp_bytes = need;
     CKC(cudaMallocAsync(&tmp, tmp_bytes + 16, st));
 
     // 1. first-occurrence order: ids sorted by `first` ascending  -> ids_b
@@ -325,11 +384,25 @@ int fxg_order_impl(const uint64_t *d_hash, const uint64_t *d_first, const uint64
             if (m2 > m) CKC(cudaMemcpyAsync(ord + m, ids_b + m, (size_t)(m2 - m) * 4, cudaMemcpyDeviceToDevice, st));
             const unsigned g2 = grid_for(m2);
             CKC(cudaMemsetAsync(touch, 0xFF, (size_t)B * 4, st));
-            k_touch_min<<<g2, 256, 0, st>>>(ord, d_hash, B, m2, bucket, touch);
-            k_touch_key<<<g2, 256, 0, st>>>(bucket, touch, m2, key);
-            need = tmp_bytes;
-            CKC(cub::DeviceRadixSort::SortPairs(tmp, need, key, key_s, ord, ord_s, (int)m2, 0, bits_for(m2), st));
-            *launches += 3 + (bits_for(m2) + 7) / 8 + 1;
+            if (B * 4 <= kTouchDirectBytes) {
+                k_touch_min<<<g2, 256, 0, st>>>(ord, d_hash, B, m2, bucket, touch);
+                k_touch_key<<<g2, 256, 0, st>>>(bucket, touch, m2, key);
+                need = tmp_bytes;
+                CKC(cub::DeviceRadixSort::SortPairs(tmp, need, key, key_s, ord, ord_s, (int)m2, 0, bits_for(m2), st));
+                *launches += 3 + (bits_for(m2) + 7) / 8 + 1;
+            } else {
+                // large table: partition by the top 8 bits of the bucket number first (k64_a / k64_b are free between steps 1 and 3)
+                unsigned long long *pn = (unsigned long long *)k64_a, *pn_p = (unsigned long long *)k64_b;
+                const int hb = bits_for(B - 1), lb = hb > 8 ? hb - 8 : 0;
+                k_bucket_pos<<<g2, 256, 0, st>>>(ord, d_hash, B, m2, bucket, pn);
+                need = tmp_bytes;
+                CKC(cub::DeviceRadixSort::SortPairs(tmp, need, bucket, key_s, pn, pn_p, (int)m2, lb, hb, st));
+                k_touch_min_part<<<g2, 256, 0, st>>>(key_s, pn_p, m2, touch);
+                k_touch_key_part<<<g2, 256, 0, st>>>(key_s, pn_p, touch, m2, key, bucket);      // bucket[] now holds the nodes
+                need = tmp_bytes;
+                CKC(cub::DeviceRadixSort::SortPairs(tmp, need, key, key_s, bucket, ord_s, (int)m2, 0, bits_for(m2), st));
+                *launches += 4 + 3 + (bits_for(m2) + 7) / 8 + 1;
+            }
             m = m2;
             if (m < U) { k_reverse<<<g2, 256, 0, st>>>(ord_s, ord, m2); *launches += 1; }
         }
