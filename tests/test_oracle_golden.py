@@ -268,3 +268,84 @@ def test_hash_bytes_known_answers():
     for s in (b"", b"A", b"ACGTACG", b"ACGTACGT", b"ACGTACGTA", b"N" * 50, bytes(range(65, 91)) * 3):
         buf = C.create_string_buffer(s, len(s) + 1)
         assert O.fxo_hash_bytes(buf, len(s), 0xc70f6907) == py_hash(s)
+
+
+def _stale_rows(seq, lens):
+    """the query buffer of the reference's aligner after each read (grow-only, keeps stale bytes: SURVEY Appendix D.1)"""
+    n, stride = seq.shape
+    rows = np.zeros_like(seq)
+    widths = np.zeros(n, np.int32)
+    shadow = np.zeros(stride + 1, np.uint8)
+    wmax = 0
+    for i in range(n):
+        l = int(lens[i])
+        shadow[:l] = seq[i, :l]
+        shadow[l] = 0
+        wmax = max(wmax, l)
+        rows[i, :wmax] = shadow[:wmax]
+        widths[i] = wmax
+    return rows, widths
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", range(12))
+def test_ref_clipper_fuzz(tmp_path, seed):
+    """random adapters (1..25 characters, sometimes with N), reads carrying whole, truncated and mutated copies of them,
+    random flag sets incl. -k / -d / -M, equal-length and mixed-length inputs: oracle vs the reference binary
+    (fastx_clipper.cpp:159-241,280-319; sequence_alignment.cpp:340-650)"""
+    rng = np.random.default_rng(7000 + seed)
+    alpha = np.frombuffer(b"ACGT", np.uint8)
+    alen = int(rng.integers(1, 26))
+    adapter = alpha[rng.integers(0, 4, alen)].copy()
+    if seed % 4 == 3 and alen > 2:
+        adapter[rng.integers(0, alen, max(1, alen // 6))] = ord("N")
+    adapter = adapter.tobytes()
+    n, L = 1500, int(rng.integers(20, 81))
+    stride = (L + 1 + 15) // 16 * 16
+    seq = np.zeros((n, stride), np.uint8)
+    seq[:, :L] = alpha[rng.integers(0, 4, (n, L))]
+    qual = np.zeros((n, stride), np.uint8)
+    qual[:, :L] = 33 + rng.integers(2, 41, (n, L))
+    for i in range(n):
+        r = rng.random()
+        if r < 0.55:                                      # a copy of the adapter, possibly mutated, possibly cut by the read end
+            a = np.frombuffer(adapter, np.uint8).copy()
+            for _ in range(int(rng.integers(0, 3))):
+                k = int(rng.integers(0, len(a)))
+                m = rng.random()
+                if m < 0.5: a[k] = alpha[rng.integers(0, 4)]
+                elif m < 0.75 and len(a) > 1: a = np.delete(a, k)
+                else: a = np.insert(a, k, alpha[rng.integers(0, 4)])
+            st = int(rng.integers(0, L))
+            m = min(len(a), L - st)
+            seq[i, st:st + m] = a[:m]
+        if rng.random() < 0.1:
+            seq[i, rng.integers(0, L, int(rng.integers(1, 4)))] = ord("N")
+    mixed = seed % 2 == 1
+    lens = H.ragged(seq, qual, rng, min_len=6) if mixed else None
+    fq = str(tmp_path / "in.fq")
+    H.write_fastq(fq, seq, qual, lens, L)
+    recs = H.read_fastx(fq)
+    for _ in range(3):
+        kw = dict(min_length=int(rng.integers(0, 30)), keep_delta=0, discard_non_clipped=0, discard_clipped=0, discard_unknown=1, min_adapter_len=0)
+        flags = ["-l", str(kw["min_length"])]
+        if rng.random() < 0.4:
+            d = int(rng.integers(1, 6)); kw["keep_delta"] = d + len(adapter); flags += ["-d", str(d)]
+        c = rng.random()
+        if c < 0.25: kw["discard_non_clipped"] = 1; flags.append("-c")
+        elif c < 0.5: kw["discard_clipped"] = 1; flags.append("-C")
+        if rng.random() < 0.5: kw["discard_unknown"] = 0; flags.append("-n")
+        if rng.random() < 0.4:
+            kw["min_adapter_len"] = int(rng.integers(1, len(adapter) + 3)); flags += ["-M", str(kw["min_adapter_len"])]
+        adapter_only = rng.random() < 0.25
+        if adapter_only: flags.append("-k")
+        if mixed:
+            rows, widths = _stale_rows(seq, lens)
+            out_len, cls, cut = H.o_clip(rows, lens, widths, 0, stride, adapter, H.FxoClipOpts(**kw))
+            full = lens
+        else:
+            out_len, cls, cut = H.o_clip(seq, None, None, L, stride, adapter, H.FxoClipOpts(**kw))
+            full = np.full(n, L, np.int32)
+        r = H.run([H.ref_tool("fastx_clipper"), "-Q33", "-a", adapter.decode(), "-i", fq] + flags)
+        exp_len = np.where(cls == 1, full, -1) if adapter_only else np.where(cls == 0, out_len, -1)
+        assert emit(recs, exp_len, 33) == r.stdout, (seed, adapter, flags)
