@@ -349,3 +349,42 @@ def test_ref_clipper_fuzz(tmp_path, seed):
         r = H.run([H.ref_tool("fastx_clipper"), "-Q33", "-a", adapter.decode(), "-i", fq] + flags)
         exp_len = np.where(cls == 1, full, -1) if adapter_only else np.where(cls == 0, out_len, -1)
         assert emit(recs, exp_len, 33) == r.stdout, (seed, adapter, flags)
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", range(6))
+def test_ref_trim_filter_stats_fuzz(tmp_path, seed):
+    """random -Q (33 / 64), qualities over the whole legal range (q = -15 .. 62, fastx.h:28-29), ragged lengths, random
+    thresholds: trimmer, filter and both quality-stats formats, oracle vs the reference binaries"""
+    rng = np.random.default_rng(9100 + seed)
+    Q = 33 if seed % 2 == 0 else 64
+    n, L = 4000, int(rng.integers(10, 121))
+    stride = (L + 15) // 16 * 16
+    alpha = np.frombuffer(b"ACGTN", np.uint8)
+    seq = np.zeros((n, stride), np.uint8)
+    seq[:, :L] = alpha[rng.choice(5, (n, L), p=[0.24, 0.24, 0.24, 0.24, 0.04])]
+    qual = np.zeros((n, stride), np.uint8)
+    qual[:, :L] = Q + rng.integers(-15, 63, (n, L))
+    qual[:, :L][qual[:, :L] > 126] = 126
+    lens = H.ragged(seq, qual, rng, min_len=1)
+    fq = str(tmp_path / "in.fq")
+    H.write_fastq(fq, seq, qual, lens, L)
+    recs = H.read_fastx(fq)
+    for _ in range(3):
+        t, l = int(rng.integers(1, 46)), int(rng.integers(0, L + 2))
+        out, bad = H.o_trim(seq, qual, lens, 0, stride, Q, t, l)
+        r = H.run([H.ref_tool("fastq_quality_trimmer"), "-Q%d" % Q, "-t", str(t), "-l", str(l), "-i", fq])
+        assert bad == -1 and emit(recs, out, Q) == r.stdout, (seed, t, l)
+        q, p = int(rng.integers(-10, 50)), int(rng.integers(1, 101))
+        keep, bad = H.o_filter(seq, qual, lens, 0, stride, Q, q, p)
+        r = H.run([H.ref_tool("fastq_quality_filter"), "-Q%d" % Q, "-q", str(q), "-p", str(p), "-i", fq])
+        assert emit(recs, np.where(keep != 0, lens, -1), Q) == r.stdout, (seed, q, p)
+    O = H.oracle()
+    for new_format in (0, 1):
+        s = O.fxo_stats_new(L)
+        O.fxo_stats_add_batch(s, _p(seq, u8p), _p(qual, u8p), _p(lens, H.i32p), 0, stride, n, Q)
+        p = str(tmp_path / ("o%d.txt" % new_format))
+        O.fxo_stats_print_path(s, p.encode(), new_format)
+        O.fxo_stats_free(s)
+        r = H.run([H.ref_tool("fastx_quality_stats"), "-Q%d" % Q, "-i", fq] + (["-N"] if new_format else []))
+        assert open(p, "rb").read() == r.stdout, (seed, new_format)
